@@ -1,0 +1,236 @@
+/*
+ * oi_b200.h -- C-ABI of the B200-native (sm_100a) hot path of zzyunzhi/object-intrinsics.
+ *
+ * The reference has NO native interface for the renderer: its hot path is Python/torch
+ * (src/third_party/neus/models/renderer.py:351-473 `NeuSRenderer.render`, :199-349 `render_core`,
+ * :137-181 `up_sample`, :44-74 `sample_pdf`, :183-197 `cat_z_vals`; src/models/fields.py:49-122
+ * ShapeNetwork / ColorNetwork / gradient; src/third_party/stylesdf/volume_renderer.py:27-61
+ * LinearLayer / FiLMSiren).  The entry points below are what a binding for that path binds
+ * (ctypes stub in INTEGRATION.md; the Python drop-in class is object_intrinsics_b200.renderer.NeuSRenderer).
+ * The three StyleGAN2 ops DO have native interfaces in the reference (pybind11); the entry points here
+ * replace them one for one and cite them.
+ *
+ * Conventions: plain pointers + sizes, all pointers are DEVICE pointers unless stated otherwise,
+ * all tensors fp32 contiguous row-major unless stated otherwise.  Every call returns OI_OK (0) or a
+ * negative OiStatus; the message is available through oi_last_error() (thread-local).  Nothing throws,
+ * exits, allocates device memory or synchronises: kernels are launched on the caller's stream
+ * (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream).  Re-entrant; no global
+ * mutable state besides the thread-local error string and per-device cached function attributes.
+ */
+#ifndef OI_B200_H_
+#define OI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OI_ABI_VERSION 1
+
+typedef enum OiStatus {
+  OI_OK = 0,
+  OI_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, bad size, misaligned buffer */
+  OI_ERR_UNSUPPORTED = -2,      /* configuration outside what the kernels implement */
+  OI_ERR_CUDA = -3,             /* a CUDA runtime call failed; message holds cudaGetErrorString */
+  OI_ERR_WORKSPACE = -4         /* workspace too small */
+} OiStatus;
+
+#define OI_MAX_DEPTH 8 /* FiLM-SIREN SDF layers (configs/train.yaml:41 D: 8) */
+#define OI_WIDTH 128   /* hidden width            (configs/train.yaml:42 W: 128) */
+#define OI_STYLE_DIM 64
+
+/* Which MLP core evaluates the FiLM-SIREN contraction. */
+typedef enum OiRenderImpl {
+  OI_IMPL_AUTO = 0,
+  OI_IMPL_FFMA = 1,   /* FP32 FFMA register-tiled contraction (exact fp32 products)          */
+  OI_IMPL_TCGEN05 = 2 /* tcgen05.mma kind::f16 with a 2-term fp16 split (3 MMAs per product) */
+} OiRenderImpl;
+
+/* ------------------------------------------------------------------------------------------------
+ * Raw network parameters, PyTorch layouts ([out, in] row-major), as registered by the reference:
+ *   pts_*      : ShapeNetwork.pts_linears[l]  = FiLMSiren  (stylesdf/volume_renderer.py:33-48)
+ *   sigma_*    : ShapeNetwork.sigma_linear    = LinearLayer(W,1)   (volume_renderer.py:83)
+ *   views_*    : ColorNetwork.views_linears   = FiLMSiren(W+3, W)  (volume_renderer.py:80-81)
+ *   rgb_*      : ColorNetwork.rgb_linear      = LinearLayer(W,3)   (volume_renderer.py:82)
+ *   variance   : SingleVarianceNetwork.variance (neus/models/fields.py:262-268)
+ *   style_*    : ShapeNetwork.style[i]        = MappingLinear(64,64) (src/models/fields.py:14-19)
+ * FiLM index 0..depth-1 = pts_linears, index OI_MAX_DEPTH = views_linears.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OiNetParams {
+  int32_t depth;                            /* D, 1..OI_MAX_DEPTH */
+  int32_t width;                            /* must be OI_WIDTH */
+  int32_t style_dim;                        /* must be OI_STYLE_DIM */
+  int32_t reserved;
+  const float* pts_weight[OI_MAX_DEPTH];    /* [W,3] for l=0, [W,W] otherwise */
+  const float* pts_bias[OI_MAX_DEPTH];      /* [W] */
+  const float* gamma_weight[OI_MAX_DEPTH + 1]; /* [W,style] */
+  const float* gamma_bias[OI_MAX_DEPTH + 1];   /* [W] */
+  const float* beta_weight[OI_MAX_DEPTH + 1];  /* [W,style] */
+  const float* beta_bias[OI_MAX_DEPTH + 1];    /* [W] */
+  const float* sigma_weight;                /* [1,W] */
+  const float* sigma_bias;                  /* [1] */
+  const float* views_weight;                /* [W, W+3] */
+  const float* views_bias;                  /* [W] */
+  const float* rgb_weight;                  /* [3,W] */
+  const float* rgb_bias;                    /* [3] */
+  const float* variance;                    /* [] */
+  const float* style_weight[3];             /* [style,style] (may be NULL if oi_style_mlp is not used) */
+  const float* style_bias[3];               /* [style] */
+} OiNetParams;
+
+/* Size in bytes of the packed weight blob for a network of the given depth. */
+int oi_packed_weights_bytes(int32_t depth, size_t* bytes);
+
+/* Re-lays the parameters into the streaming order / operand formats the render kernels consume
+ * (transposed fp32 panels for the FFMA core, swizzled fp16 hi/lo UMMA panels for the tcgen05 core,
+ * folded constants).  Call again whenever a parameter changes (after an optimiser step).
+ * `blob` must be 128-byte aligned and at least oi_packed_weights_bytes(depth) long. */
+int oi_pack_weights(const OiNetParams* params, void* blob, size_t blob_bytes, void* stream);
+
+/* ShapeNetwork.style: w = f(f(f(z))), f(x) = leaky_relu(x W^T + b, 0.2) * 1
+ * (src/models/fields.py:14-19; stylesdf/model.py:49-56).  z, w: [n_instances, 64]. */
+int oi_style_mlp(const OiNetParams* params, const float* z, float* w, int32_t n_instances, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NeuSRenderer.render (renderer.py:351-473) for the live configuration of the reference
+ * (nerf=None, n_outside=0, siren_network=None, second_order=None, compute_color=True,
+ * compute_sample_dist=False, blend_background=False, background_rgb=None).
+ * R = n_rays, n = n_samples, m = n_importance, S = n + m.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OiRenderDesc {
+  /* sizes */
+  int32_t n_rays;            /* R; rays of instance b occupy [b*rays_per_instance, (b+1)*rays_per_instance) */
+  int32_t rays_per_instance; /* R / n_instances (src/models/fields.py:55) */
+  int32_t n_samples;         /* n >= 2 */
+  int32_t n_importance;      /* m >= 0 */
+  int32_t up_sample_steps;   /* only 1 is implemented (configs/train.yaml:76) */
+  int32_t depth;             /* D of the packed network */
+  int32_t impl;              /* OiRenderImpl */
+  int32_t flags;             /* reserved, 0 */
+  float cos_anneal_ratio;    /* renderer.py:273-274 */
+  float reserved_f;
+
+  /* inputs */
+  const float* rays_o;       /* [R,3] */
+  const float* rays_d;       /* [R,3] */
+  const float* near;         /* [R,1] */
+  const float* far;          /* [R,1] */
+  const float* t_rand;       /* [R,1] = U[0,1)-0.5 per ray (renderer.py:371-373) or NULL for no jitter */
+  const float* lin_coarse;   /* [n]  = linspace(0,1,n) in fp32 (renderer.py:359); NULL = computed in-kernel */
+  const float* lin_fine;     /* [m]  = linspace(.5/m, 1-.5/m, m) (renderer.py:53); NULL = computed in-kernel */
+  const float* z_vals_in;    /* optional [R,S]: skip sampling, render these z (matched-z parity tests) or NULL */
+  const float* style_w;      /* [n_instances, 64] latent w (generator.py:237-238) */
+  const void* packed_weights;/* blob written by oi_pack_weights */
+
+  /* outputs (renderer.py:448-468); any pointer may be NULL to skip that tensor except `weights`
+   * (it carries alpha between the two phases) */
+  float* s_val;          /* [R,1] */
+  float* cdf_fine;       /* [R,S] */
+  float* weight_sum;     /* [R,1] */
+  float* weight_max;     /* [R,1] */
+  float* gradients;      /* [R,S,3] */
+  float* weights;        /* [R,S] */
+  float* gradient_error; /* [] */
+  float* inside_sphere;  /* [R,S] */
+  float* mid_z_vals;     /* [R,S] */
+  float* surface_loss;   /* [] */
+  float* sdf;            /* [R,S] */
+  float* pts_norm;       /* [R,S] */
+  float* pts;            /* [R,S,3] */
+  float* color_fine;     /* [R,3] */
+  float* raw_color;      /* [R,S,3] */
+  float* z_vals_out;     /* optional [R,S]: the (sorted) section start z-values actually rendered */
+
+  void* workspace;       /* >= oi_render_workspace_bytes(desc), 256-byte aligned */
+  size_t workspace_bytes;
+
+  /* optional cudaEvent_t handles recorded on `stream` immediately before / after the launch of the fused
+   * render_core kernel (the dominant kernel), so that callers can time it in isolation; NULL = off */
+  void* evt_core_start;
+  void* evt_core_stop;
+} OiRenderDesc;
+
+int oi_render_workspace_bytes(const OiRenderDesc* desc, size_t* bytes);
+int oi_render_forward(const OiRenderDesc* desc, void* stream);
+
+/* Number of kernel launches one oi_render_forward(desc) performs (for bench bookkeeping). */
+int oi_render_launch_count(const OiRenderDesc* desc, int32_t* launches);
+
+/* ------------------------------------------------------------------------------------------------
+ * StyleGAN2 ops.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces `_plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)`
+ * (src/third_party/ada/torch_utils/ops/upfirdn2d.cpp:16-94; kernels upfirdn2d.cu:29-341) and, with
+ * NHWC-style strides, `upfirdn2d_op.upfirdn2d(input[N,H,W,1], kernel, ...)`
+ * (src/third_party/stylesdf/op/upfirdn2d.cpp:12-22; upfirdn2d_kernel.cu:49-369).
+ * dtype: 0 = fp32, 1 = fp16, 2 = fp64 (x and y; the filter is always fp32; accumulation fp32, fp64 for fp64).
+ * Strides are in elements.  Output size must be
+ *   out_w = (in_w*up_x + pad_x0 + pad_x1 - filter_w + down_x) / down_x   (upfirdn2d.cpp:33-34). */
+typedef struct OiUpfirdnDesc {
+  const void* x;
+  const float* f;      /* [filter_h, filter_w] with strides f_stride_{h,w} */
+  void* y;
+  int32_t dtype;
+  int32_t batch, channels, in_h, in_w;
+  int64_t x_stride_n, x_stride_c, x_stride_h, x_stride_w;
+  int32_t out_h, out_w;
+  int64_t y_stride_n, y_stride_c, y_stride_h, y_stride_w;
+  int32_t filter_h, filter_w;
+  int64_t f_stride_h, f_stride_w;
+  int32_t up_x, up_y, down_x, down_y;
+  int32_t pad_x0, pad_x1, pad_y0, pad_y1;
+  int32_t flip;        /* 0: convolution (filter flipped), 1: correlation */
+  float gain;
+} OiUpfirdnDesc;
+int oi_upfirdn2d(const OiUpfirdnDesc* desc, void* stream);
+
+/* Replaces `_plugin.bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)`
+ * (src/third_party/ada/torch_utils/ops/bias_act.cpp:32-90; kernel bias_act.cu:23-147).
+ * act: 1 linear, 2 relu, 3 lrelu, 4 tanh, 5 sigmoid, 6 elu, 7 selu, 8 softplus, 9 swish.
+ * grad: 0 forward, 1 first-order, 2 second-order.  b/xref/yref/dy may be NULL.
+ * Elementwise over `size_x` dense elements; bias index = (i / step_b) % size_b. */
+typedef struct OiBiasActDesc {
+  const void* x;
+  const void* b;
+  const void* xref;
+  const void* yref;
+  const void* dy;
+  void* y;
+  int32_t dtype;       /* 0 = fp32, 1 = fp16, 2 = fp64 */
+  int32_t grad;
+  int32_t act;
+  int32_t reserved;
+  float alpha, gain, clamp; /* clamp < 0 disables */
+  int32_t size_x, size_b, step_b;
+} OiBiasActDesc;
+int oi_bias_act(const OiBiasActDesc* desc, void* stream);
+
+/* Replaces `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)`
+ * (src/third_party/stylesdf/op/fused_bias_act.cpp:11-20; kernel fused_bias_act_kernel.cu:19-98).
+ * act*10+grad: 10/11 linear, 12 -> 0, 30 lrelu fwd, 31 lrelu grad (sign taken from `ref`), 32 -> 0.
+ * bias/ref may be NULL.  bias index = (i / step_b) % size_b. */
+typedef struct OiFusedBiasActDesc {
+  const void* x;
+  const void* bias;
+  const void* ref;
+  void* y;
+  int32_t dtype;       /* 0 = fp32, 1 = fp16, 2 = fp64 */
+  int32_t act, grad;
+  int32_t size_x, size_b, step_b;
+  float alpha, scale;
+} OiFusedBiasActDesc;
+int oi_fused_bias_act(const OiFusedBiasActDesc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+const char* oi_last_error(void);
+int oi_abi_version(void);
+/* Compile-time facts about the library: "sm_100a;ffma;tcgen05" */
+const char* oi_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OI_B200_H_ */

@@ -1,0 +1,72 @@
+"""Builds liboi_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m object_intrinsics_b200.build [--force]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "liboi_b200.so")
+SOURCES = ["oi_api.cu", "oi_render_ffma.cu", "oi_render_tc.cu", "oi_render_aux.cu", "oi_ops.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+# NOTE: --use_fast_math is deliberately NOT wanted for the render path (expf/div accuracy); see below.
+NVCC_FLAGS.remove("--use_fast_math")
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _stamp():
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "oi_b200.h")]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIB_DIR, exist_ok=True)
+    stamp_file = os.path.join(LIB_DIR, "liboi_b200.stamp")
+    stamp = _stamp()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB_PATH
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {src}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{out}")
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.run(cmd, check=True)
+    with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    if verbose:
+        print("\n".join(log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,287 @@
+// extern "C" entry points of liboi_b200.so (declared in include/oi_b200.h): validation, workspace carving,
+// launch sequencing.  No allocation, no synchronisation, no exceptions.
+#include <stdarg.h>
+#include <string.h>
+
+#include "oi_internal.cuh"
+
+namespace oi {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  size_t film, scratch, partials, ticket, sdf_coarse, z_fine, tmp_raw_color, tmp_gradients, tmp_pts_norm, tmp_sdf;
+  size_t total;
+  int n_ctas;
+  size_t scratch_stride;
+};
+
+int resolve_impl(const OiRenderDesc* d) {
+  int impl = d->impl;
+  if (impl == OI_IMPL_AUTO) impl = OI_IMPL_FFMA;
+  return impl;
+}
+
+int plan_workspace(const OiRenderDesc* d, Workspace* w) {
+  const int R = d->n_rays, S = d->n_samples + d->n_importance;
+  const int n_inst = R / d->rays_per_instance;
+  const long long pts_per_inst = (long long)d->rays_per_instance * S;
+  const int tiles_per_inst = (int)((pts_per_inst + 127) / 128);
+  const int n_tiles = tiles_per_inst * n_inst;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  w->film = take((size_t)n_inst * kFilm * 2 * kW * 4);
+  int n_ctas = 0;
+  size_t stride = (resolve_impl(d) == OI_IMPL_TCGEN05) ? render_tc_scratch_floats(d->depth, &n_ctas, n_tiles)
+                                                      : render_ffma_scratch_floats(d->depth, &n_ctas, n_tiles);
+  w->n_ctas = n_ctas;
+  w->scratch_stride = stride;
+  w->scratch = take((size_t)n_ctas * stride * 4);
+  w->partials = take((size_t)R * 3 * 4);
+  w->ticket = take(256);
+  const bool hier = d->n_importance > 0 && d->z_vals_in == nullptr;
+  w->sdf_coarse = hier ? take((size_t)R * d->n_samples * 4) : 0;
+  w->z_fine = hier ? take((size_t)R * S * 4) : 0;
+  w->tmp_raw_color = d->raw_color ? 0 : take((size_t)R * S * 3 * 4);
+  w->tmp_gradients = d->gradients ? 0 : take((size_t)R * S * 3 * 4);
+  w->tmp_pts_norm = d->pts_norm ? 0 : take((size_t)R * S * 4);
+  w->tmp_sdf = d->sdf ? 0 : take((size_t)R * S * 4);
+  w->total = off;
+  return OI_OK;
+}
+
+int validate_render(const OiRenderDesc* d) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->n_rays > 0, "n_rays must be positive (got %d)", d->n_rays);
+  OI_CHECK_ARG(d->rays_per_instance > 0 && d->n_rays % d->rays_per_instance == 0,
+               "n_rays (%d) must be a multiple of rays_per_instance (%d)", d->n_rays, d->rays_per_instance);
+  OI_CHECK_ARG(d->n_samples >= 2, "n_samples must be >= 2 (got %d)", d->n_samples);
+  OI_CHECK_ARG(d->n_importance >= 0, "n_importance must be >= 0");
+  OI_CHECK_ARG(d->depth >= 1 && d->depth <= OI_MAX_DEPTH, "depth must be in [1, %d] (got %d)", OI_MAX_DEPTH, d->depth);
+  if (d->n_importance > 0 && d->up_sample_steps != 1)
+    return set_error(OI_ERR_UNSUPPORTED, "up_sample_steps=%d: only 1 is implemented", d->up_sample_steps);
+  if ((long long)d->n_rays * (d->n_samples + d->n_importance) >= (1ll << 30))
+    return set_error(OI_ERR_UNSUPPORTED, "n_rays * samples too large for 32-bit point indices");
+  OI_CHECK_ARG(d->impl >= OI_IMPL_AUTO && d->impl <= OI_IMPL_TCGEN05, "bad impl %d", d->impl);
+  OI_CHECK_ARG(d->rays_o && d->rays_d && d->near && d->far, "rays_o/rays_d/near/far must be non-NULL");
+  OI_CHECK_ARG(d->style_w && d->packed_weights, "style_w and packed_weights must be non-NULL");
+  OI_CHECK_ARG(((uintptr_t)d->packed_weights & 127) == 0, "packed_weights must be 128-byte aligned");
+  OI_CHECK_ARG(d->weights != nullptr, "the `weights` output is mandatory");
+  return OI_OK;
+}
+
+}  // namespace
+}  // namespace oi
+
+using namespace oi;
+
+extern "C" {
+
+const char* oi_last_error(void) { return g_err; }
+int oi_abi_version(void) { return OI_ABI_VERSION; }
+const char* oi_build_info(void) { return "sm_100a;ffma;tcgen05;nvcc " __VERSION__; }
+
+int oi_packed_weights_bytes(int32_t depth, size_t* bytes) {
+  OI_CHECK_ARG(bytes != nullptr, "bytes is NULL");
+  OI_CHECK_ARG(depth >= 1 && depth <= OI_MAX_DEPTH, "depth must be in [1, %d]", OI_MAX_DEPTH);
+  *bytes = blob_layout(depth).total_floats * sizeof(float);
+  return OI_OK;
+}
+
+static int check_params(const OiNetParams* p, bool need_style) {
+  OI_CHECK_ARG(p != nullptr, "params is NULL");
+  OI_CHECK_ARG(p->depth >= 1 && p->depth <= OI_MAX_DEPTH, "depth must be in [1, %d] (got %d)", OI_MAX_DEPTH, p->depth);
+  if (p->width != OI_WIDTH || p->style_dim != OI_STYLE_DIM)
+    return set_error(OI_ERR_UNSUPPORTED, "only W=%d, style_dim=%d are implemented (got %d, %d)", OI_WIDTH,
+                     OI_STYLE_DIM, p->width, p->style_dim);
+  if (need_style) {
+    for (int i = 0; i < 3; ++i) OI_CHECK_ARG(p->style_weight[i] && p->style_bias[i], "style layer %d is NULL", i);
+    return OI_OK;
+  }
+  for (int l = 0; l < p->depth; ++l)
+    OI_CHECK_ARG(p->pts_weight[l] && p->pts_bias[l] && p->gamma_weight[l] && p->gamma_bias[l] && p->beta_weight[l] &&
+                     p->beta_bias[l],
+                 "pts_linears[%d] has a NULL tensor", l);
+  OI_CHECK_ARG(p->gamma_weight[OI_MAX_DEPTH] && p->gamma_bias[OI_MAX_DEPTH] && p->beta_weight[OI_MAX_DEPTH] &&
+                   p->beta_bias[OI_MAX_DEPTH],
+               "views_linears FiLM tensors (index %d) are NULL", OI_MAX_DEPTH);
+  OI_CHECK_ARG(p->sigma_weight && p->sigma_bias && p->views_weight && p->views_bias && p->rgb_weight && p->rgb_bias &&
+                   p->variance,
+               "a head tensor is NULL");
+  return OI_OK;
+}
+
+int oi_pack_weights(const OiNetParams* params, void* blob, size_t blob_bytes, void* stream) {
+  int rc = check_params(params, false);
+  if (rc) return rc;
+  OI_CHECK_ARG(blob != nullptr && ((uintptr_t)blob & 127) == 0, "blob must be non-NULL and 128-byte aligned");
+  size_t need = blob_layout(params->depth).total_floats * sizeof(float);
+  if (blob_bytes < need) return set_error(OI_ERR_WORKSPACE, "blob too small: %zu < %zu", blob_bytes, need);
+  return launch_pack_weights(params, static_cast<float*>(blob), static_cast<cudaStream_t>(stream));
+}
+
+int oi_style_mlp(const OiNetParams* params, const float* z, float* w, int32_t n_instances, void* stream) {
+  int rc = check_params(params, true);
+  if (rc) return rc;
+  OI_CHECK_ARG(z && w && n_instances > 0, "z/w NULL or n_instances <= 0");
+  return launch_style_mlp(params, z, w, n_instances, static_cast<cudaStream_t>(stream));
+}
+
+int oi_render_workspace_bytes(const OiRenderDesc* desc, size_t* bytes) {
+  int rc = validate_render(desc);
+  if (rc) return rc;
+  OI_CHECK_ARG(bytes != nullptr, "bytes is NULL");
+  Workspace w;
+  plan_workspace(desc, &w);
+  *bytes = w.total;
+  return OI_OK;
+}
+
+int oi_render_launch_count(const OiRenderDesc* desc, int32_t* launches) {
+  int rc = validate_render(desc);
+  if (rc) return rc;
+  OI_CHECK_ARG(launches != nullptr, "launches is NULL");
+  const bool hier = desc->n_importance > 0 && desc->z_vals_in == nullptr;
+  *launches = 3 + (hier ? 2 : 0);  // film, [coarse, upsample], fine, composite
+  return OI_OK;
+}
+
+int oi_render_forward(const OiRenderDesc* d, void* stream) {
+  int rc = validate_render(d);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace w;
+  plan_workspace(d, &w);
+  OI_CHECK_ARG(d->workspace != nullptr && ((uintptr_t)d->workspace & 255) == 0,
+               "workspace must be non-NULL and 256-byte aligned");
+  if (d->workspace_bytes < w.total)
+    return set_error(OI_ERR_WORKSPACE, "workspace too small: %zu < %zu", d->workspace_bytes, w.total);
+  char* ws = static_cast<char*>(d->workspace);
+  const float* blob = static_cast<const float*>(d->packed_weights);
+  const int impl = resolve_impl(d);
+
+  const int R = d->n_rays, n = d->n_samples, m = d->n_importance, S = n + m;
+  const int n_inst = R / d->rays_per_instance;
+  float* film = reinterpret_cast<float*>(ws + w.film);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + w.ticket);
+  rc = launch_film(blob, d->depth, d->style_w, film, n_inst, ticket, st);
+  if (rc) return rc;
+
+  RenderKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R;
+  a.rays_per_inst = d->rays_per_instance;
+  a.n_inst = n_inst;
+  a.n_coarse = n;
+  a.D = d->depth;
+  a.cos_anneal = d->cos_anneal_ratio;
+  a.sample_dist = 2.0f / (float)n;  // renderer.py:356
+  a.rays_o = d->rays_o;
+  a.rays_d = d->rays_d;
+  a.near = d->near;
+  a.far = d->far;
+  a.t_rand = d->t_rand;
+  a.lin = d->lin_coarse;
+  a.blob = blob;
+  a.film = film;
+  a.scratch = reinterpret_cast<float*>(ws + w.scratch);
+  a.scratch_stride = w.scratch_stride;
+
+  const float* z_vals = d->z_vals_in;
+  const bool hier = m > 0 && z_vals == nullptr;
+  if (hier) {
+    // coarse SDF pass at the n stratified z (renderer.py:389-399)
+    RenderKArgs c = a;
+    c.coarse = 1;
+    c.S = n;
+    c.pts_per_inst = d->rays_per_instance * n;
+    c.tiles_per_inst = (c.pts_per_inst + 127) / 128;
+    c.n_tiles = c.tiles_per_inst * n_inst;
+    c.sdf_coarse = reinterpret_cast<float*>(ws + w.sdf_coarse);
+    rc = (impl == OI_IMPL_TCGEN05) ? launch_render_tc(c, st) : launch_render_ffma(c, st);
+    if (rc) return rc;
+    float* z_fine = reinterpret_cast<float*>(ws + w.z_fine);
+    rc = launch_upsample(R, n, m, d->rays_o, d->rays_d, d->near, d->far, d->t_rand, d->lin_coarse, d->lin_fine,
+                         c.sdf_coarse, z_fine, st);
+    if (rc) return rc;
+    z_vals = z_fine;
+  }
+
+  a.coarse = 0;
+  a.S = S;
+  a.pts_per_inst = d->rays_per_instance * S;
+  a.tiles_per_inst = (a.pts_per_inst + 127) / 128;
+  a.n_tiles = a.tiles_per_inst * n_inst;
+  a.z_vals = z_vals;
+  if (z_vals == nullptr && m > 0) return set_error(OI_ERR_INVALID_ARGUMENT, "internal: missing fine z values");
+  a.cdf_fine = d->cdf_fine;
+  a.gradients = d->gradients ? d->gradients : reinterpret_cast<float*>(ws + w.tmp_gradients);
+  a.alpha = d->weights;
+  a.inside_sphere = d->inside_sphere;
+  a.mid_z = d->mid_z_vals;
+  a.sdf = d->sdf ? d->sdf : reinterpret_cast<float*>(ws + w.tmp_sdf);
+  a.pts_norm = d->pts_norm ? d->pts_norm : reinterpret_cast<float*>(ws + w.tmp_pts_norm);
+  a.pts = d->pts;
+  a.raw_color = d->raw_color ? d->raw_color : reinterpret_cast<float*>(ws + w.tmp_raw_color);
+  a.z_out = d->z_vals_out;
+  if (d->evt_core_start) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d->evt_core_start), st));
+  rc = (impl == OI_IMPL_TCGEN05) ? launch_render_tc(a, st) : launch_render_ffma(a, st);
+  if (rc) return rc;
+  if (d->evt_core_stop) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d->evt_core_stop), st));
+
+  return launch_composite(R, S, blob, d->depth, d->weights, a.raw_color, a.gradients, a.pts_norm, a.sdf,
+                          d->weight_sum, d->weight_max, d->color_fine, d->s_val, d->gradient_error, d->surface_loss,
+                          reinterpret_cast<float*>(ws + w.partials), ticket, st);
+}
+
+int oi_upfirdn2d(const OiUpfirdnDesc* d, void* stream) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->x && d->f && d->y, "x, f, y must be non-NULL");
+  OI_CHECK_ARG(d->batch > 0 && d->channels > 0 && d->in_h > 0 && d->in_w > 0, "empty input");
+  OI_CHECK_ARG(d->filter_h >= 1 && d->filter_w >= 1, "f must be at least 1x1");
+  OI_CHECK_ARG(d->up_x >= 1 && d->up_y >= 1, "upsampling factor must be at least 1");
+  OI_CHECK_ARG(d->down_x >= 1 && d->down_y >= 1, "downsampling factor must be at least 1");
+  const int ow = (d->in_w * d->up_x + d->pad_x0 + d->pad_x1 - d->filter_w + d->down_x) / d->down_x;
+  const int oh = (d->in_h * d->up_y + d->pad_y0 + d->pad_y1 - d->filter_h + d->down_y) / d->down_y;
+  OI_CHECK_ARG(ow >= 1 && oh >= 1, "output must be at least 1x1");
+  OI_CHECK_ARG(ow == d->out_w && oh == d->out_h, "out size mismatch: expected %dx%d, got %dx%d", oh, ow, d->out_h,
+               d->out_w);
+  return launch_upfirdn2d(*d, static_cast<cudaStream_t>(stream));
+}
+
+int oi_bias_act(const OiBiasActDesc* d, void* stream) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->x && d->y, "x and y must be non-NULL");
+  OI_CHECK_ARG(d->size_x >= 0, "size_x must be non-negative");
+  OI_CHECK_ARG(d->grad >= 0 && d->grad <= 2, "grad must be 0, 1 or 2");
+  OI_CHECK_ARG(d->b == nullptr || (d->size_b > 0 && d->step_b > 0), "bias given but size_b/step_b invalid");
+  if (d->size_x == 0) return OI_OK;
+  return launch_bias_act(*d, static_cast<cudaStream_t>(stream));
+}
+
+int oi_fused_bias_act(const OiFusedBiasActDesc* d, void* stream) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->x && d->y, "x and y must be non-NULL");
+  OI_CHECK_ARG(d->size_x >= 0, "size_x must be non-negative");
+  OI_CHECK_ARG(d->bias == nullptr || (d->size_b > 0 && d->step_b > 0), "bias given but size_b/step_b invalid");
+  if (d->size_x == 0) return OI_OK;
+  return launch_fused_bias_act(*d, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
