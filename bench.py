@@ -191,6 +191,8 @@ def main():
     d_ro, d_rd, d_near, d_far, d_z = [t.to(dev) for t in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ev_core = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for e in ev_core:
+        e.record()   # torch creates the cudaEvent_t lazily; the C-ABI needs the handle
 
     def step_resident():
         with torch.no_grad():

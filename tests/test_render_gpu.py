@@ -109,7 +109,7 @@ def test_headline_config_full_size_properties_and_oracle(impl):
     assert linf(ro[:, None, :] + rd[:, None, :] * out["mid_z_vals"][..., None], out["pts"]) < 2e-6
     assert linf(out["pts"].norm(dim=-1), out["pts_norm"]) < 2e-6
     assert ((out["pts_norm"] < 1.0).float() - out["inside_sphere"]).abs().sum() <= 2
-    assert 0.5 < float(out["weight_sum"].mean()) < 0.95      # most rays hit the sphere-initialised SDF
+    assert 0.1 < float(out["weight_sum"].mean()) < 0.95      # the r=0.5 sphere covers ~20% of the +-5 deg patch
     ref = O.render(P, ro, rd, near, far, w=w, n_samples=64, n_importance=0, cos_anneal_ratio=1.0)
     for k in OUT_KEYS:
         tol = 3e-4 if k == "gradients" else 1e-4
