@@ -118,7 +118,7 @@ def render_differentiable(renderer, rays_o, rays_d, near, far, w, cos_anneal_rat
     next_cdf = torch.sigmoid((sdf + iter_cos * dists * 0.5) * inv_s)
     alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0)
     pts_norm = pts.norm(dim=-1)
-    relax = (pts_norm < 1.2).float().detach()
+    relax = (pts_norm < 1.2).to(pts.dtype).detach()
     weights = alpha * _excl_cumprod(1.0 - alpha + 1e-7)
     weight_sum = weights.sum(-1, keepdim=True)
     ge = (normal.norm(dim=-1) - 1.0) ** 2
@@ -130,7 +130,7 @@ def render_differentiable(renderer, rays_o, rays_d, near, far, w, cos_anneal_rat
         "gradients": normal,
         "weights": weights,
         "gradient_error": (relax * ge).sum() / (relax.sum() + 1e-5),
-        "inside_sphere": (pts_norm < 1.0).float().detach(),
+        "inside_sphere": (pts_norm < 1.0).to(pts.dtype).detach(),
         "mid_z_vals": mid_z,
         "surface_loss": torch.exp(-1e2 * sdf.abs()).mean(),
         "sdf": sdf,
