@@ -224,6 +224,12 @@ typedef struct OiFusedBiasActDesc {
 } OiFusedBiasActDesc;
 int oi_fused_bias_act(const OiFusedBiasActDesc* desc, void* stream);
 
+/* Self-test of the tcgen05 building blocks: d[128,128] = a[128,128] * B^T through the split-fp16 UMMA path.
+ * B = b[128,128] ([n][k] row-major) when packed_weights is NULL, else panel `panel` of the packed blob
+ * (order: forward l=1..D-1, colour features, reverse l=D-1..1; each is 2^8 * W in [n][k] orientation). */
+int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,
+                   float* d, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ */
 const char* oi_last_error(void);
 int oi_abi_version(void);

@@ -82,7 +82,7 @@ class OiFusedBiasActDesc(C.Structure):
 
 EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_render_workspace_bytes",
            "oi_render_forward", "oi_render_launch_count", "oi_upfirdn2d", "oi_bias_act", "oi_fused_bias_act",
-           "oi_last_error", "oi_abi_version", "oi_build_info"]
+           "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc"]
 
 _lib = None
 
@@ -109,6 +109,7 @@ def lib():
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]
     L.oi_bias_act.argtypes = [C.POINTER(OiBiasActDesc), C.c_void_p]
     L.oi_fused_bias_act.argtypes = [C.POINTER(OiFusedBiasActDesc), C.c_void_p]
+    L.oi_selftest_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     if L.oi_abi_version() != 1:
         raise RuntimeError(f"liboi_b200.so ABI version {L.oi_abi_version()} != 1")
     _lib = L

@@ -46,7 +46,7 @@ int plan_workspace(const OiRenderDesc* d, Workspace* w) {
     off = align_up(off + bytes, 256);
     return o;
   };
-  w->film = take((size_t)n_inst * kFilm * 2 * kW * 4);
+  w->film = take((size_t)n_inst * kFilm * 4 * kW * 4);  // (gamma, beta) table + (gamma', delta) table
   int n_ctas = 0;
   size_t stride = (resolve_impl(d) == OI_IMPL_TCGEN05) ? render_tc_scratch_floats(d->depth, &n_ctas, n_tiles)
                                                       : render_ffma_scratch_floats(d->depth, &n_ctas, n_tiles);
@@ -95,7 +95,7 @@ extern "C" {
 
 const char* oi_last_error(void) { return g_err; }
 int oi_abi_version(void) { return OI_ABI_VERSION; }
-const char* oi_build_info(void) { return "sm_100a;ffma;tcgen05;nvcc " __VERSION__; }
+const char* oi_build_info(void) { return "sm_100a;ffma;tcgen05"; }
 
 int oi_packed_weights_bytes(int32_t depth, size_t* bytes) {
   OI_CHECK_ARG(bytes != nullptr, "bytes is NULL");
@@ -200,6 +200,7 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   a.lin = d->lin_coarse;
   a.blob = blob;
   a.film = film;
+  a.film_tc = film + (size_t)n_inst * kFilm * 2 * kW;
   a.scratch = reinterpret_cast<float*>(ws + w.scratch);
   a.scratch_stride = w.scratch_stride;
 
@@ -248,6 +249,19 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   return launch_composite(R, S, blob, d->depth, d->weights, a.raw_color, a.gradients, a.pts_norm, a.sdf,
                           d->weight_sum, d->weight_max, d->color_fine, d->s_val, d->gradient_error, d->surface_loss,
                           reinterpret_cast<float*>(ws + w.partials), ticket, st);
+}
+
+int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,
+                   float* d, void* stream) {
+  OI_CHECK_ARG(a && d, "a and d must be non-NULL");
+  const void* img = nullptr;
+  if (packed_weights) {
+    OI_CHECK_ARG(depth >= 2 && depth <= OI_MAX_DEPTH && panel >= 0 && panel < 2 * (depth - 1) + 1, "bad depth/panel");
+    img = static_cast<const char*>(packed_weights) + blob_layout(depth).tc_off * sizeof(float) + (size_t)panel * 65536;
+  } else {
+    OI_CHECK_ARG(b != nullptr, "b must be non-NULL when no packed panel is given");
+  }
+  return launch_tc_selftest(a, b, img, d, static_cast<cudaStream_t>(stream));
 }
 
 int oi_upfirdn2d(const OiUpfirdnDesc* d, void* stream) {

@@ -104,6 +104,7 @@ struct RenderKArgs {
   const float* z_vals;  // [R,S] section starts or NULL (computed from near/far/lin/t_rand)
   const float* blob;
   const float* film;    // [n_inst][9][2][128] gamma, beta
+  const float* film_tc; // [n_inst][9][128] float2 (gamma', delta) for the tcgen05 core
   float* scratch;       // per-CTA slabs
   size_t scratch_stride;  // floats per CTA
   float *cdf_fine, *gradients, *alpha, *inside_sphere, *mid_z, *sdf, *pts_norm, *pts, *raw_color;
@@ -121,6 +122,7 @@ int launch_bias_act(const OiBiasActDesc& d, cudaStream_t s);
 int launch_fused_bias_act(const OiFusedBiasActDesc& d, cudaStream_t s);
 int launch_render_ffma(const RenderKArgs& a, cudaStream_t st);
 int launch_render_tc(const RenderKArgs& a, cudaStream_t st);
+int launch_tc_selftest(const float* A, const float* B, const void* panel, float* D, cudaStream_t st);
 size_t render_ffma_scratch_floats(int depth, int* n_ctas, int n_tiles);
 size_t render_tc_scratch_floats(int depth, int* n_ctas, int n_tiles);
 int launch_upsample(int R, int n, int m, const float* rays_o, const float* rays_d, const float* near,

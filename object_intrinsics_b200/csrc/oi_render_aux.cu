@@ -180,8 +180,14 @@ __global__ void film_kernel(const float* __restrict__ blob, int depth, const flo
   sg += fl[BlobLayout::kGammaB + l * kW + n];
   sb += fl[BlobLayout::kBetaB + l * kW + n];
   float* out = film + ((size_t)inst * kFilm + l) * 2 * kW;
-  out[n] = 15.0f * sg + 30.0f;
-  out[kW + n] = 0.25f * sb;
+  const float gamma = 15.0f * sg + 30.0f, beta = 0.25f * sb;
+  out[n] = gamma;
+  out[kW + n] = beta;
+  // second table for the tcgen05 core: (gamma', delta) with arg = gamma' * acc + delta, where acc is the
+  // accumulator of the 2^8-scaled weight panels (layer 0 runs on the FMA pipe, unscaled)
+  float2* tc_tab = reinterpret_cast<float2*>(film + (size_t)gridDim.y * kFilm * 2 * kW);
+  const float bias = blob[L.const_off + BlobLayout::kBias + l * kW + n];
+  tc_tab[((size_t)inst * kFilm + l) * kW + n] = make_float2(l == 0 ? gamma : gamma * (1.0f / 256.0f), fmaf(gamma, bias, beta));
 }
 
 // ---------------------------------------------------------------------------------------------------

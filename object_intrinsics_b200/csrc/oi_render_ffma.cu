@@ -16,6 +16,7 @@
 // The same kernel runs the coarse pass of hierarchical sampling (SDF only, points at z instead of
 // section midpoints, renderer.py:389-399) with args.coarse = 1.
 #include "oi_internal.cuh"
+#include "oi_render_common.cuh"
 
 namespace oi {
 
@@ -29,8 +30,6 @@ struct __align__(128) FfmaSmem {
   float act[kW * kTP];                   // [k][m], 16-byte chunks XOR-swizzled by (k>>2)&7   (64 KB)
   float wring[kStages][kChunkFloats];    // streamed weight chunks                            (32 KB)
   float red[2][4][kTP];                  // two-half partial sums of the narrow (<=3 output) contractions
-  float dir[3][kTP];                     // ray direction of each point
-  float dist[kTP];
   float sdfv[kTP];
   float grad[3][kTP];
   unsigned long long full[kStages];
@@ -152,7 +151,6 @@ __global__ void __launch_bounds__(kThreads, 2) render_ffma_kernel(const RenderKA
     for (int s = 0; s < kStages && pipe.pc < pipe.total; ++s) pipe_issue(sm, pipe);
 
   float* scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;  // [(D+1)][128 n][128 m]
-  const float inv_s = cst[BlobLayout::kScalars + 4];
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int inst = tile / a.tiles_per_inst;
@@ -160,66 +158,14 @@ __global__ void __launch_bounds__(kThreads, 2) render_ffma_kernel(const RenderKA
     const float* film = a.film + (size_t)inst * kFilm * 2 * kW;
 
     // ---------------- prologue: sample positions of the 128 points of this tile ----------------
-    int ray = 0, si = 0;
-    bool valid = false;
-    float mid = 0.f, dist = 0.f;
+    PointCtx pc;
+    pc.valid = false;
     if (tid < kTP) {
-      const int p = tin * kTP + tid;
-      valid = p < a.pts_per_inst;
-      const int pc = valid ? p : a.pts_per_inst - 1;
-      const int rl = pc / a.S;
-      si = pc - rl * a.S;
-      ray = inst * a.rays_per_inst + rl;
-      const float ox = a.rays_o[ray * 3 + 0], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
-      const float dx = a.rays_d[ray * 3 + 0], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
-      float z0, z1 = 0.f;
-      if (a.z_vals) {
-        z0 = a.z_vals[(size_t)ray * a.S + si];
-        if (si + 1 < a.S) z1 = a.z_vals[(size_t)ray * a.S + si + 1];
-      } else {  // renderer.py:359-360, 371-373
-        const float nr = a.near[ray], fr = a.far[ray];
-        const float span = fr - nr;
-        const float jit = a.t_rand ? a.t_rand[ray] * 2.0f / (float)a.n_coarse : 0.f;
-        const float l0 = a.lin ? a.lin[si] : (float)si / (float)(a.n_coarse - 1);
-        z0 = nr + span * l0;
-        if (a.t_rand) z0 = z0 + jit;
-        if (si + 1 < a.S) {
-          const float l1 = a.lin ? a.lin[si + 1] : (float)(si + 1) / (float)(a.n_coarse - 1);
-          z1 = nr + span * l1;
-          if (a.t_rand) z1 = z1 + jit;
-        }
-      }
-      float zp;
-      if (a.coarse) {
-        zp = z0;  // renderer.py:391
-      } else {
-        dist = (si + 1 < a.S) ? (z1 - z0) : a.sample_dist;  // renderer.py:219-222
-        mid = z0 + dist * 0.5f;                              // :225
-        zp = mid;
-      }
-      const float px = ox + dx * zp, py = oy + dy * zp, pz = oz + dz * zp;  // :228
-      const int cm = ((tid >> 2) << 2) | (tid & 3);  // rows 0..3: (k>>2)&7 == 0 -> no swizzle
-      sm.act[0 * kTP + cm] = px;
-      sm.act[1 * kTP + cm] = py;
-      sm.act[2 * kTP + cm] = pz;
-      sm.act[3 * kTP + cm] = 0.f;
-      sm.dir[0][tid] = dx;
-      sm.dir[1][tid] = dy;
-      sm.dir[2][tid] = dz;
-      sm.dist[tid] = dist;
-      if (valid && !a.coarse) {
-        const size_t gp = (size_t)ray * a.S + si;
-        const float nrm = sqrtf(px * px + py * py + pz * pz);
-        if (a.pts) {
-          a.pts[gp * 3 + 0] = px;
-          a.pts[gp * 3 + 1] = py;
-          a.pts[gp * 3 + 2] = pz;
-        }
-        if (a.mid_z) a.mid_z[gp] = mid;
-        if (a.pts_norm) a.pts_norm[gp] = nrm;
-        if (a.inside_sphere) a.inside_sphere[gp] = nrm < 1.0f ? 1.f : 0.f;
-        if (a.z_out) a.z_out[gp] = z0;
-      }
+      pc = point_prologue(a, inst, tin, tid);
+      sm.act[0 * kTP + tid] = pc.px;  // rows 0..3: (k>>2)&7 == 0 -> no swizzle
+      sm.act[1 * kTP + tid] = pc.py;
+      sm.act[2 * kTP + tid] = pc.pz;
+      sm.act[3 * kTP + tid] = 0.f;
     }
     __syncthreads();
 
@@ -261,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_ffma_kernel(const RenderKA
       if (tid < kTP) sm.sdfv[tid] = o[0] + cst[BlobLayout::kScalars + 0];
     }
     if (a.coarse) {
-      if (tid < kTP && valid) a.sdf_coarse[(size_t)ray * a.S + si] = sm.sdfv[tid];
+      if (tid < kTP && pc.valid) a.sdf_coarse[(size_t)pc.ray * a.S + pc.si] = sm.sdfv[tid];
       __syncthreads();
       continue;
     }
@@ -356,35 +302,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_ffma_kernel(const RenderKA
     narrow_contract<3>(sm, cst + BlobLayout::kWrgb, rgb, tid);
 
     // ---------------- per-point tail: colour, NeuS alpha (renderer.py:266-286) ----------------
-    if (tid < kTP && valid) {
-      const size_t gp = (size_t)ray * a.S + si;
-      const float sdf = sm.sdfv[tid];
-      const float gx = sm.grad[0][tid], gy = sm.grad[1][tid], gz = sm.grad[2][tid];
-      const float r = sigmoidf_acc(rgb[0] + cst[BlobLayout::kScalars + 1]);
-      const float g = sigmoidf_acc(rgb[1] + cst[BlobLayout::kScalars + 2]);
-      const float b = sigmoidf_acc(rgb[2] + cst[BlobLayout::kScalars + 3]);
-      const float true_cos = sm.dir[0][tid] * gx + sm.dir[1][tid] * gy + sm.dir[2][tid] * gz;
-      const float iter_cos = -(fmaxf(-true_cos * 0.5f + 0.5f, 0.f) * (1.0f - a.cos_anneal) +
-                               fmaxf(-true_cos, 0.f) * a.cos_anneal);
-      const float half_step = iter_cos * sm.dist[tid] * 0.5f;
-      const float prev_cdf = sigmoidf_acc((sdf - half_step) * inv_s);
-      const float next_cdf = sigmoidf_acc((sdf + half_step) * inv_s);
-      float alpha = (prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f);
-      alpha = fminf(fmaxf(alpha, 0.f), 1.f);
-      if (a.sdf) a.sdf[gp] = sdf;
-      if (a.cdf_fine) a.cdf_fine[gp] = prev_cdf;
-      a.alpha[gp] = alpha;
-      if (a.gradients) {
-        a.gradients[gp * 3 + 0] = gx;
-        a.gradients[gp * 3 + 1] = gy;
-        a.gradients[gp * 3 + 2] = gz;
-      }
-      if (a.raw_color) {
-        a.raw_color[gp * 3 + 0] = r;
-        a.raw_color[gp * 3 + 1] = g;
-        a.raw_color[gp * 3 + 2] = b;
-      }
-    }
+    if (tid < kTP) point_tail(a, pc, cst, sm.sdfv[tid], sm.grad[0][tid], sm.grad[1][tid], sm.grad[2][tid], rgb);
     __syncthreads();
   }
 }

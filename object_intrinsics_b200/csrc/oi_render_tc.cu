@@ -1,15 +1,460 @@
-// tcgen05 (5th-gen tensor core) core of the fused SDF render kernel (OI_IMPL_TCGEN05) -- placeholder until
-// the UMMA path lands; reports OI_ERR_UNSUPPORTED so that callers fail loudly instead of silently degrading.
+// tcgen05 (5th-gen tensor core) core of the fused SDF render kernel (OI_IMPL_TCGEN05).
+//
+// Same mathematics as oi_render_ffma.cu, but every 128x128 FiLM-SIREN contraction runs on the tensor cores:
+//   * a CTA (one per SM, persistent) owns TWO tiles of 128 sample points; row m of a tile lives in TMEM lane m;
+//   * the fp32 activation is split into two fp16 terms (h = hi + lo, |err| <= 2^-22 |h|), the fp32 weight
+//     likewise (pre-split, pre-scaled by 2^8 and pre-swizzled by oi_pack_weights), and one layer is three
+//     chains of tcgen05.mma.kind::f16 with fp32 accumulation in TMEM:  hi*Whi + lo*Whi + hi*Wlo;
+//   * the A operand (activations) is written straight into TMEM by the epilogue warps (tcgen05.st) and
+//     consumed from TMEM (.ts form) -- activations never touch shared memory;
+//   * B panels (64 KB per layer: {hi,lo} x 2 k-blocks, K-major SWIZZLE_128B images) are streamed from L2 by
+//     TMA bulk copies through a 3-stage mbarrier ring and are shared by both tiles;
+//   * per TMEM lane, one thread does the FiLM epilogue: sincos, split, tcgen05.st of the next operand,
+//     gamma*cos to the reverse-sweep scratch; while tile 0 is in its epilogue the tensor core works on tile 1.
+// Warp roles: 0-3 epilogue of tile 0, 4-7 epilogue of tile 1, 8 TMA producer, 9 MMA issuer.
 #include "oi_internal.cuh"
+#include "oi_render_common.cuh"
+#include "oi_tc.cuh"
 
 namespace oi {
 
-size_t render_tc_scratch_floats(int depth, int* n_ctas, int n_tiles) {
-  return render_ffma_scratch_floats(depth, n_ctas, n_tiles);
+namespace {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcStages = 3;
+constexpr int kPanelBytes = 65536;
+constexpr int kSubPanelBytes = 16384;
+constexpr float kWScale = 256.0f;        // weights are packed as 2^8 * W (see pack_weights_kernel)
+constexpr float kInvWScale = 1.0f / 256.0f;
+constexpr uint32_t kIdesc = tc::make_idesc_f16(128, 128);
+
+struct __align__(1024) TcSmem {
+  unsigned char w[kTcStages][kPanelBytes];  // weight panels (192 KB)
+  float2 film[2][kFilm][kW];                // per tile: (gamma', delta)
+  float4 w0[kW];                            // (W_0[n][0..2], 0)
+  float4 head[kW];                          // 2^8 * (w_sigma[n], wc_grad[0..2][n])
+  float4 rgbw[kW];                          // (W_rgb[0..2][n], 0)
+  unsigned long long w_full[kTcStages], w_empty[kTcStages];
+  unsigned long long acc_full[2], a_ready[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB per-CTA limit");
+
+__device__ __forceinline__ void sin_film(float x, float* s) {
+  const float kInv2Pi = 0.15915494309189535f;
+  const float k2PiHi = 6.2831854820251465f;
+  const float k2PiLo = -1.7484555314695172e-07f;
+  float t = fmaf(x, kInv2Pi, 12582912.0f);
+  float k = t - 12582912.0f;
+  float r = fmaf(k, -k2PiHi, x);
+  r = fmaf(k, -k2PiLo, r);
+  *s = __sinf(r);
 }
 
-int launch_render_tc(const RenderKArgs&, cudaStream_t) {
-  return set_error(OI_ERR_UNSUPPORTED, "OI_IMPL_TCGEN05 is not built into this library");
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 24 MMAs of one layer of one tile: acc = hi*Whi + lo*Whi + hi*Wlo over K = 128.
+__device__ __forceinline__ void issue_layer_mmas(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int kb = k >> 2, ks = k & 3;
+    const uint64_t bhi = tc::make_desc_k_sw128(wbase + kb * kSubPanelBytes + ks * 32);
+    const uint64_t blo = tc::make_desc_k_sw128(wbase + 2 * kSubPanelBytes + kb * kSubPanelBytes + ks * 32);
+    tc::mma_ts(acc, a_hi + k * 8, bhi, kIdesc, k > 0 ? 1u : 0u);
+    tc::mma_ts(acc, a_lo + k * 8, bhi, kIdesc, 1u);
+    tc::mma_ts(acc, a_hi + k * 8, blo, kIdesc, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.D;
+  const BlobLayout L = blob_layout(D);
+  const float* cst = a.blob + L.const_off;
+  const unsigned char* panels = reinterpret_cast<const unsigned char*>(a.blob + L.tc_off);
+  const int NP = a.coarse ? (D - 1) : (2 * (D - 1) + 1);  // MMA panels per tile
+  const int n_pairs = (a.n_tiles + 1) / 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&sm.w_full[s], 1);
+      mbar_init(&sm.w_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sm.acc_full[t], 1);
+      mbar_init(&sm.a_ready[t], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    tc::tmem_alloc(&sm.tmem_base, 512);
+    tc::tmem_relinquish();
+  }
+  for (int n = tid; n < kW; n += kTcThreads) {
+    sm.w0[n] = make_float4(cst[BlobLayout::kW0t + n], cst[BlobLayout::kW0t + kW + n], cst[BlobLayout::kW0t + 2 * kW + n], 0.f);
+    sm.head[n] = make_float4(kWScale * cst[BlobLayout::kWsig + n], kWScale * cst[BlobLayout::kWcg + n],
+                             kWScale * cst[BlobLayout::kWcg + kW + n], kWScale * cst[BlobLayout::kWcg + 2 * kW + n]);
+    sm.rgbw[n] = make_float4(cst[BlobLayout::kWrgb + n], cst[BlobLayout::kWrgb + kW + n],
+                             cst[BlobLayout::kWrgb + 2 * kW + n], 0.f);
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+        for (int p = 0; p < NP; ++p, ++it) {
+          const int stage = it % kTcStages;
+          if (it >= kTcStages) mbar_wait(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1);
+          mbar_expect_tx(&sm.w_full[stage], kPanelBytes);
+          const unsigned char* src = panels + (size_t)p * kPanelBytes;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            tma_bulk_g2s(sm.w[stage] + q * kSubPanelBytes, src + q * kSubPanelBytes, kSubPanelBytes, &sm.w_full[stage]);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int it = 0;
+      uint32_t ar_phase[2] = {0u, 0u};
+      for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+        const int n_active = (2 * pi + 1 < a.n_tiles) ? 2 : 1;
+        for (int p = 0; p < NP; ++p, ++it) {
+          const int stage = it % kTcStages;
+          mbar_wait(&sm.w_full[stage], (it / kTcStages) & 1);
+          const uint32_t wbase = smem_u32(sm.w[stage]);
+          for (int t = 0; t < n_active; ++t) {
+            mbar_wait(&sm.a_ready[t], ar_phase[t]);
+            ar_phase[t] ^= 1u;
+            tc::fence_after_thread_sync();
+            const uint32_t acc = tmem_base + t * 256;
+            issue_layer_mmas(acc, acc + 128, acc + 192, wbase);
+            tc::mma_commit(&sm.acc_full[t]);
+          }
+          tc::mma_commit(&sm.w_empty[stage]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: thread <-> TMEM lane <-> sample point =====================
+    const int t = warp >> 2;                 // tile slot
+    const int m = tid & 127;                 // point in tile == TMEM lane
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t acc = tmem_base + t * 256 + lane_field;
+    const uint32_t a_hi = acc + 128, a_lo = acc + 192;
+    float* scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride + (size_t)t * (D + 1) * kW * 128;
+    uint32_t af_phase = 0u;
+
+    for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+      const int tile = 2 * pi + t;
+      if (tile >= a.n_tiles) continue;
+      const int inst = tile / a.tiles_per_inst;
+      const int tin = tile - inst * a.tiles_per_inst;
+      {  // FiLM table of this tile's instance
+        const float2* src = reinterpret_cast<const float2*>(a.film_tc) + (size_t)inst * kFilm * kW;
+        float2* dst = &sm.film[t][0][0];
+        for (int i = m; i < kFilm * kW; i += 128) dst[i] = src[i];
+      }
+      const PointCtx pc = point_prologue(a, inst, tin, m);
+      named_bar_sync(1 + t, 128);
+
+      float sdf_acc = 0.f;
+      // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
+      {
+        const float2* fl = sm.film[t][0];
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float s[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int n = c * 32 + j + e;
+              const float4 w = sm.w0[n];
+              const float2 f = fl[n];
+              const float u = fmaf(w.z, pc.pz, fmaf(w.y, pc.py, w.x * pc.px));
+              float cs;
+              sincos_film(fmaf(f.x, u, f.y), &s[e], &cs);
+              if (!a.coarse) scr[((size_t)0 * kW + n) * 128 + m] = f.x * kInvWScale * cs;
+              if (D == 1) sdf_acc = fmaf(sm.head[n].x, s[e], sdf_acc);
+            }
+            tc::split2(s[0], s[1], hi[j >> 1], lo[j >> 1]);
+          }
+          tc::tmem_st16(a_hi + c * 16, hi);
+          tc::tmem_st16(a_lo + c * 16, lo);
+        }
+        tc::wait_st();
+        tc::fence_before_thread_sync();
+        mbar_arrive(&sm.a_ready[t]);
+      }
+      // ---------------- forward layers 1..D-1 ----------------
+      for (int l = 1; l < D; ++l) {
+        const float2* fl = sm.film[t][l];
+        mbar_wait(&sm.acc_full[t], af_phase);
+        af_phase ^= 1u;
+        tc::fence_after_thread_sync();
+        const bool last = (l == D - 1);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float u[32];
+          tc::tmem_ld32(acc + c * 32, u);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float s[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int n = c * 32 + j + e;
+              const float2 f = fl[n];
+              float cs;
+              sincos_film(fmaf(f.x, u[j + e], f.y), &s[e], &cs);
+              if (!a.coarse) scr[((size_t)l * kW + n) * 128 + m] = f.x * cs;
+              if (last) sdf_acc = fmaf(sm.head[n].x, s[e], sdf_acc);
+            }
+            tc::split2(s[0], s[1], hi[j >> 1], lo[j >> 1]);
+          }
+          if (!(last && a.coarse)) {
+            tc::tmem_st16(a_hi + c * 16, hi);
+            tc::tmem_st16(a_lo + c * 16, lo);
+          }
+        }
+        if (!(last && a.coarse)) {
+          tc::wait_st();
+          tc::fence_before_thread_sync();
+          mbar_arrive(&sm.a_ready[t]);
+        }
+      }
+      const float sdf = sdf_acc * kInvWScale + cst[BlobLayout::kScalars + 0];
+      if (a.coarse) {
+        if (pc.valid) a.sdf_coarse[(size_t)pc.ray * a.S + pc.si] = sdf;
+        named_bar_sync(1 + t, 128);
+        continue;
+      }
+      // ---------------- colour layer, feature part: park 2^8 * W_c[:, :128] h in scratch slot D;
+      //                  start the reverse sweep: t_{D-1} = w_sigma * gamma cos(arg_{D-1}) ----------------
+      mbar_wait(&sm.acc_full[t], af_phase);
+      af_phase ^= 1u;
+      tc::fence_after_thread_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float u[32];
+        tc::tmem_ld32(acc + c * 32, u);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float tv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = c * 32 + j + e;
+            scr[((size_t)D * kW + n) * 128 + m] = u[j + e];
+            tv[e] = sm.head[n].x * scr[((size_t)(D - 1) * kW + n) * 128 + m];
+          }
+          tc::split2(tv[0], tv[1], hi[j >> 1], lo[j >> 1]);
+        }
+        tc::tmem_st16(a_hi + c * 16, hi);
+        tc::tmem_st16(a_lo + c * 16, lo);
+      }
+      tc::wait_st();
+      tc::fence_before_thread_sync();
+      mbar_arrive(&sm.a_ready[t]);
+      // ---------------- reverse sweep l = D-1 .. 1 ----------------
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      for (int l = D - 1; l >= 1; --l) {
+        mbar_wait(&sm.acc_full[t], af_phase);
+        af_phase ^= 1u;
+        tc::fence_after_thread_sync();
+        const float* csl = scr + (size_t)(l - 1) * kW * 128 + m;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float u[32];
+          tc::tmem_ld32(acc + c * 32, u);
+          if (l > 1) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int n = c * 32 + j;
+              const float t0 = u[j] * csl[(size_t)n * 128];
+              const float t1 = u[j + 1] * csl[(size_t)(n + 1) * 128];
+              tc::split2(t0, t1, hi[j >> 1], lo[j >> 1]);
+            }
+            tc::tmem_st16(a_hi + c * 16, hi);
+            tc::tmem_st16(a_lo + c * 16, lo);
+          } else {  // grad_x sdf = W_0^T t_0
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = c * 32 + j;
+              const float t0 = u[j] * csl[(size_t)n * 128];
+              const float4 w = sm.w0[n];
+              gx = fmaf(w.x, t0, gx);
+              gy = fmaf(w.y, t0, gy);
+              gz = fmaf(w.z, t0, gz);
+            }
+          }
+        }
+        if (l > 1) {
+          tc::wait_st();
+          tc::fence_before_thread_sync();
+          mbar_arrive(&sm.a_ready[t]);
+        }
+      }
+      // ---------------- colour layer epilogue + rgb head ----------------
+      float rgb[3] = {0.f, 0.f, 0.f};
+      {
+        const float2* fl = sm.film[t][OI_MAX_DEPTH];
+        const float* ucl = scr + (size_t)D * kW * 128 + m;
+#pragma unroll 4
+        for (int n = 0; n < kW; ++n) {
+          const float4 hd = sm.head[n];
+          const float2 f = fl[n];
+          float pre = fmaf(hd.y, gx, ucl[(size_t)n * 128]);
+          pre = fmaf(hd.z, gy, pre);
+          pre = fmaf(hd.w, gz, pre);
+          float s;
+          sin_film(fmaf(f.x, pre, f.y), &s);
+          const float4 rw = sm.rgbw[n];
+          rgb[0] = fmaf(rw.x, s, rgb[0]);
+          rgb[1] = fmaf(rw.y, s, rgb[1]);
+          rgb[2] = fmaf(rw.z, s, rgb[2]);
+        }
+      }
+      point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
+      named_bar_sync(1 + t, 128);  // film table of this slot may be overwritten by the next tile now
+    }
+  }
+
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test of the UMMA building blocks: D[128,128] = A[128,128] * B[128,128]^T through the same
+// split / TMEM-operand / SWIZZLE_128B-panel path as the render kernel.  panel != NULL: B comes from a
+// packed 64 KB panel image by TMA (checks oi_pack_weights); panel == NULL: B is split and swizzled in-kernel.
+// ------------------------------------------------------------------------------------------------
+struct __align__(1024) SelfTestSmem {
+  unsigned char w[kPanelBytes];
+  unsigned long long w_full, acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                             const unsigned char* __restrict__ panel,
+                                                             float* __restrict__ Dout) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SelfTestSmem& sm = *reinterpret_cast<SelfTestSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&sm.w_full, 1);
+    mbar_init(&sm.acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    tc::tmem_alloc(&sm.tmem_base, 256);
+    tc::tmem_relinquish();
+  }
+  if (panel == nullptr) {
+    __half* wh = reinterpret_cast<__half*>(sm.w);
+    for (int i = tid; i < kW * kW; i += blockDim.x) {
+      const int n = i / kW, k = i % kW;
+      const float v = B[n * kW + k];
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      const int kb = k >> 6, kk = k & 63;
+      const int idx = n * 64 + (((kk >> 3) ^ (n & 7)) << 3) + (kk & 7);
+      wh[kb * 8192 + idx] = hi;
+      wh[2 * 8192 + kb * 8192 + idx] = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = sm.tmem_base;
+  if (panel != nullptr && tid == 128) {
+    mbar_expect_tx(&sm.w_full, kPanelBytes);
+    for (int q = 0; q < 4; ++q)
+      tma_bulk_g2s(sm.w + q * kSubPanelBytes, panel + q * kSubPanelBytes, kSubPanelBytes, &sm.w_full);
+  }
+  if (warp < 4) {
+    const int m = tid;
+    const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
+    const uint32_t acc = tmem_base + lane_field;
+    for (int c = 0; c < 4; ++c) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2)
+        tc::split2(A[m * kW + c * 32 + j], A[m * kW + c * 32 + j + 1], hi[j >> 1], lo[j >> 1]);
+      tc::tmem_st16(acc + 128 + c * 16, hi);
+      tc::tmem_st16(acc + 192 + c * 16, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_thread_sync();
+  }
+  __syncthreads();
+  if (tid == 128) {
+    tc::fence_after_thread_sync();
+    if (panel != nullptr) mbar_wait(&sm.w_full, 0);
+    issue_layer_mmas(tmem_base, tmem_base + 128, tmem_base + 192, smem_u32(sm.w));
+    tc::mma_commit(&sm.acc_full);
+  }
+  if (warp < 4) {
+    const int m = tid;
+    const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
+    mbar_wait(&sm.acc_full, 0);
+    tc::fence_after_thread_sync();
+    for (int c = 0; c < 4; ++c) {
+      float u[32];
+      tc::tmem_ld32(acc + c * 32, u);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Dout[m * kW + c * 32 + j] = u[j];
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace
+
+size_t render_tc_scratch_floats(int depth, int* n_ctas, int n_tiles) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_pairs = (n_tiles + 1) / 2;
+  int ctas = sms < n_pairs ? sms : n_pairs;
+  if (ctas < 1) ctas = 1;
+  if (n_ctas) *n_ctas = ctas;
+  return (size_t)2 * (depth + 1) * kW * 128;
+}
+
+int launch_render_tc(const RenderKArgs& a, cudaStream_t st) {
+  if (a.D < 2) return set_error(OI_ERR_UNSUPPORTED, "the tcgen05 core needs depth >= 2 (use OI_IMPL_FFMA)");
+  int n_ctas = 0;
+  render_tc_scratch_floats(a.D, &n_ctas, a.n_tiles);
+  OI_CHECK_CUDA(cudaFuncSetAttribute(render_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem)));
+  render_tc_kernel<<<n_ctas, kTcThreads, sizeof(TcSmem), st>>>(a);
+  OI_CHECK_CUDA(cudaGetLastError());
+  return OI_OK;
+}
+
+int launch_tc_selftest(const float* A, const float* B, const void* panel, float* D, cudaStream_t st) {
+  OI_CHECK_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(SelfTestSmem)));
+  tc_selftest_kernel<<<1, 160, sizeof(SelfTestSmem), st>>>(A, B, static_cast<const unsigned char*>(panel), D);
+  OI_CHECK_CUDA(cudaGetLastError());
+  return OI_OK;
 }
 
 }  // namespace oi
