@@ -13,7 +13,7 @@ from oracle import neus_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = ["ffma"]
+IMPLS = ["ffma", "tcgen05"]
 
 
 def _build(meta, impl):
