@@ -191,6 +191,7 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   a.n_coarse = n;
   a.D = d->depth;
   a.cos_anneal = d->cos_anneal_ratio;
+  a.flags = d->flags;
   a.sample_dist = 2.0f / (float)n;  // renderer.py:356
   a.rays_o = d->rays_o;
   a.rays_d = d->rays_d;

@@ -99,6 +99,7 @@ struct RenderKArgs {
   int D;
   int pts_per_inst, tiles_per_inst, n_tiles;
   int coarse;    // 1: SDF only at z (renderer.py:389-399), 0: full render_core at the section midpoints
+  int flags;     // OiRenderDesc.flags (bit 0: drop dead scratch lines from L2 with discard.global.L2)
   float cos_anneal, sample_dist;
   const float *rays_o, *rays_d, *near, *far, *t_rand, *lin;
   const float* z_vals;  // [R,S] section starts or NULL (computed from near/far/lin/t_rand)
@@ -165,6 +166,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// Same, but lets the hardware suspend the thread for up to `hint_ns` per probe (long waits: far fewer
+// issue slots burnt on polling than the plain try_wait loop).
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, uint32_t parity, uint32_t hint_ns = 20000u) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(hint_ns)
+      : "memory");
+}
+// Drops a 128-byte line from L2 without writing it back (the data is dead: read-once scratch).
+__device__ __forceinline__ void l2_discard_128(const void* p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,

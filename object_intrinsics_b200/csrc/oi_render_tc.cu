@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
         for (int p = 0; p < NP; ++p, ++it) {
           const int stage = it % kTcStages;
-          if (it >= kTcStages) mbar_wait(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1);
+          if (it >= kTcStages) mbar_wait_sleep(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1);
           mbar_expect_tx(&sm.w_full[stage], kPanelBytes);
           const unsigned char* src = panels + (size_t)p * kPanelBytes;
 #pragma unroll
@@ -131,10 +131,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         const int n_active = (2 * pi + 1 < a.n_tiles) ? 2 : 1;
         for (int p = 0; p < NP; ++p, ++it) {
           const int stage = it % kTcStages;
-          mbar_wait(&sm.w_full[stage], (it / kTcStages) & 1);
+          mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
           const uint32_t wbase = smem_u32(sm.w[stage]);
           for (int t = 0; t < n_active; ++t) {
-            mbar_wait(&sm.a_ready[t], ar_phase[t]);
+            mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
             ar_phase[t] ^= 1u;
             tc::fence_after_thread_sync();
             const uint32_t acc = tmem_base + t * 256;
@@ -152,8 +152,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t acc = tmem_base + t * 256 + lane_field;
     const uint32_t a_hi = acc + 128, a_lo = acc + 192;
-    float* scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride + (size_t)t * (D + 1) * kW * 128;
+    // scratch of this tile slot: (D+1) slots of [32 channel-quads][128 points] float4
+    float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
+                                             (size_t)t * (D + 1) * kW * 128) + m;
+    const bool discard = (a.flags & 1) != 0 && (m & 7) == 0;
     uint32_t af_phase = 0u;
+#define OI_SLOT(slot, q) scr4[((size_t)(slot) * 32 + (q)) * 128]
 
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
       const int tile = 2 * pi + t;
@@ -176,20 +180,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         for (int c = 0; c < 4; ++c) {
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float s[2];
+          for (int q = 0; q < 8; ++q) {
+            float s[4], cv[4];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int n = c * 32 + j + e;
+            for (int e = 0; e < 4; ++e) {
+              const int n = c * 32 + q * 4 + e;
               const float4 w = sm.w0[n];
               const float2 f = fl[n];
               const float u = fmaf(w.z, pc.pz, fmaf(w.y, pc.py, w.x * pc.px));
               float cs;
               sincos_film(fmaf(f.x, u, f.y), &s[e], &cs);
-              if (!a.coarse) scr[((size_t)0 * kW + n) * 128 + m] = f.x * kInvWScale * cs;
-              if (D == 1) sdf_acc = fmaf(sm.head[n].x, s[e], sdf_acc);
+              cv[e] = f.x * kInvWScale * cs;
             }
-            tc::split2(s[0], s[1], hi[j >> 1], lo[j >> 1]);
+            if (!a.coarse) OI_SLOT(0, c * 8 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
+            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
           tc::tmem_st16(a_hi + c * 16, hi);
           tc::tmem_st16(a_lo + c * 16, lo);
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       // ---------------- forward layers 1..D-1 ----------------
       for (int l = 1; l < D; ++l) {
         const float2* fl = sm.film[t][l];
-        mbar_wait(&sm.acc_full[t], af_phase);
+        mbar_wait_sleep(&sm.acc_full[t], af_phase);
         af_phase ^= 1u;
         tc::fence_after_thread_sync();
         const bool last = (l == D - 1);
@@ -211,18 +216,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           tc::tmem_ld32(acc + c * 32, u);
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float s[2];
+          for (int q = 0; q < 8; ++q) {
+            float s[4], cv[4];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int n = c * 32 + j + e;
+            for (int e = 0; e < 4; ++e) {
+              const int n = c * 32 + q * 4 + e;
               const float2 f = fl[n];
               float cs;
-              sincos_film(fmaf(f.x, u[j + e], f.y), &s[e], &cs);
-              if (!a.coarse) scr[((size_t)l * kW + n) * 128 + m] = f.x * cs;
+              sincos_film(fmaf(f.x, u[q * 4 + e], f.y), &s[e], &cs);
+              cv[e] = f.x * cs;
               if (last) sdf_acc = fmaf(sm.head[n].x, s[e], sdf_acc);
             }
-            tc::split2(s[0], s[1], hi[j >> 1], lo[j >> 1]);
+            if (!a.coarse) OI_SLOT(l, c * 8 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
+            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
           if (!(last && a.coarse)) {
             tc::tmem_st16(a_hi + c * 16, hi);
@@ -243,63 +250,85 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       }
       // ---------------- colour layer, feature part: park 2^8 * W_c[:, :128] h in scratch slot D;
       //                  start the reverse sweep: t_{D-1} = w_sigma * gamma cos(arg_{D-1}) ----------------
-      mbar_wait(&sm.acc_full[t], af_phase);
-      af_phase ^= 1u;
-      tc::fence_after_thread_sync();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float u[32];
-        tc::tmem_ld32(acc + c * 32, u);
-        uint32_t hi[16], lo[16];
+      {
+        float4 csn[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float tv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int n = c * 32 + j + e;
-            scr[((size_t)D * kW + n) * 128 + m] = u[j + e];
-            tv[e] = sm.head[n].x * scr[((size_t)(D - 1) * kW + n) * 128 + m];
-          }
-          tc::split2(tv[0], tv[1], hi[j >> 1], lo[j >> 1]);
-        }
-        tc::tmem_st16(a_hi + c * 16, hi);
-        tc::tmem_st16(a_lo + c * 16, lo);
-      }
-      tc::wait_st();
-      tc::fence_before_thread_sync();
-      mbar_arrive(&sm.a_ready[t]);
-      // ---------------- reverse sweep l = D-1 .. 1 ----------------
-      float gx = 0.f, gy = 0.f, gz = 0.f;
-      for (int l = D - 1; l >= 1; --l) {
-        mbar_wait(&sm.acc_full[t], af_phase);
+        for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(D - 1, q);
+        mbar_wait_sleep(&sm.acc_full[t], af_phase);
         af_phase ^= 1u;
         tc::fence_after_thread_sync();
-        const float* csl = scr + (size_t)(l - 1) * kW * 128 + m;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           float u[32];
           tc::tmem_ld32(acc + c * 32, u);
+          float4 csc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) csc[q] = csn[q];
+          if (c < 3) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(D - 1, (c + 1) * 8 + q);
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            OI_SLOT(D, c * 8 + q) = make_float4(u[q * 4], u[q * 4 + 1], u[q * 4 + 2], u[q * 4 + 3]);
+            const int n = c * 32 + q * 4;
+            tc::split2(sm.head[n].x * csc[q].x, sm.head[n + 1].x * csc[q].y, hi[2 * q], lo[2 * q]);
+            tc::split2(sm.head[n + 2].x * csc[q].z, sm.head[n + 3].x * csc[q].w, hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          tc::tmem_st16(a_hi + c * 16, hi);
+          tc::tmem_st16(a_lo + c * 16, lo);
+        }
+        tc::wait_st();
+        tc::fence_before_thread_sync();
+        mbar_arrive(&sm.a_ready[t]);
+      }
+      // ---------------- reverse sweep l = D-1 .. 1 ----------------
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      for (int l = D - 1; l >= 1; --l) {
+        float4 csn[8];   // one-chunk look-ahead of gamma*cos(arg_{l-1}), issued before the MMA wait
+#pragma unroll
+        for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(l - 1, q);
+        mbar_wait_sleep(&sm.acc_full[t], af_phase);
+        af_phase ^= 1u;
+        tc::fence_after_thread_sync();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float u[32];
+          tc::tmem_ld32(acc + c * 32, u);
+          float4 csc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) csc[q] = csn[q];
+          if (c < 3) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(l - 1, (c + 1) * 8 + q);
+          }
           if (l > 1) {
             uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int n = c * 32 + j;
-              const float t0 = u[j] * csl[(size_t)n * 128];
-              const float t1 = u[j + 1] * csl[(size_t)(n + 1) * 128];
-              tc::split2(t0, t1, hi[j >> 1], lo[j >> 1]);
+            for (int q = 0; q < 8; ++q) {
+              tc::split2(u[q * 4] * csc[q].x, u[q * 4 + 1] * csc[q].y, hi[2 * q], lo[2 * q]);
+              tc::split2(u[q * 4 + 2] * csc[q].z, u[q * 4 + 3] * csc[q].w, hi[2 * q + 1], lo[2 * q + 1]);
             }
             tc::tmem_st16(a_hi + c * 16, hi);
             tc::tmem_st16(a_lo + c * 16, lo);
           } else {  // grad_x sdf = W_0^T t_0
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = c * 32 + j;
-              const float t0 = u[j] * csl[(size_t)n * 128];
-              const float4 w = sm.w0[n];
-              gx = fmaf(w.x, t0, gx);
-              gy = fmaf(w.y, t0, gy);
-              gz = fmaf(w.z, t0, gz);
+            for (int q = 0; q < 8; ++q) {
+              const float tv[4] = {u[q * 4] * csc[q].x, u[q * 4 + 1] * csc[q].y, u[q * 4 + 2] * csc[q].z,
+                                   u[q * 4 + 3] * csc[q].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 w = sm.w0[c * 32 + q * 4 + e];
+                gx = fmaf(w.x, tv[e], gx);
+                gy = fmaf(w.y, tv[e], gy);
+                gz = fmaf(w.z, tv[e], gz);
+              }
             }
+          }
+          if (discard) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) l2_discard_128(&OI_SLOT(l - 1, c * 8 + q));
           }
         }
         if (l > 1) {
@@ -312,25 +341,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       float rgb[3] = {0.f, 0.f, 0.f};
       {
         const float2* fl = sm.film[t][OI_MAX_DEPTH];
-        const float* ucl = scr + (size_t)D * kW * 128 + m;
-#pragma unroll 4
-        for (int n = 0; n < kW; ++n) {
-          const float4 hd = sm.head[n];
-          const float2 f = fl[n];
-          float pre = fmaf(hd.y, gx, ucl[(size_t)n * 128]);
-          pre = fmaf(hd.z, gy, pre);
-          pre = fmaf(hd.w, gz, pre);
-          float s;
-          sin_film(fmaf(f.x, pre, f.y), &s);
-          const float4 rw = sm.rgbw[n];
-          rgb[0] = fmaf(rw.x, s, rgb[0]);
-          rgb[1] = fmaf(rw.y, s, rgb[1]);
-          rgb[2] = fmaf(rw.z, s, rgb[2]);
+        float4 ucn[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ucn[q] = OI_SLOT(D, q);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float4 ucc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ucc[q] = ucn[q];
+          if (c < 3) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ucn[q] = OI_SLOT(D, (c + 1) * 8 + q);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float uv[4] = {ucc[q].x, ucc[q].y, ucc[q].z, ucc[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = c * 32 + q * 4 + e;
+              const float4 hd = sm.head[n];
+              const float2 f = fl[n];
+              float pre = fmaf(hd.y, gx, uv[e]);
+              pre = fmaf(hd.z, gy, pre);
+              pre = fmaf(hd.w, gz, pre);
+              float s;
+              sin_film(fmaf(f.x, pre, f.y), &s);
+              const float4 rw = sm.rgbw[n];
+              rgb[0] = fmaf(rw.x, s, rgb[0]);
+              rgb[1] = fmaf(rw.y, s, rgb[1]);
+              rgb[2] = fmaf(rw.z, s, rgb[2]);
+            }
+          }
+          if (discard) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) l2_discard_128(&OI_SLOT(D, c * 8 + q));
+          }
         }
       }
       point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
       named_bar_sync(1 + t, 128);  // film table of this slot may be overwritten by the next tile now
     }
+#undef OI_SLOT
   }
 
   tc::fence_before_thread_sync();

@@ -23,6 +23,7 @@ There is NO CPU path and no silent fallback: a missing library or an unsupported
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -150,6 +151,7 @@ class NeuSRenderer:
         self._packed = PackedWeights()
         self._workspace: Optional[torch.Tensor] = None
         self._lin = {}
+        self.flags = int(os.environ.get("OI_RENDER_FLAGS", "0"))   # OiRenderDesc.flags (tuning switches)
         self.last_launches = 0
         self.core_events = None   # optional (torch.cuda.Event, torch.cuda.Event) recorded around the core kernel
 
@@ -247,7 +249,8 @@ class NeuSRenderer:
 
         d = _lib.OiRenderDesc()
         d.n_rays, d.rays_per_instance, d.n_samples, d.n_importance = R, R // n_inst, n, m
-        d.up_sample_steps, d.depth, d.impl, d.flags = self.up_sample_steps, self._packed.depth, _IMPL[self.impl], 0
+        d.up_sample_steps, d.depth, d.impl, d.flags = self.up_sample_steps, self._packed.depth, _IMPL[self.impl], \
+            self.flags
         d.cos_anneal_ratio = cos_anneal_ratio
         d.rays_o, d.rays_d, d.near, d.far = rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr()
         d.t_rand = _lib.ptr(t_rand)
