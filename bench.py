@@ -262,7 +262,7 @@ def main():
     value = world * R * args.steps / (total_ms * 1e-3)
     e2e_value = world * R * args.steps / (e2e_ms * 1e-3)
     core_avg_ms = sum(core_ms) / len(core_ms)
-    used_tc = (args.kernel == "tcgen05")
+    used_tc = args.kernel in ("auto", "tcgen05")   # auto resolves to the tcgen05 core for depth >= 2
     flops = N * FLOP_PER_POINT
     achieved_tflops = flops / (core_avg_ms * 1e-3) / 1e12
     if used_tc:

@@ -108,7 +108,7 @@ typedef struct OiRenderDesc {
   int32_t up_sample_steps;   /* only 1 is implemented (configs/train.yaml:76) */
   int32_t depth;             /* D of the packed network */
   int32_t impl;              /* OiRenderImpl */
-  int32_t flags;             /* reserved, 0 */
+  int32_t flags;             /* bit 0 (OI_FLAG_DISCARD_SCRATCH): drop dead reverse-sweep scratch lines from L2 (discard.global.L2) */
   float cos_anneal_ratio;    /* renderer.py:273-274 */
   float reserved_f;
 

@@ -30,7 +30,7 @@ struct Workspace {
 
 int resolve_impl(const OiRenderDesc* d) {
   int impl = d->impl;
-  if (impl == OI_IMPL_AUTO) impl = OI_IMPL_FFMA;
+  if (impl == OI_IMPL_AUTO) impl = (d->depth >= 2) ? OI_IMPL_TCGEN05 : OI_IMPL_FFMA;
   return impl;
 }
 

@@ -151,7 +151,7 @@ class NeuSRenderer:
         self._packed = PackedWeights()
         self._workspace: Optional[torch.Tensor] = None
         self._lin = {}
-        self.flags = int(os.environ.get("OI_RENDER_FLAGS", "0"))   # OiRenderDesc.flags (tuning switches)
+        self.flags = int(os.environ.get("OI_RENDER_FLAGS", "1"))   # OiRenderDesc.flags: bit 0 = L2 discard of dead scratch
         self.last_launches = 0
         self.core_events = None   # optional (torch.cuda.Event, torch.cuda.Event) recorded around the core kernel
 
