@@ -249,18 +249,17 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    # whole-job numbers: units summed over ranks / max elapsed time over ranks (no data-path collective)
+    from object_intrinsics_b200.parallel import aggregate_throughput
+    value, _, total_s = aggregate_throughput(R * args.steps, total_ms * 1e-3)
+    e2e_value, _, _ = aggregate_throughput(R * args.steps, e2e_s)
+    total_ms = total_s * 1e3
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     peaks = load_peaks()
-    value = world * R * args.steps / (total_ms * 1e-3)
-    e2e_value = world * R * args.steps / (e2e_ms * 1e-3)
     core_avg_ms = sum(core_ms) / len(core_ms)
     used_tc = args.kernel in ("auto", "tcgen05")   # auto resolves to the tcgen05 core for depth >= 2
     flops = N * FLOP_PER_POINT
@@ -271,6 +270,14 @@ def main():
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         peak = sms * FP32_FMA_LANES_PER_SM * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
         bound, peak_note = "fp32_fma", f"nominal {sms} SMs x 128 lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz"
+    kernel_name = "render_tc_kernel" if used_tc else "render_ffma_kernel"
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)[kernel_name]
+        traffic = tr["dram_bytes_per_launch"] * (R / tr["rays_per_launch"])   # ncu capture, scaled to this launch
+    except Exception:  # noqa: BLE001
+        pass
     alg_bytes = R * (BYTES_PER_RAY_IN + BYTES_PER_RAY_OUT) + N * BYTES_PER_POINT
     hbm_gbs = alg_bytes / (core_avg_ms * 1e-3) / 1e9
     line = {
@@ -281,9 +288,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "rays/s",
                 "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": R * 16},
         "gpu_launches": args.steps * (renderer.last_launches + 3),
-        "roofline": {"bound": bound, "kernel": "render_tc_kernel" if used_tc else "render_ffma_kernel",
+        "roofline": {"bound": bound, "kernel": kernel_name,
                      "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
-                     "peak_source": peak_note, "traffic": None,
+                     "peak_source": peak_note, "traffic": traffic,
                      "core_kernel_ms": core_avg_ms, "algorithmic_flop_per_launch": flops,
                      "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": hbm_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes,

@@ -1,0 +1,117 @@
+"""CPU tests: C-ABI library loads and exports every symbol include/oi_b200.h declares, argument validation fails
+loudly without touching the GPU, instance sharding / throughput aggregation over a world_size-2 gloo group."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "oi_b200.h")).read()
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(oi_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    from object_intrinsics_b200 import _lib
+    L = _lib.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(L, s), f"liboi_b200.so does not export {s}"
+    assert set(syms) == set(_lib.EXPORTS), (set(syms) ^ set(_lib.EXPORTS))
+    assert L.oi_abi_version() == 1
+    assert b"sm_100a" in L.oi_build_info()
+
+
+def test_argument_validation_without_gpu():
+    from object_intrinsics_b200 import _lib
+    L = _lib.lib()
+    n = C.c_size_t(0)
+    assert L.oi_packed_weights_bytes(8, C.byref(n)) == 0 and n.value > 2_000_000
+    assert L.oi_packed_weights_bytes(0, C.byref(n)) == -1
+    assert b"depth" in L.oi_last_error()
+    d = _lib.OiRenderDesc()
+    assert L.oi_render_forward(C.byref(d), None) == -1                 # n_rays == 0
+    d.n_rays, d.rays_per_instance, d.n_samples, d.depth = 10, 3, 16, 8
+    assert L.oi_render_forward(C.byref(d), None) == -1 and b"multiple" in L.oi_last_error()
+    d.rays_per_instance, d.n_importance, d.up_sample_steps = 5, 4, 2
+    assert L.oi_render_workspace_bytes(C.byref(d), C.byref(n)) == -2   # OI_ERR_UNSUPPORTED
+    with pytest.raises(NotImplementedError):
+        _lib.check(-2, "x")
+    u = _lib.OiUpfirdnDesc()
+    assert L.oi_upfirdn2d(C.byref(u), None) == -1
+    b = _lib.OiBiasActDesc()
+    assert L.oi_bias_act(C.byref(b), None) == -1
+    f = _lib.OiFusedBiasActDesc()
+    assert L.oi_fused_bias_act(C.byref(f), None) == -1
+    p = _lib.OiNetParams()
+    p.depth, p.width, p.style_dim = 8, 256, 64
+    assert L.oi_pack_weights(C.byref(p), None, 0, None) == -2          # W != 128 unsupported
+
+
+def test_renderer_rejects_cpu_and_unsupported_arguments():
+    from object_intrinsics_b200 import fields
+    from object_intrinsics_b200.renderer import NeuSRenderer
+    sdf = fields.ShapeNetwork(D=2)
+    col, dev = fields.ColorNetwork(D=2), fields.SingleVarianceNetwork()
+    r = NeuSRenderer(None, sdf, dev, col, n_samples=8, n_importance=0, n_outside=0, up_sample_steps=1, perturb=0)
+    ro = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r.render(ro, ro, ro[:, :1], ro[:, :1], w=torch.zeros(1, 64))
+    with pytest.raises(NotImplementedError):
+        r.render(ro, ro, ro[:, :1], ro[:, :1], w=torch.zeros(1, 64), second_order=True)
+    with pytest.raises(ValueError):
+        NeuSRenderer(None, sdf, dev, col, 8, 0, 0, 1, 0, impl="triton")
+    r2 = NeuSRenderer(None, sdf, dev, col, 8, 0, 1, 1, 0)
+    with pytest.raises(NotImplementedError):
+        r2.render(ro, ro, ro[:, :1], ro[:, :1], w=torch.zeros(1, 64))
+
+
+def test_shard_instances_is_a_partition():
+    from object_intrinsics_b200.parallel import shard_instances
+    for total in (1, 7, 32, 33):
+        for world in (1, 2, 4, 8):
+            got = [i for r in range(world) for i in shard_instances(total, world, r)]
+            assert got == list(range(total))
+            sizes = [len(shard_instances(total, world, r)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_instances(4, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from object_intrinsics_b200.parallel import aggregate_throughput, env_rank_world, rank_seed, shard_instances
+    assert env_rank_world() == (rank, rank, world)
+    mine = shard_instances(5, world, rank)                      # 5 instances over 2 ranks -> 3 + 2
+    units = len(mine) * 4096.0
+    secs = 0.5 if rank == 0 else 0.8
+    thr, total, tmax = aggregate_throughput(units, secs)
+    q.put((rank, list(mine), rank_seed(1234, rank), thr, total, tmax))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_sharding_and_aggregation():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 1, 2] and res[1][1] == [3, 4]
+    assert res[0][2] == 1234 and res[1][2] == 1235
+    for _, _, _, thr, total, tmax in res:                        # every rank sees the same aggregate
+        assert total == 5 * 4096.0 and tmax == 0.8 and abs(thr - total / 0.8) < 1e-9
