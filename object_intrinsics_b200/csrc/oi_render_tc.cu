@@ -106,6 +106,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_base;
 
+  // flag bit 1: de-phase odd CTAs by roughly half a tile-pair period so that the chip-wide live scratch
+  // footprint (which peaks at the end of every forward sweep) is spread out instead of peaking everywhere at once
+  if ((a.flags & 2) && (blockIdx.x & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < 60000) {
+    }
+  }
+
   if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {

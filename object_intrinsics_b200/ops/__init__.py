@@ -1,5 +1,9 @@
-"""sm_100a rewrites of the StyleGAN2 ops vendored by the reference (src/third_party/{stylesdf/op,ada/torch_utils/ops})."""
-from .fused_act import FusedLeakyReLU, fused_bias_act, fused_leaky_relu  # noqa: F401
-from .bias_act import bias_act  # noqa: F401
-from .upfirdn2d import (downsample2d, filter2d, setup_filter, upfirdn2d, upfirdn2d_native_layout,  # noqa: F401
-                        upsample2d)
+"""sm_100a rewrites of the StyleGAN2 ops vendored by the reference.
+
+Module layout mirrors the reference so that call sites read the same:
+  ops.upfirdn2d  <- src/third_party/ada/torch_utils/ops/upfirdn2d.py   (upfirdn2d, upsample2d, downsample2d, ...)
+                    + upfirdn2d_native_layout for src/third_party/stylesdf/op/upfirdn2d.py
+  ops.bias_act   <- src/third_party/ada/torch_utils/ops/bias_act.py    (bias_act)
+  ops.fused_act  <- src/third_party/stylesdf/op/fused_act.py           (fused_leaky_relu, FusedLeakyReLU)
+"""
+from . import bias_act, fused_act, upfirdn2d  # noqa: F401

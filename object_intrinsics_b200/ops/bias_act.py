@@ -41,7 +41,9 @@ def bias_act_raw(x, b, xref, yref, dy, grad: int, dim: int, act: int, alpha: flo
         return None if (t is None or t.numel() == 0) else t
 
     b, xref, yref, dy = opt(b), opt(xref), opt(yref), opt(dy)
-    if not x.is_non_overlapping_and_dense():
+    dense = x.is_contiguous() or (x.ndim == 4 and x.is_contiguous(memory_format=torch.channels_last)) or \
+        (x.ndim == 5 and x.is_contiguous(memory_format=torch.channels_last_3d))
+    if not dense:
         raise RuntimeError("x must be non-overlapping and dense")
     for name, t in (("xref", xref), ("yref", yref), ("dy", dy)):
         if t is not None and not (_dense_layout_ok(t, x) and t.dtype == x.dtype and t.device == x.device):

@@ -193,6 +193,8 @@ class NeuSRenderer:
         if perturb_overwrite >= 0:
             perturb = perturb_overwrite
         R = rays_o.shape[0]
+        if R % w.shape[0] != 0:                                                               # fields.py:55
+            raise ValueError(f"number of rays ({R}) must be a multiple of the number of instances ({w.shape[0]})")
         if t_rand is None and perturb > 0:
             t_rand = torch.rand([R, 1], device=rays_o.device) - 0.5                           # renderer.py:372
 
