@@ -186,6 +186,7 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, uint32_
 __device__ __forceinline__ void l2_discard_128(const void* p) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                              unsigned long long* bar) {

@@ -27,6 +27,7 @@ constexpr int kSubPanelBytes = 16384;
 constexpr float kWScale = 256.0f;        // weights are packed as 2^8 * W (see pack_weights_kernel)
 constexpr float kInvWScale = 1.0f / 256.0f;
 constexpr uint32_t kIdesc = tc::make_idesc_f16(128, 128);
+constexpr uint32_t kIdescHalf = tc::make_idesc_f16(128, 64);
 
 struct __align__(1024) TcSmem {
   unsigned char w[kTcStages][kPanelBytes];  // weight panels (192 KB)
@@ -35,12 +36,21 @@ struct __align__(1024) TcSmem {
   float4 head[kW];                          // 2^8 * (w_sigma[n], wc_grad[0..2][n])
   float4 rgbw[kW];                          // (W_rgb[0..2][n], 0)
   unsigned long long w_full[kTcStages], w_empty[kTcStages];
-  unsigned long long acc_full[2], a_ready[2];
+  unsigned long long acc_full[4], a_ready[2];   // acc_full[2*slot + column half]
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB per-CTA limit");
 
+// sin / cos of a FiLM pre-activation for the tensor-core epilogue.  OI_TC_SINCOS_REDUCE = 1: two-constant
+// Cody-Waite reduction before the MUFU approximations (as in the FFMA core).  0 (default): feed the MUFU unit
+// directly -- its input scaling x * (1/2pi) is an fp32 multiply, i.e. an absolute phase error of |x| * 6e-8 rad,
+// the same order as the fp32 rounding of the pre-activation itself (ulp(32) = 3.8e-6), and it saves four
+// instructions per element on a path that is bound by issue slots.
+#ifndef OI_TC_SINCOS_REDUCE
+#define OI_TC_SINCOS_REDUCE 0
+#endif
 __device__ __forceinline__ void sin_film(float x, float* s) {
+#if OI_TC_SINCOS_REDUCE
   const float kInv2Pi = 0.15915494309189535f;
   const float k2PiHi = 6.2831854820251465f;
   const float k2PiLo = -1.7484555314695172e-07f;
@@ -49,6 +59,17 @@ __device__ __forceinline__ void sin_film(float x, float* s) {
   float r = fmaf(k, -k2PiHi, x);
   r = fmaf(k, -k2PiLo, r);
   *s = __sinf(r);
+#else
+  *s = __sinf(x);
+#endif
+}
+__device__ __forceinline__ void sincos_tc(float x, float* s, float* c) {
+#if OI_TC_SINCOS_REDUCE
+  sincos_film(x, s, c);
+#else
+  *s = __sinf(x);
+  *c = __cosf(x);
+#endif
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -68,6 +89,21 @@ __device__ __forceinline__ void issue_layer_mmas(uint32_t acc, uint32_t a_hi, ui
   }
 }
 
+// One column half (N = 64 output channels) of a layer: the epilogue can start on channels 0..63 while the
+// tensor core still works on channels 64..127.
+__device__ __forceinline__ void issue_layer_mmas_half(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase, int h) {
+  const uint32_t row_off = (uint32_t)h * 64u * 128u;   // 64 rows of 128 bytes inside each 16 KB sub-panel
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int kb = k >> 2, ks = k & 3;
+    const uint64_t bhi = tc::make_desc_k_sw128(wbase + kb * kSubPanelBytes + row_off + ks * 32);
+    const uint64_t blo = tc::make_desc_k_sw128(wbase + 2 * kSubPanelBytes + kb * kSubPanelBytes + row_off + ks * 32);
+    tc::mma_ts(acc + h * 64, a_hi + k * 8, bhi, kIdescHalf, k > 0 ? 1u : 0u);
+    tc::mma_ts(acc + h * 64, a_lo + k * 8, bhi, kIdescHalf, 1u);
+    tc::mma_ts(acc + h * 64, a_hi + k * 8, blo, kIdescHalf, 1u);
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -84,10 +120,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       mbar_init(&sm.w_full[s], 1);
       mbar_init(&sm.w_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&sm.acc_full[t], 1);
-      mbar_init(&sm.a_ready[t], 128);
-    }
+    for (int t = 0; t < 2; ++t) mbar_init(&sm.a_ready[t], 128);
+    for (int t = 0; t < 4; ++t) mbar_init(&sm.acc_full[t], 1);
     mbar_fence_init();
   }
   if (warp == 8) {
@@ -135,23 +169,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     if (lane == 0) {
       int it = 0;
       uint32_t ar_phase[2] = {0u, 0u};
+      long long tw_w = 0, tw_a = 0;
+      const long long t_begin = clock64();
       for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
         const int n_active = (2 * pi + 1 < a.n_tiles) ? 2 : 1;
         for (int p = 0; p < NP; ++p, ++it) {
           const int stage = it % kTcStages;
-          mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
+          {
+            const long long t_ = clock64();
+            mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
+            tw_w += clock64() - t_;
+          }
           const uint32_t wbase = smem_u32(sm.w[stage]);
           for (int t = 0; t < n_active; ++t) {
-            mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
+            {
+              const long long t_ = clock64();
+              mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
+              tw_a += clock64() - t_;
+            }
             ar_phase[t] ^= 1u;
             tc::fence_after_thread_sync();
             const uint32_t acc = tmem_base + t * 256;
+            // NOTE: both column halves are committed together.  Committing half 0 early would let the epilogue
+            // overwrite the (in-place) TMEM A operand while the half-1 MMAs still read it.
             issue_layer_mmas(acc, acc + 128, acc + 192, wbase);
-            tc::mma_commit(&sm.acc_full[t]);
+            tc::mma_commit(&sm.acc_full[2 * t]);
           }
           tc::mma_commit(&sm.w_empty[stage]);
         }
       }
+      if ((a.flags & 4) && blockIdx.x == 0)
+        printf("[oi tc] mma thread: total %lld clk, waiting weights %lld, waiting A operands %lld\n",
+               clock64() - t_begin, tw_w, tw_a);
     }
   } else {
     // ===================== epilogue warps: thread <-> TMEM lane <-> sample point =====================
@@ -165,6 +214,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
                                              (size_t)t * (D + 1) * kW * 128) + m;
     const bool discard = (a.flags & 1) != 0 && (m & 7) == 0;
     uint32_t af_phase = 0u;
+    long long tw_fwd = 0, tw_rev = 0, tp_fwd = 0, tp_rev = 0, tp_col = 0;
+    const long long t_begin = clock64();
 #define OI_SLOT(slot, q) scr4[((size_t)(slot) * 32 + (q)) * 128]
 
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
@@ -179,6 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       }
       const PointCtx pc = point_prologue(a, inst, tin, m);
       named_bar_sync(1 + t, 128);
+      const long long t_tile = clock64();
 
       float sdf_acc = 0.f;
       // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
@@ -197,7 +249,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               const float2 f = fl[n];
               const float u = fmaf(w.z, pc.pz, fmaf(w.y, pc.py, w.x * pc.px));
               float cs;
-              sincos_film(fmaf(f.x, u, f.y), &s[e], &cs);
+              sincos_tc(fmaf(f.x, u, f.y), &s[e], &cs);
               cv[e] = f.x * kInvWScale * cs;
             }
             if (!a.coarse) OI_SLOT(0, c * 8 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
@@ -212,16 +264,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         mbar_arrive(&sm.a_ready[t]);
       }
       // ---------------- forward layers 1..D-1 ----------------
+      // The accumulator is drained in four 32-column chunks through two register buffers: the tcgen05.ld of
+      // chunk c+1 is in flight while chunk c goes through the FiLM epilogue.
       for (int l = 1; l < D; ++l) {
         const float2* fl = sm.film[t][l];
-        mbar_wait_sleep(&sm.acc_full[t], af_phase);
-        af_phase ^= 1u;
-        tc::fence_after_thread_sync();
         const bool last = (l == D - 1);
-#pragma unroll 1
+        {
+          const long long t_ = clock64();
+          mbar_wait_sleep(&sm.acc_full[2 * t], af_phase);
+          tw_fwd += clock64() - t_;
+          tc::fence_after_thread_sync();
+        }
+        af_phase ^= 1u;
+        uint32_t ub[2][32];
+        tc::tmem_ld32_async(acc, ub[0]);
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float u[32];
-          tc::tmem_ld32(acc + c * 32, u);
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld32_async(acc + (c + 1) * 32, ub[(c + 1) & 1]);
+          const uint32_t(&u)[32] = ub[c & 1];
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -231,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               const int n = c * 32 + q * 4 + e;
               const float2 f = fl[n];
               float cs;
-              sincos_film(fmaf(f.x, u[q * 4 + e], f.y), &s[e], &cs);
+              sincos_tc(fmaf(f.x, __uint_as_float(u[q * 4 + e]), f.y), &s[e], &cs);
               cv[e] = f.x * cs;
               if (last) sdf_acc = fmaf(sm.head[n].x, s[e], sdf_acc);
             }
@@ -251,6 +312,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
       const float sdf = sdf_acc * kInvWScale + cst[BlobLayout::kScalars + 0];
+      const long long t_fwd_end = clock64();
+      tp_fwd += t_fwd_end - t_tile;
       if (a.coarse) {
         if (pc.valid) a.sdf_coarse[(size_t)pc.ray * a.S + pc.si] = sdf;
         named_bar_sync(1 + t, 128);
@@ -262,11 +325,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         float4 csn[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(D - 1, q);
-        mbar_wait_sleep(&sm.acc_full[t], af_phase);
-        af_phase ^= 1u;
-        tc::fence_after_thread_sync();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          if (c == 0) {
+            const long long t_ = clock64();
+            mbar_wait_sleep(&sm.acc_full[2 * t], af_phase);
+            tw_rev += clock64() - t_;
+            tc::fence_after_thread_sync();
+          }
           float u[32];
           tc::tmem_ld32(acc + c * 32, u);
           float4 csc[8];
@@ -287,6 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           tc::tmem_st16(a_hi + c * 16, hi);
           tc::tmem_st16(a_lo + c * 16, lo);
         }
+        af_phase ^= 1u;
         tc::wait_st();
         tc::fence_before_thread_sync();
         mbar_arrive(&sm.a_ready[t]);
@@ -297,11 +364,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         float4 csn[8];   // one-chunk look-ahead of gamma*cos(arg_{l-1}), issued before the MMA wait
 #pragma unroll
         for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(l - 1, q);
-        mbar_wait_sleep(&sm.acc_full[t], af_phase);
-        af_phase ^= 1u;
-        tc::fence_after_thread_sync();
+        // pull the scratch lines of the NEXT reverse layer (and, near the end, the parked colour pre-activation)
+        // from DRAM into L2 two phases ahead of their use; one lane per 128-byte line
+        if ((m & 7) == 0) {
+          const int pf_slot = (l >= 2) ? (l - 2) : D;
+#pragma unroll 8
+          for (int q = 0; q < 32; ++q) l2_prefetch(&OI_SLOT(pf_slot, q));
+        }
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          if (c == 0) {
+            const long long t_ = clock64();
+            mbar_wait_sleep(&sm.acc_full[2 * t], af_phase);
+            tw_rev += clock64() - t_;
+            tc::fence_after_thread_sync();
+          }
           float u[32];
           tc::tmem_ld32(acc + c * 32, u);
           float4 csc[8];
@@ -339,6 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
             for (int q = 0; q < 8; ++q) l2_discard_128(&OI_SLOT(l - 1, c * 8 + q));
           }
         }
+        af_phase ^= 1u;
         if (l > 1) {
           tc::wait_st();
           tc::fence_before_thread_sync();
@@ -346,6 +424,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
       // ---------------- colour layer epilogue + rgb head ----------------
+      const long long t_rev_end = clock64();
+      tp_rev += t_rev_end - t_fwd_end;
       float rgb[3] = {0.f, 0.f, 0.f};
       {
         const float2* fl = sm.film[t][OI_MAX_DEPTH];
@@ -387,8 +467,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
       point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
+      tp_col += clock64() - t_rev_end;
       named_bar_sync(1 + t, 128);  // film table of this slot may be overwritten by the next tile now
     }
+    if ((a.flags & 4) && blockIdx.x == 0 && (m == 0 || m == 127))
+      printf("[oi tc] slot %d lane %d: total %lld clk | forward %lld (waiting MMA %lld) | colour-park+reverse %lld "
+             "(waiting MMA %lld) | colour epilogue+tail %lld\n",
+             t, m, clock64() - t_begin, tp_fwd, tw_fwd, tp_rev, tw_rev, tp_col);
 #undef OI_SLOT
   }
 
