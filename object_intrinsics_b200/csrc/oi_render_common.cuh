@@ -16,7 +16,8 @@ struct PointCtx {
 
 // Sample position of point `p_local` of tile `tin` of instance `inst` (renderer.py:359-373, 219-228; coarse pass
 // :391).  Also writes the position-only outputs (pts, mid_z_vals, pts_norm, inside_sphere, z_vals).
-__device__ __forceinline__ PointCtx point_prologue(const RenderKArgs& a, int inst, int tin, int p_local) {
+__device__ __forceinline__ PointCtx point_prologue(const RenderKArgs& a, int inst, int tin, int p_local,
+                                                   bool write_outputs = true) {
   PointCtx c;
   const int p = tin * 128 + p_local;
   c.valid = p < a.pts_per_inst;
@@ -60,7 +61,7 @@ __device__ __forceinline__ PointCtx point_prologue(const RenderKArgs& a, int ins
   c.px = ox + c.dx * zp;
   c.py = oy + c.dy * zp;
   c.pz = oz + c.dz * zp;
-  if (c.valid && !a.coarse) {
+  if (c.valid && !a.coarse && write_outputs) {
     const size_t gp = (size_t)ray * a.S + si;
     const float nrm = sqrtf(c.px * c.px + c.py * c.py + c.pz * c.pz);
     if (a.pts) {

@@ -20,7 +20,9 @@ namespace oi {
 
 namespace {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 576;            // 16 epilogue warps + TMA producer + MMA issuer
+constexpr int kEpiThreadsPerSlot = 256;     // 8 warps per tile slot
+constexpr int kProducerWarp = 16, kMmaWarp = 17;
 constexpr int kTcStages = 3;
 constexpr int kPanelBytes = 65536;
 constexpr int kSubPanelBytes = 16384;
@@ -36,7 +38,8 @@ struct __align__(1024) TcSmem {
   float4 head[kW];                          // 2^8 * (w_sigma[n], wc_grad[0..2][n])
   float4 rgbw[kW];                          // (W_rgb[0..2][n], 0)
   unsigned long long w_full[kTcStages], w_empty[kTcStages];
-  unsigned long long acc_full[4], a_ready[2];   // acc_full[2*slot + column half]
+  float xch[2][128][8];                     // per slot / point: partial sums exchanged between the column halves
+  unsigned long long acc_full[2], a_ready[2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB per-CTA limit");
@@ -120,11 +123,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       mbar_init(&sm.w_full[s], 1);
       mbar_init(&sm.w_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) mbar_init(&sm.a_ready[t], 128);
-    for (int t = 0; t < 4; ++t) mbar_init(&sm.acc_full[t], 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sm.a_ready[t], kEpiThreadsPerSlot);
+      mbar_init(&sm.acc_full[t], 1);
+    }
     mbar_fence_init();
   }
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     tc::tmem_alloc(&sm.tmem_base, 512);
     tc::tmem_relinquish();
   }
@@ -140,15 +145,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_base;
 
-  // flag bit 1: de-phase odd CTAs by roughly half a tile-pair period so that the chip-wide live scratch
-  // footprint (which peaks at the end of every forward sweep) is spread out instead of peaking everywhere at once
-  if ((a.flags & 2) && (blockIdx.x & 1)) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < 60000) {
-    }
-  }
-
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
@@ -164,59 +161,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int it = 0;
       uint32_t ar_phase[2] = {0u, 0u};
-      long long tw_w = 0, tw_a = 0;
-      const long long t_begin = clock64();
       for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
         const int n_active = (2 * pi + 1 < a.n_tiles) ? 2 : 1;
         for (int p = 0; p < NP; ++p, ++it) {
           const int stage = it % kTcStages;
-          {
-            const long long t_ = clock64();
-            mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
-            tw_w += clock64() - t_;
-          }
+          mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
           const uint32_t wbase = smem_u32(sm.w[stage]);
           for (int t = 0; t < n_active; ++t) {
-            {
-              const long long t_ = clock64();
-              mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
-              tw_a += clock64() - t_;
-            }
+            mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
             ar_phase[t] ^= 1u;
             tc::fence_after_thread_sync();
             const uint32_t acc = tmem_base + t * 256;
-            // NOTE: both column halves are committed together.  Committing half 0 early would let the epilogue
-            // overwrite the (in-place) TMEM A operand while the half-1 MMAs still read it.
+            // The whole layer is committed at once: the A operand is overwritten in place by the epilogue, so
+            // the epilogue must not start before every MMA that reads it has completed.
             issue_layer_mmas(acc, acc + 128, acc + 192, wbase);
-            tc::mma_commit(&sm.acc_full[2 * t]);
+            tc::mma_commit(&sm.acc_full[t]);
           }
           tc::mma_commit(&sm.w_empty[stage]);
         }
       }
-      if ((a.flags & 4) && blockIdx.x == 0)
-        printf("[oi tc] mma thread: total %lld clk, waiting weights %lld, waiting A operands %lld\n",
-               clock64() - t_begin, tw_w, tw_a);
     }
   } else {
-    // ===================== epilogue warps: thread <-> TMEM lane <-> sample point =====================
-    const int t = warp >> 2;                 // tile slot
-    const int m = tid & 127;                 // point in tile == TMEM lane
+    // ===================== epilogue warps =====================
+    // 16 warps: slot t = warp / 8 (tile of the pair), column half h = (warp / 4) % 2, TMEM lane quarter = warp % 4.
+    // Thread (m, h) owns channels [64h, 64h+64) of sample point m of its tile: four 16-column chunks per layer.
+    const int t = warp >> 3;
+    const int h = (warp >> 2) & 1;
+    const int m = (warp & 3) * 32 + lane;
+    const int sub = tid & (kEpiThreadsPerSlot - 1);
+    const int n0 = h * 64;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t acc = tmem_base + t * 256 + lane_field;
-    const uint32_t a_hi = acc + 128, a_lo = acc + 192;
-    // scratch of this tile slot: (D+1) slots of [32 channel-quads][128 points] float4
+    const uint32_t acc = tmem_base + t * 256 + lane_field + n0;          // my 64 accumulator columns
+    const uint32_t a_hi = tmem_base + t * 256 + lane_field + 128 + h * 32;  // my 32 packed A_hi columns
+    const uint32_t a_lo = a_hi + 64;
+    // scratch of this tile slot: (D+1) slots of [32 channel-quads][128 points] float4; mine: quads 16h..16h+15
     float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
-                                             (size_t)t * (D + 1) * kW * 128) + m;
+                                             (size_t)t * (D + 1) * kW * 128) + (size_t)(h * 16) * 128 + m;
     const bool discard = (a.flags & 1) != 0 && (m & 7) == 0;
     uint32_t af_phase = 0u;
-    long long tw_fwd = 0, tw_rev = 0, tp_fwd = 0, tp_rev = 0, tp_col = 0;
-    const long long t_begin = clock64();
 #define OI_SLOT(slot, q) scr4[((size_t)(slot) * 32 + (q)) * 128]
+#define OI_A_READY()               \
+  do {                             \
+    tc::wait_st();                 \
+    tc::fence_before_thread_sync(); \
+    mbar_arrive(&sm.a_ready[t]);   \
+  } while (0)
+#define OI_WAIT_ACC()                                \
+  do {                                               \
+    mbar_wait_sleep(&sm.acc_full[t], af_phase);      \
+    af_phase ^= 1u;                                  \
+    tc::fence_after_thread_sync();                   \
+  } while (0)
 
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
       const int tile = 2 * pi + t;
@@ -226,185 +226,177 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       {  // FiLM table of this tile's instance
         const float2* src = reinterpret_cast<const float2*>(a.film_tc) + (size_t)inst * kFilm * kW;
         float2* dst = &sm.film[t][0][0];
-        for (int i = m; i < kFilm * kW; i += 128) dst[i] = src[i];
+        for (int i = sub; i < kFilm * kW; i += kEpiThreadsPerSlot) dst[i] = src[i];
       }
-      const PointCtx pc = point_prologue(a, inst, tin, m);
-      named_bar_sync(1 + t, 128);
-      const long long t_tile = clock64();
+      float px, py, pz;
+      {
+        const PointCtx pc = point_prologue(a, inst, tin, m, h == 0);
+        px = pc.px;
+        py = pc.py;
+        pz = pc.pz;
+      }
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);
 
       float sdf_acc = 0.f;
       // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
       {
-        const float2* fl = sm.film[t][0];
+        const float2* fl = sm.film[t][0] + n0;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          uint32_t hi[16], lo[16];
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             float s[4], cv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int n = c * 32 + q * 4 + e;
-              const float4 w = sm.w0[n];
-              const float2 f = fl[n];
-              const float u = fmaf(w.z, pc.pz, fmaf(w.y, pc.py, w.x * pc.px));
+              const int j = c * 16 + q * 4 + e;
+              const float4 w = sm.w0[n0 + j];
+              const float2 f = fl[j];
+              const float u = fmaf(w.z, pz, fmaf(w.y, py, w.x * px));
               float cs;
               sincos_tc(fmaf(f.x, u, f.y), &s[e], &cs);
               cv[e] = f.x * kInvWScale * cs;
             }
-            if (!a.coarse) OI_SLOT(0, c * 8 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            if (!a.coarse) OI_SLOT(0, c * 4 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
             tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
             tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
-          tc::tmem_st16(a_hi + c * 16, hi);
-          tc::tmem_st16(a_lo + c * 16, lo);
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
         }
-        tc::wait_st();
-        tc::fence_before_thread_sync();
-        mbar_arrive(&sm.a_ready[t]);
+        OI_A_READY();
       }
-      // ---------------- forward layers 1..D-1 ----------------
-      // The accumulator is drained in four 32-column chunks through two register buffers: the tcgen05.ld of
-      // chunk c+1 is in flight while chunk c goes through the FiLM epilogue.
+      // ---------------- forward layers 1..D-1: accumulator chunk c+1 is in flight while chunk c is processed ----
       for (int l = 1; l < D; ++l) {
-        const float2* fl = sm.film[t][l];
+        const float2* fl = sm.film[t][l] + n0;
         const bool last = (l == D - 1);
-        {
-          const long long t_ = clock64();
-          mbar_wait_sleep(&sm.acc_full[2 * t], af_phase);
-          tw_fwd += clock64() - t_;
-          tc::fence_after_thread_sync();
-        }
-        af_phase ^= 1u;
-        uint32_t ub[2][32];
-        tc::tmem_ld32_async(acc, ub[0]);
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           tc::wait_ld();
-          if (c < 3) tc::tmem_ld32_async(acc + (c + 1) * 32, ub[(c + 1) & 1]);
-          const uint32_t(&u)[32] = ub[c & 1];
-          uint32_t hi[16], lo[16];
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             float s[4], cv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int n = c * 32 + q * 4 + e;
-              const float2 f = fl[n];
+              const int j = c * 16 + q * 4 + e;
+              const float2 f = fl[j];
               float cs;
               sincos_tc(fmaf(f.x, __uint_as_float(u[q * 4 + e]), f.y), &s[e], &cs);
               cv[e] = f.x * cs;
-              if (last) sdf_acc = fmaf(sm.head[n].x, s[e], sdf_acc);
+              if (last) sdf_acc = fmaf(sm.head[n0 + j].x, s[e], sdf_acc);
             }
-            if (!a.coarse) OI_SLOT(l, c * 8 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            if (!a.coarse) OI_SLOT(l, c * 4 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
             tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
             tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
           if (!(last && a.coarse)) {
-            tc::tmem_st16(a_hi + c * 16, hi);
-            tc::tmem_st16(a_lo + c * 16, lo);
+            tc::tmem_st8(a_hi + c * 8, hi);
+            tc::tmem_st8(a_lo + c * 8, lo);
           }
         }
-        if (!(last && a.coarse)) {
-          tc::wait_st();
-          tc::fence_before_thread_sync();
-          mbar_arrive(&sm.a_ready[t]);
-        }
+        if (!(last && a.coarse)) OI_A_READY();
       }
-      const float sdf = sdf_acc * kInvWScale + cst[BlobLayout::kScalars + 0];
-      const long long t_fwd_end = clock64();
-      tp_fwd += t_fwd_end - t_tile;
+      float* xch = &sm.xch[t][m][0];
       if (a.coarse) {
-        if (pc.valid) a.sdf_coarse[(size_t)pc.ray * a.S + pc.si] = sdf;
-        named_bar_sync(1 + t, 128);
+        // sdf = sum of the two column halves
+        if (h == 1) xch[0] = sdf_acc;
+        named_bar_sync(1 + t, kEpiThreadsPerSlot);
+        if (h == 0) {
+          const PointCtx pc = point_prologue(a, inst, tin, m, false);
+          if (pc.valid)
+            a.sdf_coarse[(size_t)pc.ray * a.S + pc.si] = (sdf_acc + xch[0]) * kInvWScale + cst[BlobLayout::kScalars + 0];
+        }
+        named_bar_sync(1 + t, kEpiThreadsPerSlot);
         continue;
       }
       // ---------------- colour layer, feature part: park 2^8 * W_c[:, :128] h in scratch slot D;
       //                  start the reverse sweep: t_{D-1} = w_sigma * gamma cos(arg_{D-1}) ----------------
       {
-        float4 csn[8];
+        float4 csn[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(D - 1, q);
-#pragma unroll 1
+        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(D - 1, q);
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (c == 0) {
-            const long long t_ = clock64();
-            mbar_wait_sleep(&sm.acc_full[2 * t], af_phase);
-            tw_rev += clock64() - t_;
-            tc::fence_after_thread_sync();
-          }
-          float u[32];
-          tc::tmem_ld32(acc + c * 32, u);
-          float4 csc[8];
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          float4 csc[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) csc[q] = csn[q];
+          for (int q = 0; q < 4; ++q) csc[q] = csn[q];
           if (c < 3) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(D - 1, (c + 1) * 8 + q);
+            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(D - 1, (c + 1) * 4 + q);
           }
-          uint32_t hi[16], lo[16];
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            OI_SLOT(D, c * 8 + q) = make_float4(u[q * 4], u[q * 4 + 1], u[q * 4 + 2], u[q * 4 + 3]);
-            const int n = c * 32 + q * 4;
+          for (int q = 0; q < 4; ++q) {
+            OI_SLOT(D, c * 4 + q) = make_float4(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1]),
+                                                 __uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3]));
+            const int n = n0 + c * 16 + q * 4;
             tc::split2(sm.head[n].x * csc[q].x, sm.head[n + 1].x * csc[q].y, hi[2 * q], lo[2 * q]);
             tc::split2(sm.head[n + 2].x * csc[q].z, sm.head[n + 3].x * csc[q].w, hi[2 * q + 1], lo[2 * q + 1]);
           }
-          tc::tmem_st16(a_hi + c * 16, hi);
-          tc::tmem_st16(a_lo + c * 16, lo);
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
         }
-        af_phase ^= 1u;
-        tc::wait_st();
-        tc::fence_before_thread_sync();
-        mbar_arrive(&sm.a_ready[t]);
+        OI_A_READY();
       }
       // ---------------- reverse sweep l = D-1 .. 1 ----------------
       float gx = 0.f, gy = 0.f, gz = 0.f;
       for (int l = D - 1; l >= 1; --l) {
-        float4 csn[8];   // one-chunk look-ahead of gamma*cos(arg_{l-1}), issued before the MMA wait
+        float4 csn[4];   // one-chunk look-ahead of gamma*cos(arg_{l-1}), issued before the MMA wait
 #pragma unroll
-        for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(l - 1, q);
+        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(l - 1, q);
         // pull the scratch lines of the NEXT reverse layer (and, near the end, the parked colour pre-activation)
-        // from DRAM into L2 two phases ahead of their use; one lane per 128-byte line
+        // from DRAM into L2 a whole phase ahead of their use; one lane per 128-byte line
         if ((m & 7) == 0) {
           const int pf_slot = (l >= 2) ? (l - 2) : D;
-#pragma unroll 8
-          for (int q = 0; q < 32; ++q) l2_prefetch(&OI_SLOT(pf_slot, q));
+#pragma unroll 4
+          for (int q = 0; q < 16; ++q) l2_prefetch(&OI_SLOT(pf_slot, q));
         }
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (c == 0) {
-            const long long t_ = clock64();
-            mbar_wait_sleep(&sm.acc_full[2 * t], af_phase);
-            tw_rev += clock64() - t_;
-            tc::fence_after_thread_sync();
-          }
-          float u[32];
-          tc::tmem_ld32(acc + c * 32, u);
-          float4 csc[8];
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) csc[q] = csn[q];
+        for (int c = 0; c < 4; ++c) {
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          float4 csc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) csc[q] = csn[q];
           if (c < 3) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) csn[q] = OI_SLOT(l - 1, (c + 1) * 8 + q);
+            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(l - 1, (c + 1) * 4 + q);
           }
           if (l > 1) {
-            uint32_t hi[16], lo[16];
+            uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              tc::split2(u[q * 4] * csc[q].x, u[q * 4 + 1] * csc[q].y, hi[2 * q], lo[2 * q]);
-              tc::split2(u[q * 4 + 2] * csc[q].z, u[q * 4 + 3] * csc[q].w, hi[2 * q + 1], lo[2 * q + 1]);
+            for (int q = 0; q < 4; ++q) {
+              tc::split2(__uint_as_float(u[q * 4]) * csc[q].x, __uint_as_float(u[q * 4 + 1]) * csc[q].y, hi[2 * q],
+                         lo[2 * q]);
+              tc::split2(__uint_as_float(u[q * 4 + 2]) * csc[q].z, __uint_as_float(u[q * 4 + 3]) * csc[q].w,
+                         hi[2 * q + 1], lo[2 * q + 1]);
             }
-            tc::tmem_st16(a_hi + c * 16, hi);
-            tc::tmem_st16(a_lo + c * 16, lo);
-          } else {  // grad_x sdf = W_0^T t_0
+            tc::tmem_st8(a_hi + c * 8, hi);
+            tc::tmem_st8(a_lo + c * 8, lo);
+          } else {  // grad_x sdf = W_0^T t_0 (this thread's 64 channels)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float tv[4] = {u[q * 4] * csc[q].x, u[q * 4 + 1] * csc[q].y, u[q * 4 + 2] * csc[q].z,
-                                   u[q * 4 + 3] * csc[q].w};
+            for (int q = 0; q < 4; ++q) {
+              const float tv[4] = {__uint_as_float(u[q * 4]) * csc[q].x, __uint_as_float(u[q * 4 + 1]) * csc[q].y,
+                                   __uint_as_float(u[q * 4 + 2]) * csc[q].z, __uint_as_float(u[q * 4 + 3]) * csc[q].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float4 w = sm.w0[c * 32 + q * 4 + e];
+                const float4 w = sm.w0[n0 + c * 16 + q * 4 + e];
                 gx = fmaf(w.x, tv[e], gx);
                 gy = fmaf(w.y, tv[e], gy);
                 gz = fmaf(w.z, tv[e], gz);
@@ -413,48 +405,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           }
           if (discard) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) l2_discard_128(&OI_SLOT(l - 1, c * 8 + q));
+            for (int q = 0; q < 4; ++q) l2_discard_128(&OI_SLOT(l - 1, c * 4 + q));
           }
         }
-        af_phase ^= 1u;
-        if (l > 1) {
-          tc::wait_st();
-          tc::fence_before_thread_sync();
-          mbar_arrive(&sm.a_ready[t]);
-        }
+        if (l > 1) OI_A_READY();
       }
-      // ---------------- colour layer epilogue + rgb head ----------------
-      const long long t_rev_end = clock64();
-      tp_rev += t_rev_end - t_fwd_end;
+      // ---------------- combine the two column halves: sdf and grad_x sdf ----------------
+      xch[h * 4 + 0] = sdf_acc;
+      xch[h * 4 + 1] = gx;
+      xch[h * 4 + 2] = gy;
+      xch[h * 4 + 3] = gz;
+      float4 ucn[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT(D, q);
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);
+      {
+        const int o = (h ^ 1) * 4;
+        sdf_acc += xch[o + 0];
+        gx += xch[o + 1];
+        gy += xch[o + 2];
+        gz += xch[o + 3];
+      }
+      const float sdf = sdf_acc * kInvWScale + cst[BlobLayout::kScalars + 0];
+      // ---------------- colour layer epilogue + rgb head (this thread's 64 channels) ----------------
       float rgb[3] = {0.f, 0.f, 0.f};
       {
-        const float2* fl = sm.film[t][OI_MAX_DEPTH];
-        float4 ucn[8];
+        const float2* fl = sm.film[t][OI_MAX_DEPTH] + n0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ucn[q] = OI_SLOT(D, q);
-#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          float4 ucc[8];
+          float4 ucc[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) ucc[q] = ucn[q];
+          for (int q = 0; q < 4; ++q) ucc[q] = ucn[q];
           if (c < 3) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) ucn[q] = OI_SLOT(D, (c + 1) * 8 + q);
+            for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT(D, (c + 1) * 4 + q);
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             const float uv[4] = {ucc[q].x, ucc[q].y, ucc[q].z, ucc[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int n = c * 32 + q * 4 + e;
-              const float4 hd = sm.head[n];
-              const float2 f = fl[n];
+              const int j = c * 16 + q * 4 + e;
+              const float4 hd = sm.head[n0 + j];
+              const float2 f = fl[j];
               float pre = fmaf(hd.y, gx, uv[e]);
               pre = fmaf(hd.z, gy, pre);
               pre = fmaf(hd.w, gz, pre);
               float s;
               sin_film(fmaf(f.x, pre, f.y), &s);
-              const float4 rw = sm.rgbw[n];
+              const float4 rw = sm.rgbw[n0 + j];
               rgb[0] = fmaf(rw.x, s, rgb[0]);
               rgb[1] = fmaf(rw.y, s, rgb[1]);
               rgb[2] = fmaf(rw.z, s, rgb[2]);
@@ -462,24 +461,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           }
           if (discard) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) l2_discard_128(&OI_SLOT(D, c * 8 + q));
+            for (int q = 0; q < 4; ++q) l2_discard_128(&OI_SLOT(D, c * 4 + q));
           }
         }
       }
-      point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
-      tp_col += clock64() - t_rev_end;
-      named_bar_sync(1 + t, 128);  // film table of this slot may be overwritten by the next tile now
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);   // everybody has read the first exchange
+      if (h == 1) {
+        xch[0] = rgb[0];
+        xch[1] = rgb[1];
+        xch[2] = rgb[2];
+      }
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);
+      if (h == 0) {
+        rgb[0] += xch[0];
+        rgb[1] += xch[1];
+        rgb[2] += xch[2];
+        const PointCtx pc = point_prologue(a, inst, tin, m, false);
+        point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
+      }
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);  // film table / exchange buffer of this slot may be reused now
     }
-    if ((a.flags & 4) && blockIdx.x == 0 && (m == 0 || m == 127))
-      printf("[oi tc] slot %d lane %d: total %lld clk | forward %lld (waiting MMA %lld) | colour-park+reverse %lld "
-             "(waiting MMA %lld) | colour epilogue+tail %lld\n",
-             t, m, clock64() - t_begin, tp_fwd, tw_fwd, tp_rev, tw_rev, tp_col);
 #undef OI_SLOT
+#undef OI_A_READY
+#undef OI_WAIT_ACC
   }
 
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == kProducerWarp) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
