@@ -187,7 +187,10 @@ __global__ void film_kernel(const float* __restrict__ blob, int depth, const flo
   // accumulator of the 2^8-scaled weight panels (layer 0 runs on the FMA pipe, unscaled)
   float2* tc_tab = reinterpret_cast<float2*>(film + (size_t)gridDim.y * kFilm * 2 * kW);
   const float bias = blob[L.const_off + BlobLayout::kBias + l * kW + n];
-  tc_tab[((size_t)inst * kFilm + l) * kW + n] = make_float2(l == 0 ? gamma : gamma * (1.0f / 256.0f), fmaf(gamma, bias, beta));
+  // pair layout: [gamma'_{2p}, gamma'_{2p+1}, delta_{2p}, delta_{2p+1}] so that one 16-byte load feeds an FFMA2
+  float* row = reinterpret_cast<float*>(tc_tab) + ((size_t)inst * kFilm + l) * kW * 2;
+  row[(n >> 1) * 4 + (n & 1)] = (l == 0) ? gamma : gamma * (1.0f / 256.0f);
+  row[(n >> 1) * 4 + 2 + (n & 1)] = fmaf(gamma, bias, beta);
 }
 
 // ---------------------------------------------------------------------------------------------------

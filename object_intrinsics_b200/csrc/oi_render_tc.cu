@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       float sdf_acc = 0.f;
       // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
       {
-        const float2* fl = sm.film[t][0] + n0;
+        const float4* fl = reinterpret_cast<const float4*>(sm.film[t][0]) + n0 / 2;   // (g0, g1, d0, d1) per pair
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t hi[8], lo[8];
@@ -248,14 +248,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           for (int q = 0; q < 4; ++q) {
             float s[4], cv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 4; e += 2) {
               const int j = c * 16 + q * 4 + e;
-              const float4 w = sm.w0[n0 + j];
-              const float2 f = fl[j];
-              const float u = fmaf(w.z, pz, fmaf(w.y, py, w.x * px));
-              float cs;
-              sincos_tc(fmaf(f.x, u, f.y), &s[e], &cs);
-              cv[e] = f.x * kInvWScale * cs;
+              const float4 w0 = sm.w0[n0 + j], w1 = sm.w0[n0 + j + 1];
+              const float4 f = fl[j >> 1];
+              const float2 u = make_float2(fmaf(w0.z, pz, fmaf(w0.y, py, w0.x * px)),
+                                           fmaf(w1.z, pz, fmaf(w1.y, py, w1.x * px)));
+              const float2 arg = tc::fma2(make_float2(f.x, f.y), u, make_float2(f.z, f.w));
+              float c0, c1;
+              sincos_tc(arg.x, &s[e], &c0);
+              sincos_tc(arg.y, &s[e + 1], &c1);
+              const float2 cvp = tc::mul2(make_float2(f.x * kInvWScale, f.y * kInvWScale), make_float2(c0, c1));
+              cv[e] = cvp.x;
+              cv[e + 1] = cvp.y;
             }
             if (!a.coarse) OI_SLOT(0, c * 4 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
             tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       }
       // ---------------- forward layers 1..D-1: accumulator chunk c+1 is in flight while chunk c is processed ----
       for (int l = 1; l < D; ++l) {
-        const float2* fl = sm.film[t][l] + n0;
+        const float4* fl = reinterpret_cast<const float4*>(sm.film[t][l]) + n0 / 2;
         const bool last = (l == D - 1);
         OI_WAIT_ACC();
         uint32_t ub[2][16];
@@ -283,13 +288,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           for (int q = 0; q < 4; ++q) {
             float s[4], cv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 4; e += 2) {
               const int j = c * 16 + q * 4 + e;
-              const float2 f = fl[j];
-              float cs;
-              sincos_tc(fmaf(f.x, __uint_as_float(u[q * 4 + e]), f.y), &s[e], &cs);
-              cv[e] = f.x * cs;
-              if (last) sdf_acc = fmaf(sm.head[n0 + j].x, s[e], sdf_acc);
+              const float4 f = fl[j >> 1];
+              const float2 arg = tc::fma2(make_float2(f.x, f.y),
+                                          make_float2(__uint_as_float(u[q * 4 + e]), __uint_as_float(u[q * 4 + e + 1])),
+                                          make_float2(f.z, f.w));
+              float c0, c1;
+              sincos_tc(arg.x, &s[e], &c0);
+              sincos_tc(arg.y, &s[e + 1], &c1);
+              const float2 cvp = tc::mul2(make_float2(f.x, f.y), make_float2(c0, c1));
+              cv[e] = cvp.x;
+              cv[e + 1] = cvp.y;
+              if (last) {
+                sdf_acc = fmaf(sm.head[n0 + j].x, s[e], sdf_acc);
+                sdf_acc = fmaf(sm.head[n0 + j + 1].x, s[e + 1], sdf_acc);
+              }
             }
             if (!a.coarse) OI_SLOT(l, c * 4 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
             tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
@@ -382,10 +396,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              tc::split2(__uint_as_float(u[q * 4]) * csc[q].x, __uint_as_float(u[q * 4 + 1]) * csc[q].y, hi[2 * q],
-                         lo[2 * q]);
-              tc::split2(__uint_as_float(u[q * 4 + 2]) * csc[q].z, __uint_as_float(u[q * 4 + 3]) * csc[q].w,
-                         hi[2 * q + 1], lo[2 * q + 1]);
+              const float2 t01 = tc::mul2(make_float2(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1])),
+                                          make_float2(csc[q].x, csc[q].y));
+              const float2 t23 = tc::mul2(make_float2(__uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3])),
+                                          make_float2(csc[q].z, csc[q].w));
+              tc::split2(t01.x, t01.y, hi[2 * q], lo[2 * q]);
+              tc::split2(t23.x, t23.y, hi[2 * q + 1], lo[2 * q + 1]);
             }
             tc::tmem_st8(a_hi + c * 8, hi);
             tc::tmem_st8(a_lo + c * 8, lo);
@@ -430,7 +446,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       // ---------------- colour layer epilogue + rgb head (this thread's 64 channels) ----------------
       float rgb[3] = {0.f, 0.f, 0.f};
       {
-        const float2* fl = sm.film[t][OI_MAX_DEPTH] + n0;
+        const float* flc = reinterpret_cast<const float*>(sm.film[t][OI_MAX_DEPTH]) + n0 * 2;   // pair layout
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float4 ucc[4];
@@ -447,7 +463,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
             for (int e = 0; e < 4; ++e) {
               const int j = c * 16 + q * 4 + e;
               const float4 hd = sm.head[n0 + j];
-              const float2 f = fl[j];
+              const float2 f = make_float2(flc[(j >> 1) * 4 + (j & 1)], flc[(j >> 1) * 4 + 2 + (j & 1)]);
               float pre = fmaf(hd.y, gx, uv[e]);
               pre = fmaf(hd.z, gy, pre);
               pre = fmaf(hd.w, gz, pre);
