@@ -224,6 +224,51 @@ typedef struct OiFusedBiasActDesc {
 } OiFusedBiasActDesc;
 int oi_fused_bias_act(const OiFusedBiasActDesc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Callers either side of the render path.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Generator.gen_rays_at + build_rays (+ near_far_from_sphere when near/far are given)
+ * (src/models/generator.py:255-279, 317-333, 336-342).  4x4 matrices are row-major. */
+typedef struct OiGenRaysDesc {
+  int32_t n_instances, resolution, scene_resolution, reserved;
+  float cam_dist, reserved_f;
+  const float* b2w;            /* [bs,4,4] box -> world */
+  const float* c2b;            /* [bs,4,4] camera -> box (= w2b @ c2w, generator.py:73) */
+  const float* w2c;            /* [4,4] camera.w2c */
+  const float* intrinsics_inv; /* [4,4] camera.intrinsics_inv */
+  float* rays_o;               /* [bs,P,P,3] (materialised; the reference returns a stride-0 expand) */
+  float* rays_d;               /* [bs,P,P,3] */
+  float* x_offset;             /* [bs] or NULL */
+  float* y_offset;             /* [bs] or NULL */
+  float* near;                 /* [bs*P*P,1] or NULL */
+  float* far;                  /* [bs*P*P,1] or NULL */
+} OiGenRaysDesc;
+int oi_gen_rays(const OiGenRaysDesc* desc, void* stream);
+
+/* Generator.render_maps with the directional Phong light (src/models/generator.py:80-174;
+ * src/models/lighting.py:61-76,94-119,126-225).  Inputs are the renderer's outputs; every output map is
+ * [bs, C, P, P] (C = 3 or 1) and may be NULL. */
+typedef struct OiRenderMapsDesc {
+  int32_t n_rays, rays_per_instance, n_samples, reserved;
+  float shininess, reserved_f;
+  float ambient_color[3], diffuse_color[3], specular_color[3], pad;
+  const float* weights;     /* [R,S] */
+  const float* gradients;   /* [R,S,3] */
+  const float* raw_color;   /* [R,S,3] */
+  const float* pts;         /* [R,S,3] */
+  const float* mid_z_vals;  /* [R,S] or NULL (z_map / z_min) */
+  const float* weight_sum;  /* [R,1] */
+  const float* color_fine;  /* [R,3] */
+  const float* rays_o;      /* [R,3] camera position per ray (box frame) */
+  const float* light_dir;   /* [bs,3] light direction in each box frame (lighting.py:115-119) */
+  const float* bg_color;    /* [bs,3] */
+  float *image, *image_no_bg, *mask, *shading_map, *color_map, *weight_sum_map;
+  float *amb_shading_map, *diff_shading_map, *normal_map, *no_specular_map, *specular_map, *z_map;
+  float* z_min_per_ray;     /* [R] min_s mid_z (reduced per instance by the caller) or NULL */
+} OiRenderMapsDesc;
+int oi_render_maps(const OiRenderMapsDesc* desc, void* stream);
+
 /* Self-test of the tcgen05 building blocks: d[128,128] = a[128,128] * B^T through the split-fp16 UMMA path.
  * B = b[128,128] ([n][k] row-major) when packed_weights is NULL, else panel `panel` of the packed blob
  * (order: forward l=1..D-1, colour features, reverse l=D-1..1; each is 2^8 * W in [n][k] orientation). */

@@ -80,9 +80,32 @@ class OiFusedBiasActDesc(C.Structure):
     ]
 
 
+class OiGenRaysDesc(C.Structure):
+    _fields_ = [
+        ("n_instances", C.c_int32), ("resolution", C.c_int32), ("scene_resolution", C.c_int32), ("reserved", C.c_int32),
+        ("cam_dist", C.c_float), ("reserved_f", C.c_float),
+        ("b2w", f32p), ("c2b", f32p), ("w2c", f32p), ("intrinsics_inv", f32p),
+        ("rays_o", f32p), ("rays_d", f32p), ("x_offset", f32p), ("y_offset", f32p), ("near", f32p), ("far", f32p),
+    ]
+
+
+class OiRenderMapsDesc(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int32), ("rays_per_instance", C.c_int32), ("n_samples", C.c_int32), ("reserved", C.c_int32),
+        ("shininess", C.c_float), ("reserved_f", C.c_float),
+        ("ambient_color", C.c_float * 3), ("diffuse_color", C.c_float * 3), ("specular_color", C.c_float * 3),
+        ("pad", C.c_float),
+        ("weights", f32p), ("gradients", f32p), ("raw_color", f32p), ("pts", f32p), ("mid_z_vals", f32p),
+        ("weight_sum", f32p), ("color_fine", f32p), ("rays_o", f32p), ("light_dir", f32p), ("bg_color", f32p),
+        ("image", f32p), ("image_no_bg", f32p), ("mask", f32p), ("shading_map", f32p), ("color_map", f32p),
+        ("weight_sum_map", f32p), ("amb_shading_map", f32p), ("diff_shading_map", f32p), ("normal_map", f32p),
+        ("no_specular_map", f32p), ("specular_map", f32p), ("z_map", f32p), ("z_min_per_ray", f32p),
+    ]
+
+
 EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_render_workspace_bytes",
            "oi_render_forward", "oi_render_launch_count", "oi_upfirdn2d", "oi_bias_act", "oi_fused_bias_act",
-           "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc"]
+           "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps"]
 
 _lib = None
 
@@ -109,6 +132,8 @@ def lib():
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]
     L.oi_bias_act.argtypes = [C.POINTER(OiBiasActDesc), C.c_void_p]
     L.oi_fused_bias_act.argtypes = [C.POINTER(OiFusedBiasActDesc), C.c_void_p]
+    L.oi_gen_rays.argtypes = [C.POINTER(OiGenRaysDesc), C.c_void_p]
+    L.oi_render_maps.argtypes = [C.POINTER(OiRenderMapsDesc), C.c_void_p]
     L.oi_selftest_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     if L.oi_abi_version() != 1:
         raise RuntimeError(f"liboi_b200.so ABI version {L.oi_abi_version()} != 1")

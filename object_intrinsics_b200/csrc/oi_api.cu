@@ -265,6 +265,24 @@ int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, i
   return launch_tc_selftest(a, b, img, d, static_cast<cudaStream_t>(stream));
 }
 
+int oi_gen_rays(const OiGenRaysDesc* d, void* stream) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->n_instances > 0 && d->resolution >= 2 && d->scene_resolution > 0, "bad sizes");
+  OI_CHECK_ARG(d->b2w && d->c2b && d->w2c && d->intrinsics_inv && d->rays_o && d->rays_d, "NULL pointer");
+  OI_CHECK_ARG((d->near == nullptr) == (d->far == nullptr), "near and far must be given together");
+  return launch_gen_rays(*d, static_cast<cudaStream_t>(stream));
+}
+
+int oi_render_maps(const OiRenderMapsDesc* d, void* stream) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->n_rays > 0 && d->rays_per_instance > 0 && d->n_rays % d->rays_per_instance == 0 && d->n_samples > 0,
+               "bad sizes");
+  OI_CHECK_ARG(d->weights && d->gradients && d->raw_color && d->pts && d->weight_sum && d->color_fine && d->rays_o &&
+                   d->light_dir && d->bg_color,
+               "NULL input pointer");
+  return launch_render_maps(*d, static_cast<cudaStream_t>(stream));
+}
+
 int oi_upfirdn2d(const OiUpfirdnDesc* d, void* stream) {
   OI_CHECK_ARG(d != nullptr, "desc is NULL");
   OI_CHECK_ARG(d->x && d->f && d->y, "x, f, y must be non-NULL");

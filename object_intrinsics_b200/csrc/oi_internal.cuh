@@ -121,6 +121,8 @@ int launch_film(const float* blob, int depth, const float* style_w, float* film,
 int launch_upfirdn2d(const OiUpfirdnDesc& d, cudaStream_t s);
 int launch_bias_act(const OiBiasActDesc& d, cudaStream_t s);
 int launch_fused_bias_act(const OiFusedBiasActDesc& d, cudaStream_t s);
+int launch_gen_rays(const OiGenRaysDesc& d, cudaStream_t st);
+int launch_render_maps(const OiRenderMapsDesc& d, cudaStream_t st);
 int launch_render_ffma(const RenderKArgs& a, cudaStream_t st);
 int launch_render_tc(const RenderKArgs& a, cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* B, const void* panel, float* D, cudaStream_t st);

@@ -81,6 +81,29 @@ class MappingLinear(nn.Module):
         return fused_leaky_relu(F.linear(x, self.weight), self.bias, negative_slope=0.2, scale=1)
 
 
+class StyleMLP(nn.Sequential):
+    """ShapeNetwork.style (fields.py:14-19).  Same children / state_dict keys as the reference's nn.Sequential of
+    three MappingLinear; when no gradient is needed the whole MLP is ONE kernel (C-ABI `oi_style_mlp`) instead of
+    three GEMV + three fused bias/activation launches."""
+
+    def forward(self, z):
+        needs_grad = torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad or not z.is_cuda or z.dtype != torch.float32 or len(self) != 3:
+            return super().forward(z)
+        import ctypes as C
+        from . import _lib
+        p = _lib.OiNetParams()
+        p.depth, p.width, p.style_dim = 1, _lib.OI_WIDTH, z.shape[-1]
+        for i, layer in enumerate(self):
+            p.style_weight[i], p.style_bias[i] = layer.weight.data_ptr(), layer.bias.data_ptr()
+        zz = z.contiguous()
+        w = torch.empty_like(zz)
+        with torch.cuda.device(z.device):
+            _lib.check(_lib.lib().oi_style_mlp(C.byref(p), zz.data_ptr(), w.data_ptr(), zz.shape[0],
+                                               _lib.current_stream_ptr(z.device)), "oi_style_mlp")
+        return w
+
+
 class ShapeNetwork(nn.Module):
     """FiLM-SIREN SDF network + 3-layer style MLP  (src/models/fields.py:10-77)."""
 
@@ -88,7 +111,7 @@ class ShapeNetwork(nn.Module):
         super().__init__()
         if checkpoint_path is not None:
             raise NotImplementedError("load weights with load_state_dict / load_flat_params instead")
-        self.style = nn.Sequential(*[MappingLinear(style_dim, style_dim) for _ in range(3)])
+        self.style = StyleMLP(*[MappingLinear(style_dim, style_dim) for _ in range(3)])
         self.pts_linears = nn.ModuleList(
             [FiLMSiren(input_ch, W, style_dim, is_first=True)] + [FiLMSiren(W, W, style_dim) for _ in range(D - 1)])
         self.sigma_linear = LinearLayer(W, 1)
