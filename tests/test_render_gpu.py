@@ -163,3 +163,27 @@ def test_weight_cache_tracks_parameter_updates():
     o3 = _run_kernel(r, inp, meta)
     assert r._packed.repacks == n1 + 1
     assert linf(o3["sdf"], o1["sdf"] + 0.125) < 1e-6
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_config4_hierarchical_full_patch(impl):
+    """BASELINE config 4 shape family at a 64x64 patch: 64 + 64 hierarchical samples, D=8."""
+    meta = dict(params="params_D8.npz", D=8, n_samples=64, n_importance=64, cos_anneal_ratio=1.0)
+    P, r = _build(meta, impl)
+    ro, rd, near, far = O.synthetic_rays(1, 64, seed=77)
+    z = torch.randn(1, 64, generator=torch.Generator().manual_seed(77))
+    w = O.style_mlp(P, z)
+    inp = dict(rays_o=ro, rays_d=rd, near=near, far=far, z=z, w=w)
+    out = _run_kernel(r, inp, meta, return_z_vals=True)
+    zv = out["z_vals"]
+    assert zv.shape == (4096, 128) and (zv[:, 1:] >= zv[:, :-1]).all()
+    assert (zv[:, :1] >= near - 1e-4).all() and (zv[:, -1:] <= far + 1e-4).all()
+    W = out["weights"]
+    assert torch.isfinite(W).all() and (W >= 0).all()
+    assert linf(W.sum(-1, keepdim=True), out["weight_sum"]) < 1e-5
+    assert linf((out["raw_color"] * W[..., None]).sum(1), out["color_fine"]) < 1e-5
+    ref = O.render(P, ro, rd, near, far, w=w, n_samples=64, n_importance=64, cos_anneal_ratio=1.0)
+    for k in ("color_fine", "weight_sum"):
+        assert linf(out[k], ref[k]) <= 1e-4, (k, linf(out[k], ref[k]))
+    bad = int(((zv - ref["z_vals"]).abs() > 1e-3).sum())
+    assert bad <= zv.numel() // 500, bad
