@@ -159,6 +159,81 @@ int oi_render_forward(const OiRenderDesc* desc, void* stream);
 int oi_render_launch_count(const OiRenderDesc* desc, int32_t* launches);
 
 /* ------------------------------------------------------------------------------------------------
+ * Backward of NeuSRenderer.render w.r.t. every parameter the path reads.  The reference gets it from
+ * torch.autograd (render #1 of each training step, src/trainers/gan_pose_trainer.py:110,141), including the
+ * second-order terms through the SDF normal that `fields.py:104-122` builds with create_graph=True.  Here it
+ * is one reverse sweep per 128-point tile that recomputes the forward (nothing but the render outputs is
+ * kept between forward and backward).  Sampling is not differentiated (renderer.py:390 runs it under
+ * no_grad): pass the z-values the forward rendered (OiRenderDesc.z_vals_out).  Rays are treated as constants.
+ *
+ * Gradients are ACCUMULATED (+=) into the OiNetGrads tensors, which have the shapes of the corresponding
+ * OiNetParams tensors; the caller zeroes them when it wants plain gradients.  The FiLM linears
+ * (gamma/beta weight and bias) and the latent w receive their gradient through the FiLM tables:
+ * d_film_gamma / d_film_beta are dL/dgamma, dL/dbeta with gamma = 15 (G w + g) + 30, beta = 0.25 (B w + c)
+ * (volume_renderer.py:27-30); the remaining chain is two tiny matrix products left to the caller.
+ * Summation over points uses floating-point atomics: results are reproducible to rounding, not bit-wise.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OiNetGrads {
+  float* pts_weight[OI_MAX_DEPTH];  /* [W,3] for l=0, [W,W] otherwise */
+  float* pts_bias[OI_MAX_DEPTH];    /* [W] */
+  float* sigma_weight;              /* [1,W] */
+  float* sigma_bias;                /* [1] */
+  float* views_weight;              /* [W, W+3] */
+  float* views_bias;                /* [W] */
+  float* rgb_weight;                /* [3,W] */
+  float* rgb_bias;                  /* [3] */
+  float* variance;                  /* [] */
+  float* film_gamma;                /* [n_instances, OI_MAX_DEPTH+1, W] (slot OI_MAX_DEPTH = views_linears) */
+  float* film_beta;                 /* [n_instances, OI_MAX_DEPTH+1, W] */
+} OiNetGrads;
+
+typedef struct OiRenderBwdDesc {
+  int32_t n_rays;            /* R */
+  int32_t rays_per_instance;
+  int32_t n_samples_total;   /* S = n_samples + n_importance */
+  int32_t n_samples;         /* n (sample_dist = 2/n, renderer.py:356) */
+  int32_t depth;             /* D >= 2 */
+  int32_t flags;
+  float cos_anneal_ratio;
+  float reserved_f;
+
+  /* inputs of the forward call */
+  const float* rays_o;       /* [R,3] */
+  const float* rays_d;       /* [R,3] */
+  const float* z_vals;       /* [R,S] section starts rendered by the forward (z_vals_out) */
+  const float* style_w;      /* [n_instances,64] */
+  const void* packed_weights;
+
+  /* outputs of the forward call that the tail needs */
+  const float* sdf;          /* [R,S] */
+  const float* gradients;    /* [R,S,3] */
+  const float* raw_color;    /* [R,S,3] */
+
+  /* incoming adjoints dL/d(output); each may be NULL (= zero) */
+  const float* g_weights;        /* [R,S] */
+  const float* g_weight_sum;     /* [R,1] */
+  const float* g_weight_max;     /* [R,1] */
+  const float* g_color_fine;     /* [R,3] */
+  const float* g_raw_color;      /* [R,S,3] */
+  const float* g_gradients;      /* [R,S,3] */
+  const float* g_sdf;            /* [R,S] */
+  const float* g_cdf_fine;       /* [R,S] */
+  const float* g_s_val;          /* [R,1] */
+  const float* g_gradient_error; /* [] */
+  const float* g_surface_loss;   /* [] */
+
+  OiNetGrads grads;          /* every pointer must be non-NULL */
+
+  void* workspace;           /* >= oi_render_backward_workspace_bytes(desc), 256-byte aligned */
+  size_t workspace_bytes;
+  void* evt_core_start;      /* optional cudaEvent_t pair around the MLP backward kernel */
+  void* evt_core_stop;
+} OiRenderBwdDesc;
+
+int oi_render_backward_workspace_bytes(const OiRenderBwdDesc* desc, size_t* bytes);
+int oi_render_backward(const OiRenderBwdDesc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * StyleGAN2 ops.
  * ---------------------------------------------------------------------------------------------- */
 

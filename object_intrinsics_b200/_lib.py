@@ -49,6 +49,32 @@ class OiRenderDesc(C.Structure):
     ]
 
 
+class OiNetGrads(C.Structure):
+    _fields_ = [
+        ("pts_weight", f32p * OI_MAX_DEPTH), ("pts_bias", f32p * OI_MAX_DEPTH),
+        ("sigma_weight", f32p), ("sigma_bias", f32p), ("views_weight", f32p), ("views_bias", f32p),
+        ("rgb_weight", f32p), ("rgb_bias", f32p), ("variance", f32p), ("film_gamma", f32p), ("film_beta", f32p),
+    ]
+
+
+BWD_ADJOINT_KEYS = ("weights", "weight_sum", "weight_max", "color_fine", "raw_color", "gradients", "sdf", "cdf_fine",
+                    "s_val", "gradient_error", "surface_loss")
+
+
+class OiRenderBwdDesc(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int32), ("rays_per_instance", C.c_int32), ("n_samples_total", C.c_int32),
+        ("n_samples", C.c_int32), ("depth", C.c_int32), ("flags", C.c_int32),
+        ("cos_anneal_ratio", C.c_float), ("reserved_f", C.c_float),
+        ("rays_o", f32p), ("rays_d", f32p), ("z_vals", f32p), ("style_w", f32p), ("packed_weights", C.c_void_p),
+        ("sdf", f32p), ("gradients", f32p), ("raw_color", f32p),
+    ] + [("g_" + k, f32p) for k in BWD_ADJOINT_KEYS] + [
+        ("grads", OiNetGrads),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("evt_core_start", C.c_void_p), ("evt_core_stop", C.c_void_p),
+    ]
+
+
 class OiUpfirdnDesc(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("f", C.c_void_p), ("y", C.c_void_p), ("dtype", C.c_int32),
@@ -105,7 +131,8 @@ class OiRenderMapsDesc(C.Structure):
 
 EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_render_workspace_bytes",
            "oi_render_forward", "oi_render_launch_count", "oi_upfirdn2d", "oi_bias_act", "oi_fused_bias_act",
-           "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps"]
+           "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps",
+           "oi_render_backward_workspace_bytes", "oi_render_backward"]
 
 _lib = None
 
@@ -129,6 +156,8 @@ def lib():
     L.oi_render_workspace_bytes.argtypes = [C.POINTER(OiRenderDesc), C.POINTER(C.c_size_t)]
     L.oi_render_forward.argtypes = [C.POINTER(OiRenderDesc), C.c_void_p]
     L.oi_render_launch_count.argtypes = [C.POINTER(OiRenderDesc), C.POINTER(C.c_int32)]
+    L.oi_render_backward_workspace_bytes.argtypes = [C.POINTER(OiRenderBwdDesc), C.POINTER(C.c_size_t)]
+    L.oi_render_backward.argtypes = [C.POINTER(OiRenderBwdDesc), C.c_void_p]
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]
     L.oi_bias_act.argtypes = [C.POINTER(OiBiasActDesc), C.c_void_p]
     L.oi_fused_bias_act.argtypes = [C.POINTER(OiFusedBiasActDesc), C.c_void_p]

@@ -95,7 +95,7 @@ extern "C" {
 
 const char* oi_last_error(void) { return g_err; }
 int oi_abi_version(void) { return OI_ABI_VERSION; }
-const char* oi_build_info(void) { return "sm_100a;ffma;tcgen05"; }
+const char* oi_build_info(void) { return "sm_100a;ffma;tcgen05;backward"; }
 
 int oi_packed_weights_bytes(int32_t depth, size_t* bytes) {
   OI_CHECK_ARG(bytes != nullptr, "bytes is NULL");
@@ -250,6 +250,112 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   return launch_composite(R, S, blob, d->depth, d->weights, a.raw_color, a.gradients, a.pts_norm, a.sdf,
                           d->weight_sum, d->weight_max, d->color_fine, d->s_val, d->gradient_error, d->surface_loss,
                           reinterpret_cast<float*>(ws + w.partials), ticket, st);
+}
+
+namespace {
+struct BwdWorkspace {
+  size_t film, d_film, adj, invs_partial, relax_count, ticket, scratch, total;
+  int n_ctas, n_inst, tiles_per_inst, n_tiles;
+};
+
+int validate_bwd(const OiRenderBwdDesc* d) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->n_rays > 0, "n_rays must be positive (got %d)", d->n_rays);
+  OI_CHECK_ARG(d->rays_per_instance > 0 && d->n_rays % d->rays_per_instance == 0,
+               "n_rays (%d) must be a multiple of rays_per_instance (%d)", d->n_rays, d->rays_per_instance);
+  OI_CHECK_ARG(d->n_samples >= 2 && d->n_samples_total >= d->n_samples, "bad n_samples / n_samples_total");
+  if (d->depth < 2 || d->depth > OI_MAX_DEPTH)
+    return set_error(OI_ERR_UNSUPPORTED, "backward needs 2 <= depth <= %d (got %d)", OI_MAX_DEPTH, d->depth);
+  if ((long long)d->n_rays * d->n_samples_total >= (1ll << 30))
+    return set_error(OI_ERR_UNSUPPORTED, "n_rays * samples too large for 32-bit point indices");
+  OI_CHECK_ARG(d->rays_o && d->rays_d && d->z_vals && d->style_w && d->packed_weights, "NULL input pointer");
+  OI_CHECK_ARG(((uintptr_t)d->packed_weights & 127) == 0, "packed_weights must be 128-byte aligned");
+  OI_CHECK_ARG(d->sdf && d->gradients && d->raw_color, "sdf / gradients / raw_color of the forward are required");
+  const OiNetGrads& g = d->grads;
+  for (int l = 0; l < d->depth; ++l)
+    OI_CHECK_ARG(g.pts_weight[l] && g.pts_bias[l], "grads.pts_weight/bias[%d] is NULL", l);
+  for (int l = 1; l < d->depth; ++l)
+    OI_CHECK_ARG(((uintptr_t)g.pts_weight[l] & 15) == 0, "grads.pts_weight[%d] must be 16-byte aligned", l);
+  OI_CHECK_ARG(g.sigma_weight && g.sigma_bias && g.views_weight && g.views_bias && g.rgb_weight && g.rgb_bias &&
+                   g.variance && g.film_gamma && g.film_beta,
+               "a grads pointer is NULL");
+  return OI_OK;
+}
+
+void plan_bwd(const OiRenderBwdDesc* d, BwdWorkspace* w) {
+  const int R = d->n_rays, S = d->n_samples_total;
+  w->n_inst = R / d->rays_per_instance;
+  const long long pts_per_inst = (long long)d->rays_per_instance * S;
+  w->tiles_per_inst = (int)((pts_per_inst + 127) / 128);
+  w->n_tiles = w->tiles_per_inst * w->n_inst;
+  w->n_ctas = render_bwd_ctas(w->n_tiles);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  w->film = take((size_t)w->n_inst * kFilm * 4 * kW * 4);
+  w->d_film = take((size_t)w->n_inst * kFilm * 2 * kW * 4);
+  w->adj = take((size_t)R * S * 8 * 4);
+  w->invs_partial = take((size_t)R * 4);
+  w->relax_count = take(256);
+  w->ticket = take(256);
+  w->scratch = take((size_t)w->n_ctas * render_bwd_scratch_floats() * 4);
+  w->total = off;
+}
+}  // namespace
+
+int oi_render_backward_workspace_bytes(const OiRenderBwdDesc* desc, size_t* bytes) {
+  int rc = validate_bwd(desc);
+  if (rc) return rc;
+  OI_CHECK_ARG(bytes != nullptr, "bytes is NULL");
+  BwdWorkspace w;
+  plan_bwd(desc, &w);
+  *bytes = w.total;
+  return OI_OK;
+}
+
+int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
+  int rc = validate_bwd(d);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BwdWorkspace w;
+  plan_bwd(d, &w);
+  OI_CHECK_ARG(d->workspace != nullptr && ((uintptr_t)d->workspace & 255) == 0,
+               "workspace must be non-NULL and 256-byte aligned");
+  if (d->workspace_bytes < w.total)
+    return set_error(OI_ERR_WORKSPACE, "workspace too small: %zu < %zu", d->workspace_bytes, w.total);
+  char* ws = static_cast<char*>(d->workspace);
+  const float* blob = static_cast<const float*>(d->packed_weights);
+  float* film = reinterpret_cast<float*>(ws + w.film);
+  rc = launch_film(blob, d->depth, d->style_w, film, w.n_inst, reinterpret_cast<unsigned int*>(ws + w.ticket), st);
+  if (rc) return rc;
+
+  RenderKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = d->n_rays;
+  a.rays_per_inst = d->rays_per_instance;
+  a.n_inst = w.n_inst;
+  a.n_coarse = d->n_samples;
+  a.D = d->depth;
+  a.cos_anneal = d->cos_anneal_ratio;
+  a.flags = d->flags;
+  a.sample_dist = 2.0f / (float)d->n_samples;  // renderer.py:356
+  a.rays_o = d->rays_o;
+  a.rays_d = d->rays_d;
+  a.z_vals = d->z_vals;
+  a.blob = blob;
+  a.film = film;
+  a.coarse = 0;
+  a.S = d->n_samples_total;
+  a.pts_per_inst = d->rays_per_instance * a.S;
+  a.tiles_per_inst = w.tiles_per_inst;
+  a.n_tiles = w.n_tiles;
+  return launch_render_bwd(*d, a, reinterpret_cast<float*>(ws + w.adj), reinterpret_cast<float*>(ws + w.invs_partial),
+                           reinterpret_cast<unsigned int*>(ws + w.relax_count),
+                           reinterpret_cast<float*>(ws + w.d_film), reinterpret_cast<float*>(ws + w.scratch), w.n_ctas,
+                           st);
 }
 
 int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,

@@ -35,6 +35,9 @@ int set_error(int code, const char* fmt, ...);
 //               8 chunks               : views_linears.weight[:, :128]^T (feature part of the colour layer)
 //               8 chunks per l=D-1..1  : W_l as stored by torch (row k = output channel, column n = input
 //                                        channel) -- the operand of the reverse (input-gradient) sweep
+//             (the forward kernels stop here: n_chunks_fine)
+//               8 chunks               : views_linears.weight[:, :128] as stored (row k = colour channel,
+//                                        column n = feature channel) -- backward kernel only
 //   [const]   bias[9][128] (slot 8 = views_linears.bias), w_sigma[128], wc_grad[3][128]
 //             (= views_linears.weight[:, 128+j]), w_rgb[3][128], w0t[3][128] (= W_0^T), scalars[8] =
 //             {b_sigma, b_rgb[0..2], inv_s, 1/inv_s, 0, 0}
@@ -52,6 +55,7 @@ struct BlobLayout {
   int depth;
   int n_chunks_fine;    // 9 + 16 (D-1)
   int n_chunks_coarse;  // 1 + 8 (D-1)
+  int n_chunks_stream;  // n_chunks_fine + 8 (chunks only the backward kernel streams)
   size_t stream_off, const_off, film_off, tc_off, total_floats;
   // const section sub-offsets (relative to const_off)
   static constexpr int kBias = 0;                      // [9][128]
@@ -77,7 +81,8 @@ __host__ __device__ inline BlobLayout blob_layout(int depth) {
   L.n_chunks_fine = 9 + 16 * (depth - 1);
   L.n_chunks_coarse = 1 + 8 * (depth - 1);
   L.stream_off = 0;
-  L.const_off = (size_t)L.n_chunks_fine * kChunkFloats;
+  L.n_chunks_stream = L.n_chunks_fine + 8;
+  L.const_off = (size_t)L.n_chunks_stream * kChunkFloats;
   L.film_off = L.const_off + ((BlobLayout::kConstFloats + 31) / 32) * 32;
   L.tc_off = L.film_off + ((BlobLayout::kFilmFloats + 31) / 32) * 32;
   L.total_floats = L.tc_off + tc_section_floats(depth);
@@ -126,6 +131,10 @@ int launch_render_maps(const OiRenderMapsDesc& d, cudaStream_t st);
 int launch_render_ffma(const RenderKArgs& a, cudaStream_t st);
 int launch_render_tc(const RenderKArgs& a, cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* B, const void* panel, float* D, cudaStream_t st);
+int launch_render_bwd(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
+                      unsigned int* relax_count, float* d_film, float* scratch, int n_ctas, cudaStream_t st);
+int render_bwd_ctas(int n_tiles);
+size_t render_bwd_scratch_floats();
 size_t render_ffma_scratch_floats(int depth, int* n_ctas, int n_tiles);
 size_t render_tc_scratch_floats(int depth, int* n_ctas, int n_tiles);
 int launch_upsample(int R, int n, int m, const float* rays_o, const float* rays_d, const float* near,

@@ -27,7 +27,7 @@ __global__ void pack_weights_kernel(const PackArgs a, float* __restrict__ blob) 
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
 
   // ---- stream section
-  const size_t stream_floats = (size_t)L.n_chunks_fine * kChunkFloats;
+  const size_t stream_floats = (size_t)L.n_chunks_stream * kChunkFloats;
   for (size_t i = tid; i < stream_floats; i += nthreads) {
     const int chunk = (int)(i / kChunkFloats);
     const int r = (int)(i % kChunkFloats) / kW;  // row in chunk
@@ -38,8 +38,10 @@ __global__ void pack_weights_kernel(const PackArgs a, float* __restrict__ blob) 
     } else {
       int c = chunk - 1;
       const int k = (c % 8) * kKC + r;
-      const int seg = c / 8;  // 0..D-2 forward, D-1 colour, D..2D-2 reverse
-      if (seg < D - 1) {
+      const int seg = c / 8;  // 0..D-2 forward, D-1 colour, D..2D-2 reverse, 2D-1 colour as stored (backward)
+      if (seg == 2 * D - 1) {
+        v = p.views_weight[k * (kW + 3) + n];
+      } else if (seg < D - 1) {
         v = p.pts_weight[seg + 1][n * kW + k];  // W_l^T
       } else if (seg == D - 1) {
         v = p.views_weight[n * (kW + 3) + k];

@@ -14,10 +14,13 @@ The renderer owns no parameters; the three networks stay the `nn.Module`s regist
 (checkpoints / EMA / DDP unchanged).  Packed weight blobs are derived caches keyed on the parameters'
 (data_ptr, _version) and rebuilt when any parameter changes.
 
-No-grad calls (renders #2/#3 of every training step, and inference) run the hand-written CUDA path through
-the C-ABI library.  Grad-mode calls (render #1, the generator step) need d/dtheta through the analytic normal
-(second order); they run `torch_graph.render_differentiable`, this package's own differentiable torch
-formulation on the GPU (the hand-written backward is the next step).
+Every call runs the hand-written CUDA path through the C-ABI library.  Grad-mode calls (render #1 of a training
+step, the generator update) go through `_RenderFunction`: the same forward kernels, and `oi_render_backward`
+(csrc/oi_render_bwd.cu) for d/dtheta of every parameter the path reads, including the second-order terms through
+the analytic normal that the reference obtains from autograd (`fields.py:104-122`, create_graph=True).  Rays are
+constants of the training path (poses are sampled, `generator.py:66-78`); a call whose rays require grad raises
+unless the renderer was built with `grad_impl="torch"` (`torch_graph.render_differentiable`, the differentiable
+torch formulation kept for that case and as the A/B reference of the backward kernel).
 There is NO CPU path and no silent fallback: a missing library or an unsupported argument raises.
 """
 from __future__ import annotations
@@ -131,11 +134,132 @@ class PackedWeights:
         return self.blob
 
 
+FN_OUT_KEYS = OUT_KEYS_PER_POINT + OUT_KEYS_PER_POINT3 + OUT_KEYS_PER_RAY + ("color_fine", "gradient_error",
+                                                                           "surface_loss", "z_vals")
+FN_NON_DIFF = ("inside_sphere", "mid_z_vals", "pts_norm", "pts", "z_vals")
+
+
+def film_tables(sdf_network, color_network, w):
+    """gamma, beta [bs, 9, 128] as differentiable torch ops (volume_renderer.py:27-30,47-48,56-57).  Only the
+    autograd graph of this result is used (it routes dL/dgamma, dL/dbeta to the FiLM linears and to w); the
+    kernels compute their own tables from the packed blob."""
+    mods = _film_modules(sdf_network, color_network)
+    Wg = torch.stack([m.gamma.weight for m in mods])      # [L,128,64]
+    bg = torch.stack([m.gamma.bias for m in mods])
+    Wb = torch.stack([m.beta.weight for m in mods])
+    bb = torch.stack([m.beta.bias for m in mods])
+    gam = 15.0 * (torch.einsum("bk,lnk->bln", w, Wg) + bg[None]) + 30.0
+    bet = 0.25 * (torch.einsum("bk,lnk->bln", w, Wb) + bb[None])
+    return gam, bet
+
+
+class _RenderFunction(torch.autograd.Function):
+    """Forward = the fused CUDA render; backward = oi_render_backward.  Differentiable inputs: the FiLM tables
+    (depth+1 slots) and the tensors of `_direct_params`."""
+
+    @staticmethod
+    def forward(ctx, renderer, geo, gam, bet, *direct):
+        params, rays_o, rays_d, near, far, w, cos_anneal_ratio, t_rand, z_vals = geo
+        out = renderer._render_cuda(params, rays_o, rays_d, near, far, w, cos_anneal_ratio, t_rand, z_vals, True)
+        ctx.renderer = renderer
+        ctx.cos_anneal_ratio = cos_anneal_ratio
+        ctx.blob = renderer._packed.blob
+        ctx.blob_key = renderer._packed.key
+        ctx.depth = renderer._packed.depth
+        ctx.n_film = gam.shape[1]
+        ctx.direct_shapes = [t.shape for t in direct]
+        f32c = lambda t: t.detach().to(torch.float32).contiguous()
+        ctx.save_for_backward(f32c(rays_o), f32c(rays_d), out["z_vals"], f32c(w), out["sdf"], out["gradients"],
+                              out["raw_color"])
+        res = tuple(out[k] for k in FN_OUT_KEYS)
+        ctx.mark_non_differentiable(*[out[k] for k in FN_NON_DIFF])
+        return res
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        rays_o, rays_d, z_vals, w, sdf, gradients, raw_color = ctx.saved_tensors
+        r = ctx.renderer
+        if r._packed.key != ctx.blob_key:
+            raise RuntimeError("a parameter of the render path was modified between forward and backward")
+        L = _lib.lib()
+        dev = rays_o.device
+        R, S = z_vals.shape
+        n_inst = w.shape[0]
+        D = ctx.depth
+        gmap = dict(zip(FN_OUT_KEYS, gouts))
+        keep = []
+
+        def adj(k):
+            g = gmap.get(k)
+            if g is None:
+                return None
+            g = g.detach().to(torch.float32).contiguous()
+            keep.append(g)
+            return g.data_ptr()
+
+        # one zeroed flat buffer carved into the gradient tensors (shapes of the parameters)
+        shapes = [("pts_weight%d" % l, (128, 3 if l == 0 else 128)) for l in range(D)] + \
+                 [("pts_bias%d" % l, (128,)) for l in range(D)] + \
+                 [("sigma_weight", (1, 128)), ("sigma_bias", (1,)), ("views_weight", (128, 131)),
+                  ("views_bias", (128,)), ("rgb_weight", (3, 128)), ("rgb_bias", (3,)), ("variance", ()),
+                  ("film_gamma", (n_inst, _lib.OI_MAX_DEPTH + 1, 128)), ("film_beta", (n_inst, _lib.OI_MAX_DEPTH + 1, 128))]
+        offs, total = {}, 0
+        for k, shp in shapes:
+            n = 1
+            for v in shp:
+                n *= v
+            offs[k] = (total, n, shp)
+            total += (n + 3) // 4 * 4          # keep every tensor 16-byte aligned (vector reductions)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        G = {k: flat[o:o + n].view(shp) for k, (o, n, shp) in offs.items()}
+
+        d = _lib.OiRenderBwdDesc()
+        d.n_rays, d.rays_per_instance, d.n_samples_total, d.n_samples = R, R // n_inst, S, r.n_samples
+        d.depth, d.flags, d.cos_anneal_ratio = D, r.flags, ctx.cos_anneal_ratio
+        d.rays_o, d.rays_d, d.z_vals, d.style_w = rays_o.data_ptr(), rays_d.data_ptr(), z_vals.data_ptr(), w.data_ptr()
+        d.packed_weights = ctx.blob.data_ptr()
+        d.sdf, d.gradients, d.raw_color = sdf.data_ptr(), gradients.data_ptr(), raw_color.data_ptr()
+        for k in _lib.BWD_ADJOINT_KEYS:
+            setattr(d, "g_" + k, adj(k))
+        for l in range(D):
+            d.grads.pts_weight[l] = G["pts_weight%d" % l].data_ptr()
+            d.grads.pts_bias[l] = G["pts_bias%d" % l].data_ptr()
+        for k in ("sigma_weight", "sigma_bias", "views_weight", "views_bias", "rgb_weight", "rgb_bias", "variance",
+                  "film_gamma", "film_beta"):
+            setattr(d.grads, k, G[k].data_ptr())
+        if r.bwd_events is not None:
+            d.evt_core_start, d.evt_core_stop = r.bwd_events[0].cuda_event, r.bwd_events[1].cuda_event
+        nbytes = C.c_size_t(0)
+        with torch.cuda.device(dev):
+            _lib.check(L.oi_render_backward_workspace_bytes(C.byref(d), C.byref(nbytes)),
+                       "oi_render_backward_workspace_bytes")
+            if r._bwd_workspace is None or r._bwd_workspace.numel() < nbytes.value or r._bwd_workspace.device != dev:
+                r._bwd_workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            d.workspace, d.workspace_bytes = r._bwd_workspace.data_ptr(), r._bwd_workspace.numel()
+            _lib.check(L.oi_render_backward(C.byref(d), _lib.current_stream_ptr(dev)), "oi_render_backward")
+        film_slots = list(range(D)) + [_lib.OI_MAX_DEPTH]
+        g_gam = G["film_gamma"][:, film_slots]
+        g_bet = G["film_beta"][:, film_slots]
+        direct = [G["pts_weight%d" % l] for l in range(D)] + [G["pts_bias%d" % l] for l in range(D)] + \
+                 [G[k] for k in ("sigma_weight", "sigma_bias", "views_weight", "views_bias", "rgb_weight", "rgb_bias",
+                                 "variance")]
+        direct = [g.reshape(shp) for g, shp in zip(direct, ctx.direct_shapes)]
+        return (None, None, g_gam, g_bet, *direct)
+
+
+def _direct_params(sdf_network, color_network, deviation_network):
+    """Parameters whose gradient oi_render_backward writes directly (order fixed by _RenderFunction.backward)."""
+    return [f.weight for f in sdf_network.pts_linears] + [f.bias for f in sdf_network.pts_linears] + \
+           [sdf_network.sigma_linear.weight, sdf_network.sigma_linear.bias, color_network.views_linears.weight,
+            color_network.views_linears.bias, color_network.rgb_linear.weight, color_network.rgb_linear.bias,
+            deviation_network.variance]
+
+
 class NeuSRenderer:
-    """Same constructor keywords as the reference class (renderer.py:77-96) plus `impl`."""
+    """Same constructor keywords as the reference class (renderer.py:77-96) plus `impl` and `grad_impl`."""
 
     def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside,
-                 up_sample_steps, perturb, impl: str = "auto"):
+                 up_sample_steps, perturb, impl: str = "auto", grad_impl: str = "cuda"):
         self.nerf = nerf
         self.sdf_network = sdf_network
         self.deviation_network = deviation_network
@@ -148,8 +272,13 @@ class NeuSRenderer:
         self.impl = impl
         if impl not in _IMPL:
             raise ValueError(f"impl must be one of {sorted(_IMPL)}")
+        if grad_impl not in ("cuda", "torch"):
+            raise ValueError("grad_impl must be 'cuda' or 'torch'")
+        self.grad_impl = os.environ.get("OI_GRAD_IMPL", grad_impl)
         self._packed = PackedWeights()
         self._workspace: Optional[torch.Tensor] = None
+        self._bwd_workspace: Optional[torch.Tensor] = None
+        self.bwd_events = None    # optional (torch.cuda.Event, torch.cuda.Event) around the MLP backward kernel
         self._lin = {}
         self.flags = int(os.environ.get("OI_RENDER_FLAGS", "1"))   # OiRenderDesc.flags: bit 0 = L2 discard of dead scratch
         self.last_launches = 0
@@ -199,12 +328,25 @@ class NeuSRenderer:
             t_rand = torch.rand([R, 1], device=rays_o.device) - 0.5                           # renderer.py:372
 
         params = collect_params(self.sdf_network, self.color_network, self.deviation_network, with_style=False)
-        needs_grad = torch.is_grad_enabled() and (
-            any(t.requires_grad for _, t in params) or w.requires_grad or rays_o.requires_grad or rays_d.requires_grad)
-        if needs_grad:
+        rays_grad = any(t is not None and t.requires_grad for t in (rays_o, rays_d, near, far, z_vals))
+        needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for _, t in params) or w.requires_grad or
+                                                  rays_grad)
+        if needs_grad and self.grad_impl == "torch":
             from . import torch_graph
             ret = torch_graph.render_differentiable(self, rays_o, rays_d, near, far, w, float(cos_anneal_ratio),
                                                     t_rand, z_vals)
+        elif needs_grad:
+            if rays_grad:
+                raise NotImplementedError("gradients w.r.t. rays / near / far / z_vals are not produced by the CUDA "
+                                          "backward (the training path samples poses); build the renderer with "
+                                          "grad_impl='torch' for that")
+            gam, bet = film_tables(self.sdf_network, self.color_network, w)
+            geo = (params, rays_o, rays_d, near, far, w, float(cos_anneal_ratio), t_rand, z_vals)
+            res = _RenderFunction.apply(self, geo, gam, bet, *_direct_params(self.sdf_network, self.color_network,
+                                                                             self.deviation_network))
+            ret = dict(zip(FN_OUT_KEYS, res))
+            if not return_z_vals:
+                ret.pop("z_vals")
         else:
             ret = self._render_cuda(params, rays_o, rays_d, near, far, w, float(cos_anneal_ratio), t_rand, z_vals,
                                     return_z_vals)
