@@ -46,6 +46,8 @@ for name, bs, patch, n, m in [("cfg2 bs=1 (64x64 x 64)", 1, 64, 64, 0), ("cfg2 b
         r = NeuSRenderer(None, sdf, dev, col, n_samples=n, n_importance=m, n_outside=0, up_sample_steps=1, perturb=1,
                          grad_impl=gi)
         r.bwd_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        for e in r.bwd_events:
+            e.record()   # torch creates the cudaEvent_t lazily; the C-ABI needs the handle
 
         def gstep():
             for p in params:
