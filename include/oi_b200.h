@@ -350,6 +350,15 @@ int oi_render_maps(const OiRenderMapsDesc* desc, void* stream);
 int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,
                    float* d, void* stream);
 
+/* Self-test of the point-contraction kernel of the tensor-core backward (csrc/oi_wgrad_tc.cu):
+ *   d[i][j] += sum_m tf_x(X)[m][i] * tf_y(Y)[m][j],   col[i] += sum_m tf_x(X)[m][i] * aux[row col_mult][m]
+ * over n_tiles tiles of 128 points.  slabs: [n_tiles][slabs_per_tile][32 channel-quads][128 points][4] fp32,
+ * aux: [n_tiles][16][128] fp32; tf: 0 identity, 1 sin; col_mult < 0: no multiplier.  d [128,128] and col [128]
+ * are accumulated into (zero them first).  The work is split over n_splits CTAs. */
+int oi_selftest_wgrad(const float* slabs, const float* aux, int32_t n_tiles, int32_t slabs_per_tile, int32_t x_slab,
+                      int32_t y_slab, int32_t x_tf, int32_t y_tf, int32_t col_mult, int32_t n_splits, float* d,
+                      float* col, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ */
 const char* oi_last_error(void);
 int oi_abi_version(void);

@@ -132,7 +132,7 @@ class OiRenderMapsDesc(C.Structure):
 EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_render_workspace_bytes",
            "oi_render_forward", "oi_render_launch_count", "oi_upfirdn2d", "oi_bias_act", "oi_fused_bias_act",
            "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps",
-           "oi_render_backward_workspace_bytes", "oi_render_backward"]
+           "oi_render_backward_workspace_bytes", "oi_render_backward", "oi_selftest_wgrad"]
 
 _lib = None
 
@@ -158,6 +158,7 @@ def lib():
     L.oi_render_launch_count.argtypes = [C.POINTER(OiRenderDesc), C.POINTER(C.c_int32)]
     L.oi_render_backward_workspace_bytes.argtypes = [C.POINTER(OiRenderBwdDesc), C.POINTER(C.c_size_t)]
     L.oi_render_backward.argtypes = [C.POINTER(OiRenderBwdDesc), C.c_void_p]
+    L.oi_selftest_wgrad.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p, C.c_void_p, C.c_void_p]
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]
     L.oi_bias_act.argtypes = [C.POINTER(OiBiasActDesc), C.c_void_p]
     L.oi_fused_bias_act.argtypes = [C.POINTER(OiFusedBiasActDesc), C.c_void_p]

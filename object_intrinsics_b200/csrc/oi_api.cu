@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "oi_internal.cuh"
+#include "oi_wgrad.cuh"
 
 namespace oi {
 
@@ -369,6 +370,36 @@ int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, i
     OI_CHECK_ARG(b != nullptr, "b must be non-NULL when no packed panel is given");
   }
   return launch_tc_selftest(a, b, img, d, static_cast<cudaStream_t>(stream));
+}
+
+int oi_selftest_wgrad(const float* slabs, const float* aux, int32_t n_tiles, int32_t slabs_per_tile, int32_t x_slab,
+                      int32_t y_slab, int32_t x_tf, int32_t y_tf, int32_t col_mult, int32_t n_splits, float* d,
+                      float* col, void* stream) {
+  OI_CHECK_ARG(slabs && aux && d && col, "NULL pointer");
+  OI_CHECK_ARG(n_tiles > 0 && slabs_per_tile > 0 && n_splits > 0, "bad sizes");
+  OI_CHECK_ARG(x_slab >= 0 && x_slab < slabs_per_tile && y_slab >= 0 && y_slab < slabs_per_tile, "bad slab index");
+  OI_CHECK_ARG(col_mult < 16, "col_mult must be an aux row (< 16) or negative");
+  WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_tiles = n_tiles;
+  a.tiles_per_inst = n_tiles;
+  a.n_groups = 1;
+  a.n_splits = n_splits;
+  a.slabs_per_tile = slabs_per_tile;
+  a.slabs = slabs;
+  a.aux = aux;
+  WgGroup& g = a.groups[0];
+  g.n_pairs = 1;
+  g.pairs[0] = WgPair{x_slab, y_slab, x_tf, y_tf};
+  g.n_cols = 1;
+  g.cols[0].src = WG_SRC_PAIR_X;
+  g.cols[0].mult = col_mult;
+  g.cols[0].out = col;
+  g.cols[0].inst_stride = 0;
+  g.cols[0].ch_stride = 1;
+  g.out = d;
+  g.out_ld = 128;
+  return launch_wgrad_tc(a, static_cast<cudaStream_t>(stream));
 }
 
 int oi_gen_rays(const OiGenRaysDesc* d, void* stream) {

@@ -53,3 +53,36 @@ def test_packed_panels_match_network_weights():
         d = _selftest(a, blob=blob, depth=D, panel=panel).cpu()
         err = float((d.double() - ref).abs().max())
         assert err <= 2e-6 * float(ref.abs().max()), (panel, err)
+
+
+@pytest.mark.parametrize("n_tiles,n_splits,x_tf,y_tf,mult", [(1, 1, 0, 0, -1), (5, 2, 0, 1, 3), (7, 7, 1, 0, -1)])
+def test_wgrad_point_contraction(n_tiles, n_splits, x_tf, y_tf, mult):
+    """MN-major bf16x2-split UMMA contraction over points + column sums (csrc/oi_wgrad_tc.cu) vs fp64 einsum."""
+    import ctypes as C
+    from object_intrinsics_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(n_tiles)
+    spt = 3
+    # values spanning many binades: adjoint-like dynamic range
+    slabs = torch.randn(n_tiles, spt, 32, 128, 4, device="cuda", generator=g) * \
+        torch.exp(4.0 * torch.randn(n_tiles, spt, 1, 128, 1, device="cuda", generator=g))
+    if x_tf:      # sin operands are FiLM pre-activations: |a| up to ~100 rad (MUFU sin, as in the forward core)
+        slabs[:, 2] = 30.0 * torch.randn(n_tiles, 32, 128, 4, device="cuda", generator=g)
+    if y_tf:
+        slabs[:, 0] = 30.0 * torch.randn(n_tiles, 32, 128, 4, device="cuda", generator=g)
+    aux = torch.randn(n_tiles, 16, 128, device="cuda", generator=g)
+    d = torch.zeros(128, 128, device="cuda")
+    col = torch.zeros(128, device="cuda")
+    _lib.check(L.oi_selftest_wgrad(slabs.data_ptr(), aux.data_ptr(), n_tiles, spt, 2, 0, x_tf, y_tf, mult, n_splits,
+                                   d.data_ptr(), col.data_ptr(), None), "oi_selftest_wgrad")
+    torch.cuda.synchronize()
+    tf = lambda t, k: torch.sin(t) if k else t
+    # [tile, q, m, 4] -> [tile*m, channel]
+    X = tf(slabs[:, 2].double(), x_tf).permute(0, 2, 1, 3).reshape(n_tiles * 128, 128)
+    Y = tf(slabs[:, 0].double(), y_tf).permute(0, 2, 1, 3).reshape(n_tiles * 128, 128)
+    ref = X.T @ Y
+    mm = aux[:, mult].double().reshape(-1, 1) if mult >= 0 else 1.0
+    ref_col = (X * mm).sum(0)
+    bound = (X.abs().T @ Y.abs())
+    assert float(((d.double() - ref).abs() / (bound + 1e-30)).max()) < 3e-5
+    assert float(((col.double() - ref_col).abs() / ((X * mm).abs().sum(0) + 1e-30)).max()) < 1e-5
