@@ -193,7 +193,9 @@ typedef struct OiRenderBwdDesc {
   int32_t n_samples_total;   /* S = n_samples + n_importance */
   int32_t n_samples;         /* n (sample_dist = 2/n, renderer.py:356) */
   int32_t depth;             /* D >= 2 */
+  int32_t impl;              /* OiRenderImpl: FFMA = one FP32 kernel; TCGEN05 (= AUTO) = two tensor-core kernels */
   int32_t flags;
+  int32_t reserved;
   float cos_anneal_ratio;
   float reserved_f;
 

@@ -64,8 +64,8 @@ BWD_ADJOINT_KEYS = ("weights", "weight_sum", "weight_max", "color_fine", "raw_co
 class OiRenderBwdDesc(C.Structure):
     _fields_ = [
         ("n_rays", C.c_int32), ("rays_per_instance", C.c_int32), ("n_samples_total", C.c_int32),
-        ("n_samples", C.c_int32), ("depth", C.c_int32), ("flags", C.c_int32),
-        ("cos_anneal_ratio", C.c_float), ("reserved_f", C.c_float),
+        ("n_samples", C.c_int32), ("depth", C.c_int32), ("impl", C.c_int32), ("flags", C.c_int32),
+        ("reserved", C.c_int32), ("cos_anneal_ratio", C.c_float), ("reserved_f", C.c_float),
         ("rays_o", f32p), ("rays_d", f32p), ("z_vals", f32p), ("style_w", f32p), ("packed_weights", C.c_void_p),
         ("sdf", f32p), ("gradients", f32p), ("raw_color", f32p),
     ] + [("g_" + k, f32p) for k in BWD_ADJOINT_KEYS] + [

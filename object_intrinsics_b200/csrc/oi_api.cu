@@ -255,9 +255,11 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
 
 namespace {
 struct BwdWorkspace {
-  size_t film, d_film, adj, invs_partial, relax_count, ticket, scratch, total;
-  int n_ctas, n_inst, tiles_per_inst, n_tiles;
+  size_t film, film_b, d_film, adj, invs_partial, relax_count, ticket, scratch, slabs, aux, total;
+  int n_ctas, n_inst, tiles_per_inst, n_tiles, chunk_tiles;
+  bool tc;
 };
+constexpr int kBwdChunkTiles = 2048;  // tiles per (bwd_tc_kernel, wgrad_tc_kernel) round: 5.8 GB of slabs
 
 int validate_bwd(const OiRenderBwdDesc* d) {
   OI_CHECK_ARG(d != nullptr, "desc is NULL");
@@ -269,6 +271,7 @@ int validate_bwd(const OiRenderBwdDesc* d) {
     return set_error(OI_ERR_UNSUPPORTED, "backward needs 2 <= depth <= %d (got %d)", OI_MAX_DEPTH, d->depth);
   if ((long long)d->n_rays * d->n_samples_total >= (1ll << 30))
     return set_error(OI_ERR_UNSUPPORTED, "n_rays * samples too large for 32-bit point indices");
+  OI_CHECK_ARG(d->impl >= OI_IMPL_AUTO && d->impl <= OI_IMPL_TCGEN05, "bad impl %d", d->impl);
   OI_CHECK_ARG(d->rays_o && d->rays_d && d->z_vals && d->style_w && d->packed_weights, "NULL input pointer");
   OI_CHECK_ARG(((uintptr_t)d->packed_weights & 127) == 0, "packed_weights must be 128-byte aligned");
   OI_CHECK_ARG(d->sdf && d->gradients && d->raw_color, "sdf / gradients / raw_color of the forward are required");
@@ -289,7 +292,9 @@ void plan_bwd(const OiRenderBwdDesc* d, BwdWorkspace* w) {
   const long long pts_per_inst = (long long)d->rays_per_instance * S;
   w->tiles_per_inst = (int)((pts_per_inst + 127) / 128);
   w->n_tiles = w->tiles_per_inst * w->n_inst;
-  w->n_ctas = render_bwd_ctas(w->n_tiles);
+  w->tc = d->impl != OI_IMPL_FFMA;
+  w->chunk_tiles = w->n_tiles < kBwdChunkTiles ? w->n_tiles : kBwdChunkTiles;
+  w->n_ctas = w->tc ? render_bwd_tc_ctas(w->chunk_tiles) : render_bwd_ctas(w->n_tiles);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -297,12 +302,20 @@ void plan_bwd(const OiRenderBwdDesc* d, BwdWorkspace* w) {
     return o;
   };
   w->film = take((size_t)w->n_inst * kFilm * 4 * kW * 4);
+  w->film_b = take((size_t)w->n_inst * kFilm * 2 * kW * 4);
   w->d_film = take((size_t)w->n_inst * kFilm * 2 * kW * 4);
   w->adj = take((size_t)R * S * 8 * 4);
   w->invs_partial = take((size_t)R * 4);
   w->relax_count = take(256);
   w->ticket = take(256);
-  w->scratch = take((size_t)w->n_ctas * render_bwd_scratch_floats() * 4);
+  if (w->tc) {
+    w->scratch = take((size_t)w->n_ctas * render_bwd_tc_scratch_floats() * 4);
+    w->slabs = take((size_t)w->chunk_tiles * kSlabsPerTile * kSlabFloats * 4);
+    w->aux = take((size_t)w->chunk_tiles * 16 * 128 * 4);
+  } else {
+    w->scratch = take((size_t)w->n_ctas * render_bwd_scratch_floats() * 4);
+    w->slabs = w->aux = 0;
+  }
   w->total = off;
 }
 }  // namespace
@@ -353,10 +366,18 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
   a.pts_per_inst = d->rays_per_instance * a.S;
   a.tiles_per_inst = w.tiles_per_inst;
   a.n_tiles = w.n_tiles;
-  return launch_render_bwd(*d, a, reinterpret_cast<float*>(ws + w.adj), reinterpret_cast<float*>(ws + w.invs_partial),
-                           reinterpret_cast<unsigned int*>(ws + w.relax_count),
-                           reinterpret_cast<float*>(ws + w.d_film), reinterpret_cast<float*>(ws + w.scratch), w.n_ctas,
-                           st);
+  a.film_tc = film + (size_t)w.n_inst * kFilm * 2 * kW;
+  float* adj = reinterpret_cast<float*>(ws + w.adj);
+  float* invs_partial = reinterpret_cast<float*>(ws + w.invs_partial);
+  float* d_film = reinterpret_cast<float*>(ws + w.d_film);
+  rc = launch_bwd_tail(*d, a, adj, invs_partial, reinterpret_cast<unsigned int*>(ws + w.relax_count), d_film, st);
+  if (rc) return rc;
+  if (!w.tc)
+    return launch_render_bwd_ffma(*d, a, adj, invs_partial, d_film, reinterpret_cast<float*>(ws + w.scratch), w.n_ctas,
+                                  st);
+  return launch_render_bwd_tc(*d, a, adj, invs_partial, reinterpret_cast<float*>(ws + w.film_b), d_film,
+                              reinterpret_cast<float*>(ws + w.scratch), reinterpret_cast<float*>(ws + w.slabs),
+                              reinterpret_cast<float*>(ws + w.aux), w.chunk_tiles, w.n_ctas, st);
 }
 
 int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,

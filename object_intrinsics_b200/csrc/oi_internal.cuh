@@ -43,6 +43,8 @@ int set_error(int code, const char* fmt, ...);
 //             {b_sigma, b_rgb[0..2], inv_s, 1/inv_s, 0, 0}
 //   [film]    gamma_w[9][128][64], gamma_b[9][128], beta_w[9][128][64], beta_b[9][128]
 //   [tc]      fp16 hi/lo UMMA operand panels for the tcgen05 core (see oi_render_tc.cu)
+//   [tcb]     bf16 hi/lo UMMA operand panels (unscaled) for the adjoint sweeps of the tcgen05 backward
+//             (oi_render_bwd_tc.cu): colour-as-stored, forward orientation l=1..D-1, reverse orientation l=D-1..1
 // ------------------------------------------------------------------------------------------------
 constexpr int kW = OI_WIDTH;
 constexpr int kStyle = OI_STYLE_DIM;
@@ -56,7 +58,7 @@ struct BlobLayout {
   int n_chunks_fine;    // 9 + 16 (D-1)
   int n_chunks_coarse;  // 1 + 8 (D-1)
   int n_chunks_stream;  // n_chunks_fine + 8 (chunks only the backward kernel streams)
-  size_t stream_off, const_off, film_off, tc_off, total_floats;
+  size_t stream_off, const_off, film_off, tc_off, tcb_off, total_floats;
   // const section sub-offsets (relative to const_off)
   static constexpr int kBias = 0;                      // [9][128]
   static constexpr int kWsig = kFilm * kW;             // [128]
@@ -85,7 +87,8 @@ __host__ __device__ inline BlobLayout blob_layout(int depth) {
   L.const_off = (size_t)L.n_chunks_stream * kChunkFloats;
   L.film_off = L.const_off + ((BlobLayout::kConstFloats + 31) / 32) * 32;
   L.tc_off = L.film_off + ((BlobLayout::kFilmFloats + 31) / 32) * 32;
-  L.total_floats = L.tc_off + tc_section_floats(depth);
+  L.tcb_off = L.tc_off + tc_section_floats(depth);
+  L.total_floats = L.tcb_off + tc_section_floats(depth);
   return L;
 }
 
@@ -131,10 +134,18 @@ int launch_render_maps(const OiRenderMapsDesc& d, cudaStream_t st);
 int launch_render_ffma(const RenderKArgs& a, cudaStream_t st);
 int launch_render_tc(const RenderKArgs& a, cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* B, const void* panel, float* D, cudaStream_t st);
-int launch_render_bwd(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
-                      unsigned int* relax_count, float* d_film, float* scratch, int n_ctas, cudaStream_t st);
+int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
+                    unsigned int* relax_count, float* d_film, cudaStream_t st);
+int launch_render_bwd_ffma(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj,
+                           const float* invs_partial, float* d_film, float* scratch, int n_ctas, cudaStream_t st);
+int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
+                         float* film_b, float* d_film, float* scratch, float* slabs, float* aux, int chunk_tiles,
+                         int n_ctas, cudaStream_t st);
 int render_bwd_ctas(int n_tiles);
 size_t render_bwd_scratch_floats();
+int render_bwd_tc_ctas(int n_tiles);
+size_t render_bwd_tc_scratch_floats();
+size_t render_bwd_tc_slab_floats_per_tile();
 size_t render_ffma_scratch_floats(int depth, int* n_ctas, int n_tiles);
 size_t render_tc_scratch_floats(int depth, int* n_ctas, int n_tiles);
 int launch_upsample(int R, int n, int m, const float* rays_o, const float* rays_d, const float* near,

@@ -2,6 +2,9 @@
 // hierarchical up-sampling (renderer.py:137-197 + 44-74) and per-ray compositing (renderer.py:300-338,448-455).
 #include <cuda_fp16.h>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "oi_internal.cuh"
 
 namespace oi {
@@ -134,6 +137,30 @@ __global__ void pack_weights_kernel(const PackArgs a, float* __restrict__ blob) 
     const __half lo = __float2half_rn(v - __half2float(hi));
     // panel image: [hi: kblock0 (8192) | kblock1 (8192)] [lo: kblock0 | kblock1]  (halves)
     __half* base = tc + (size_t)panel * (4 * 8192);
+    const int kb = k >> 6, kk = k & 63;
+    base[kb * 8192 + sw128_index(n, kk)] = hi;
+    base[2 * 8192 + kb * 8192 + sw128_index(n, kk)] = lo;
+  }
+  // ---- bf16 section for the adjoint sweeps of the tcgen05 backward (unscaled: bf16 has fp32's exponent range).
+  // Panel order: colour as stored (N = feature channel, K = colour channel), forward orientation l = 1..D-1
+  // (t_bar_l = W_l g_bar_l), reverse orientation l = D-1..1 (h_bar_l = W_l^T u_bar_l).
+  __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(blob + L.tcb_off);
+  for (size_t i = tid; i < tc_elems; i += nthreads) {
+    const int panel = (int)(i / (kW * kW));
+    const int n = (int)(i % (kW * kW)) / kW;
+    const int k = (int)(i % kW);
+    float v;
+    if (panel == 0) {
+      v = p.views_weight[k * (kW + 3) + n];
+    } else if (panel < D) {
+      v = p.pts_weight[panel][n * kW + k];
+    } else {
+      const int l = (D - 1) - (panel - D);
+      v = p.pts_weight[l][k * kW + n];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* base = tb + (size_t)panel * (4 * 8192);
     const int kb = k >> 6, kk = k & 63;
     base[kb * 8192 + sw128_index(n, kk)] = hi;
     base[2 * 8192 + kb * 8192 + sw128_index(n, kk)] = lo;

@@ -939,8 +939,9 @@ int render_bwd_ctas(int n_tiles) {
 }
 size_t render_bwd_scratch_floats() { return (size_t)kNumSlots * kSlot; }
 
-int launch_render_bwd(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
-                      unsigned int* relax_count, float* d_film, float* scratch, int n_ctas, cudaStream_t st) {
+// relax count + per-ray tail: fills adj [N][8] and invs_partial [R]; zeroes d_film.
+int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
+                    unsigned int* relax_count, float* d_film, cudaStream_t st) {
   TailArgs t;
   t.R = d.n_rays;
   t.S = d.n_samples_total;
@@ -968,17 +969,20 @@ int launch_render_bwd(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* a
   t.adj = adj;
   t.invs_partial = invs_partial;
   t.relax_count = relax_count;
-
-  const int n_inst = geo.n_inst;
   OI_CHECK_CUDA(cudaMemsetAsync(relax_count, 0, 256, st));
-  OI_CHECK_CUDA(cudaMemsetAsync(d_film, 0, (size_t)n_inst * kFilm * 2 * kW * sizeof(float), st));
+  OI_CHECK_CUDA(cudaMemsetAsync(d_film, 0, (size_t)geo.n_inst * kFilm * 2 * kW * sizeof(float), st));
   if (d.g_gradient_error) {
     relax_count_kernel<<<296, 256, 0, st>>>(t);
     OI_CHECK_CUDA(cudaGetLastError());
   }
   tail_bwd_kernel<<<(t.R + 63) / 64, 64, 0, st>>>(t);
   OI_CHECK_CUDA(cudaGetLastError());
+  return OI_OK;
+}
 
+// FP32-FFMA MLP backward (one kernel) + finalize.
+int launch_render_bwd_ffma(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj,
+                           const float* invs_partial, float* d_film, float* scratch, int n_ctas, cudaStream_t st) {
   BwdKArgs a;
   a.r = geo;
   a.adj = adj;
@@ -994,8 +998,8 @@ int launch_render_bwd(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* a
   OI_CHECK_CUDA(cudaGetLastError());
   if (d.evt_core_stop) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d.evt_core_stop), st));
 
-  finalize_bwd_kernel<<<d.depth + 2, kW, 0, st>>>(d.depth, n_inst, d.n_rays, geo.film, d_film, invs_partial, geo.blob,
-                                                  d.grads);
+  finalize_bwd_kernel<<<d.depth + 2, kW, 0, st>>>(d.depth, geo.n_inst, d.n_rays, geo.film, d_film, invs_partial,
+                                                  geo.blob, d.grads);
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

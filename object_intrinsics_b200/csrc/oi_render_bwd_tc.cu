@@ -1,0 +1,799 @@
+// tcgen05 first kernel of the render backward (OI_IMPL_TCGEN05): every per-point sweep of the reverse-mode
+// algorithm of oi_render_bwd.cu / oracle/backward_oracle.py on the tensor cores, in the structure of the forward
+// core (oi_render_tc.cu): one persistent CTA per SM, two 128-point tile slots, row m of a tile <-> TMEM lane m <->
+// two epilogue threads (64 channels each), activations / adjoints written straight into TMEM as the A operand of
+// the next tcgen05.mma, 64 KB weight panels streamed by TMA through a 3-stage ring.
+//
+// Per tile, 4D-2 MMA layers:
+//   recompute  forward l=1..D-1, colour features, reverse l=D-1..1      (fp16 2-term split, panels of the forward)
+//   adjoint    colour^T, backward-of-reverse l=1..D-1 (operand W_l), backward-of-forward l=D-1..1 (operand W_l^T)
+//              (bf16 2-term split: adjoints have no bounded range; unscaled bf16 panels)
+// Contractions over POINTS (weight gradients, per-channel sums) are not done here: every per-point quantity they
+// need is left as an fp32 slab [32 channel-quads][128 points] float4 per tile (oi_wgrad.cuh) and contracted by
+// wgrad_tc_kernel.  Warp roles: 0-7 / 8-15 epilogue of slot 0 / 1, 16 TMA producer, 17 MMA issuer.
+#include <cuda_bf16.h>
+
+#include "oi_internal.cuh"
+#include "oi_render_common.cuh"
+#include "oi_tc.cuh"
+#include "oi_wgrad.cuh"
+
+namespace oi {
+
+namespace {
+
+constexpr int kTcThreads = 576;
+constexpr int kEpiThreadsPerSlot = 256;
+constexpr int kProducerWarp = 16, kMmaWarp = 17;
+constexpr int kTcStages = 3;
+constexpr int kPanelBytes = 65536;
+constexpr int kSubPanelBytes = 16384;
+constexpr float kWScale = 256.0f;
+constexpr float kInvWScale = 1.0f / 256.0f;
+constexpr uint32_t kIdescF16 = tc::make_idesc_f16(128, 128);
+constexpr uint32_t kIdescBf16 = tc::make_idesc_f16(128, 128) | (1u << 7) | (1u << 10);
+
+// per-CTA scratch slabs of one slot ([32 quads][128 points] float4 each)
+constexpr int kCtaG = 0;    // G[l] -> index l-1 (l = 1..7); later holds c_bar_{l-1}
+constexpr int kCtaUC = 7;   // 2^8 * W_cf h_D
+constexpr int kCtaHB = 8;   // h_bar_D
+constexpr int kCtaSlabs = 9;
+
+struct BwdTcArgs {
+  RenderKArgs r;
+  const float* adj;        // [N][8]
+  const float2* film_b;    // [n_inst][9][128] (beta, 1/gamma)
+  float* scratch;
+  size_t scratch_stride;   // floats per CTA
+  float* slabs;            // [tiles of this launch][kSlabsPerTile][32][128] float4
+  float* aux;              // [tiles of this launch][16][128]
+  int tile_begin, tile_end;
+};
+
+struct __align__(1024) BwdTcSmem {
+  unsigned char w[kTcStages][kPanelBytes];
+  float2 film[2][kFilm][kW];   // per slot: (gamma', delta) in the pair layout of film_kernel
+  float4 w0[kW];               // (W_0[n][0..2], 0)
+  float4 head[kW];             // 2^8 * (w_sigma[n], wc_grad[0..2][n])
+  float4 rgbw[kW];             // (W_rgb[0..2][n], 0)
+  unsigned long long w_full[kTcStages], w_empty[kTcStages];
+  float xch[2][128][8];
+  unsigned long long acc_full[2], a_ready[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(BwdTcSmem) <= 227 * 1024, "BwdTcSmem exceeds the 227 KB per-CTA limit");
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void issue_layer_mmas(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase,
+                                                 uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int kb = k >> 2, ks = k & 3;
+    const uint64_t bhi = tc::make_desc_k_sw128(wbase + kb * kSubPanelBytes + ks * 32);
+    const uint64_t blo = tc::make_desc_k_sw128(wbase + 2 * kSubPanelBytes + kb * kSubPanelBytes + ks * 32);
+    tc::mma_ts(acc, a_hi + k * 8, bhi, idesc, k > 0 ? 1u : 0u);
+    tc::mma_ts(acc, a_lo + k * 8, bhi, idesc, 1u);
+    tc::mma_ts(acc, a_hi + k * 8, blo, idesc, 1u);
+  }
+}
+
+__device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  BwdTcSmem& sm = *reinterpret_cast<BwdTcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.r.D;
+  const BlobLayout L = blob_layout(D);
+  const float* cst = a.r.blob + L.const_off;
+  const unsigned char* panels_f16 = reinterpret_cast<const unsigned char*>(a.r.blob + L.tc_off);
+  const unsigned char* panels_bf16 = reinterpret_cast<const unsigned char*>(a.r.blob + L.tcb_off);
+  const int NR = 2 * (D - 1) + 1;   // recompute panels (fp16)
+  const int NP = 4 * D - 2;         // all MMA layers per tile
+  const int n_tiles = a.tile_end - a.tile_begin;
+  const int n_pairs = (n_tiles + 1) / 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&sm.w_full[s], 1);
+      mbar_init(&sm.w_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sm.a_ready[t], kEpiThreadsPerSlot);
+      mbar_init(&sm.acc_full[t], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kProducerWarp) {
+    tc::tmem_alloc(&sm.tmem_base, 512);
+    tc::tmem_relinquish();
+  }
+  for (int n = tid; n < kW; n += kTcThreads) {
+    sm.w0[n] = make_float4(cst[BlobLayout::kW0t + n], cst[BlobLayout::kW0t + kW + n], cst[BlobLayout::kW0t + 2 * kW + n], 0.f);
+    sm.head[n] = make_float4(kWScale * cst[BlobLayout::kWsig + n], kWScale * cst[BlobLayout::kWcg + n],
+                             kWScale * cst[BlobLayout::kWcg + kW + n], kWScale * cst[BlobLayout::kWcg + 2 * kW + n]);
+    sm.rgbw[n] = make_float4(cst[BlobLayout::kWrgb + n], cst[BlobLayout::kWrgb + kW + n],
+                             cst[BlobLayout::kWrgb + 2 * kW + n], 0.f);
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+        for (int p = 0; p < NP; ++p, ++it) {
+          const int stage = it % kTcStages;
+          if (it >= kTcStages) mbar_wait_sleep(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1);
+          mbar_expect_tx(&sm.w_full[stage], kPanelBytes);
+          // adjoint panels: [colour^T | forward orientation l=1..D-1 | reverse orientation l=D-1..1]
+          const unsigned char* src = (p < NR) ? panels_f16 + (size_t)p * kPanelBytes
+                                              : panels_bf16 + (size_t)(p - NR) * kPanelBytes;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            tma_bulk_g2s(sm.w[stage] + q * kSubPanelBytes, src + q * kSubPanelBytes, kSubPanelBytes, &sm.w_full[stage]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int it = 0;
+      uint32_t ar_phase[2] = {0u, 0u};
+      for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+        const int n_active = (2 * pi + 1 < n_tiles) ? 2 : 1;
+        for (int p = 0; p < NP; ++p, ++it) {
+          const int stage = it % kTcStages;
+          mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
+          const uint32_t wbase = smem_u32(sm.w[stage]);
+          const uint32_t idesc = (p < NR) ? kIdescF16 : kIdescBf16;
+          for (int t = 0; t < n_active; ++t) {
+            mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
+            ar_phase[t] ^= 1u;
+            tc::fence_after_thread_sync();
+            const uint32_t acc = tmem_base + t * 256;
+            issue_layer_mmas(acc, acc + 128, acc + 192, wbase, idesc);
+            tc::mma_commit(&sm.acc_full[t]);
+          }
+          tc::mma_commit(&sm.w_empty[stage]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int t = warp >> 3;
+    const int h = (warp >> 2) & 1;
+    const int m = (warp & 3) * 32 + lane;
+    const int sub = tid & (kEpiThreadsPerSlot - 1);
+    const int n0 = h * 64;
+    const int Q0 = h * 16;   // first channel quad of this thread
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t acc = tmem_base + t * 256 + lane_field + n0;
+    const uint32_t a_hi = tmem_base + t * 256 + lane_field + 128 + h * 32;
+    const uint32_t a_lo = a_hi + 64;
+    float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
+                                             (size_t)t * kCtaSlabs * kSlabFloats) + m;
+    uint32_t af_phase = 0u;
+#define OI_CTA(slab, quad) scr4[((size_t)(slab) * 32 + (quad)) * 128]
+#define OI_GS(slab, quad) gs4[((size_t)(slab) * 32 + (quad)) * 128]
+#define OI_A_READY()               \
+  do {                             \
+    tc::wait_st();                 \
+    tc::fence_before_thread_sync(); \
+    mbar_arrive(&sm.a_ready[t]);   \
+  } while (0)
+#define OI_WAIT_ACC()                                \
+  do {                                               \
+    mbar_wait_sleep(&sm.acc_full[t], af_phase);      \
+    af_phase ^= 1u;                                  \
+    tc::fence_after_thread_sync();                   \
+  } while (0)
+
+    for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+      const int lt = 2 * pi + t;   // tile index inside this launch
+      if (lt >= n_tiles) continue;
+      const int tile = a.tile_begin + lt;
+      const int inst = tile / a.r.tiles_per_inst;
+      const int tin = tile - inst * a.r.tiles_per_inst;
+      float4* gs4 = reinterpret_cast<float4*>(a.slabs + (size_t)lt * kSlabsPerTile * kSlabFloats) + m;
+      float* aux = a.aux + (size_t)lt * 16 * 128 + m;
+      const float2* fb_inst = a.film_b + (size_t)inst * kFilm * kW;
+      {
+        const float2* src = reinterpret_cast<const float2*>(a.r.film_tc) + (size_t)inst * kFilm * kW;
+        float2* dst = &sm.film[t][0][0];
+        for (int i = sub; i < kFilm * kW; i += kEpiThreadsPerSlot) dst[i] = src[i];
+      }
+      float px, py, pz, sdf_bar, nb0, nb1, nb2, zb0, zb1, zb2;
+      {
+        const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
+        px = pc.px;
+        py = pc.py;
+        pz = pc.pz;
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+        if (pc.valid) {
+          const float4* ap = reinterpret_cast<const float4*>(a.adj + ((size_t)pc.ray * a.r.S + pc.si) * 8);
+          q0 = ap[0];
+          q1 = ap[1];
+        }
+        sdf_bar = q0.x; nb0 = q0.y; nb1 = q0.z; nb2 = q0.w;
+        zb0 = q1.x; zb1 = q1.y; zb2 = q1.z;
+        if (h == 0) {
+          aux[(kAuxX + 0) * 128] = px;
+          aux[(kAuxX + 1) * 128] = py;
+          aux[(kAuxX + 2) * 128] = pz;
+          aux[(kAuxZB + 0) * 128] = zb0;
+          aux[(kAuxZB + 1) * 128] = zb1;
+          aux[(kAuxZB + 2) * 128] = zb2;
+          aux[kAuxSB * 128] = sdf_bar;
+        }
+      }
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);
+
+      // =========================== recompute ===========================
+      // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
+      {
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][0]) + n0 * 2;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float s[4], ar[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 16 + q * 4 + e;
+              const float4 w0 = sm.w0[n0 + j];
+              const float u = fmaf(w0.z, pz, fmaf(w0.y, py, w0.x * px));
+              ar[e] = fmaf(flf[(j >> 1) * 4 + (j & 1)], u, flf[(j >> 1) * 4 + 2 + (j & 1)]);
+              s[e] = __sinf(ar[e]);
+            }
+            OI_GS(kSlabArg + 0, Q0 + c * 4 + q) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
+            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
+        }
+        OI_A_READY();
+      }
+      // ---------------- forward layers 1..D-1 ----------------
+      for (int l = 1; l < D; ++l) {
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float s[4], ar[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 16 + q * 4 + e;
+              ar[e] = fmaf(flf[(j >> 1) * 4 + (j & 1)], __uint_as_float(u[q * 4 + e]), flf[(j >> 1) * 4 + 2 + (j & 1)]);
+              s[e] = __sinf(ar[e]);
+            }
+            OI_GS(kSlabArg + l, Q0 + c * 4 + q) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
+            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
+        }
+        OI_A_READY();
+      }
+      // ---------------- colour features -> slot UC; t_{D-1} = w_sigma gamma cos(a_{D-1}) ----------------
+      {
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][D - 1]) + n0 * 2;
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int quad = Q0 + c * 4 + q;
+            OI_CTA(kCtaUC, quad) = make_float4(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1]),
+                                               __uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3]));
+            const float4 ar4 = OI_GS(kSlabArg + D - 1, quad);
+            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
+            float tv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 16 + q * 4 + e;
+              tv[e] = sm.head[n0 + j].x * flf[(j >> 1) * 4 + (j & 1)] * __cosf(ar[e]);  // 2^8 w_s * gamma/2^8 * cos
+            }
+            OI_GS(kSlabT + D - 1, quad) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+            tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
+            tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
+        }
+        OI_A_READY();
+      }
+      // ---------------- reverse sweep l = D-1 .. 1: g_l (slot G[l]), t_{l-1} (slab T[l-1]) ----------------
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      for (int l = D - 1; l >= 1; --l) {
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][l - 1]) + n0 * 2;
+        const float gscale = (l - 1 == 0) ? kInvWScale : 1.0f;   // gamma'_0 is unscaled
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int quad = Q0 + c * 4 + q;
+            const float4 ar4 = OI_GS(kSlabArg + l - 1, quad);
+            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
+            float gv[4], tv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 16 + q * 4 + e;
+              const float accv = __uint_as_float(u[q * 4 + e]);           // 2^8 g_l
+              gv[e] = accv * kInvWScale;
+              tv[e] = accv * (flf[(j >> 1) * 4 + (j & 1)] * gscale) * __cosf(ar[e]);  // g_l gamma cos = t_{l-1}
+            }
+            OI_CTA(kCtaG + l - 1, quad) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+            OI_GS(kSlabT + l - 1, quad) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+            if (l > 1) {
+              tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
+              tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 w = sm.w0[n0 + c * 16 + q * 4 + e];
+                gx = fmaf(w.x, tv[e], gx);
+                gy = fmaf(w.y, tv[e], gy);
+                gz = fmaf(w.z, tv[e], gz);
+              }
+            }
+          }
+          if (l > 1) {
+            tc::tmem_st8(a_hi + c * 8, hi);
+            tc::tmem_st8(a_lo + c * 8, lo);
+          }
+        }
+        if (l > 1) OI_A_READY();
+      }
+      // ---------------- combine the two column halves: normal ----------------
+      float* xch = &sm.xch[t][m][0];
+      xch[h * 4 + 1] = gx;
+      xch[h * 4 + 2] = gy;
+      xch[h * 4 + 3] = gz;
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);
+      {
+        const int o = (h ^ 1) * 4;
+        gx += xch[o + 1];
+        gy += xch[o + 2];
+        gz += xch[o + 3];
+      }
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);   // exchange buffer free again
+
+      // =========================== adjoint sweeps ===========================
+      // ---------------- colour layer: recompute + backward; A <- u_bar_c (bf16) ----------------
+      float nc0 = 0.f, nc1 = 0.f, nc2 = 0.f;   // W_cg^T u_bar_c, this thread's channels
+      {
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][OI_MAX_DEPTH]) + n0 * 2;
+        const float2* fb = fb_inst + OI_MAX_DEPTH * kW + n0;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int quad = Q0 + c * 4 + q;
+            const float4 uc4 = OI_CTA(kCtaUC, quad);
+            const float uc[4] = {uc4.x, uc4.y, uc4.z, uc4.w};
+            float ar[4], ub_[4], dg[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 16 + q * 4 + e;
+              const float4 hd = sm.head[n0 + j];
+              float pre = fmaf(hd.y, gx, uc[e]);
+              pre = fmaf(hd.z, gy, pre);
+              pre = fmaf(hd.w, gz, pre);
+              const float gp = flf[(j >> 1) * 4 + (j & 1)];
+              ar[e] = fmaf(gp, pre, flf[(j >> 1) * 4 + 2 + (j & 1)]);
+              const float cs = __cosf(ar[e]);
+              const float4 rw = sm.rgbw[n0 + j];
+              const float hb = fmaf(rw.x, zb0, fmaf(rw.y, zb1, rw.z * zb2));
+              const float ab = hb * cs;
+              const float2 bg = __ldg(fb + j);                 // (beta, 1/gamma)
+              dg[e] = ab * (ar[e] - bg.x) * bg.y;              // a_bar * u_c
+              ub_[e] = ab * (gp * kWScale);                    // u_bar_c = a_bar * gamma
+              nc0 = fmaf(hd.y * kInvWScale, ub_[e], nc0);
+              nc1 = fmaf(hd.z * kInvWScale, ub_[e], nc1);
+              nc2 = fmaf(hd.w * kInvWScale, ub_[e], nc2);
+            }
+            OI_GS(kSlabArgC, quad) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+            OI_GS(kSlabDGC, quad) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+            OI_GS(kSlabUBC, quad) = make_float4(ub_[0], ub_[1], ub_[2], ub_[3]);
+            split2_bf16(ub_[0], ub_[1], hi[2 * q], lo[2 * q]);
+            split2_bf16(ub_[2], ub_[3], hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
+        }
+        OI_A_READY();
+      }
+      // normal_bar = direct + W_cg^T u_bar_c (both halves)
+      xch[h * 4 + 1] = nc0;
+      xch[h * 4 + 2] = nc1;
+      xch[h * 4 + 3] = nc2;
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);
+      {
+        const int o = (h ^ 1) * 4;
+        nb0 += nc0 + xch[o + 1];
+        nb1 += nc1 + xch[o + 2];
+        nb2 += nc2 + xch[o + 3];
+      }
+      if (h == 0) {
+        aux[(kAuxN + 0) * 128] = gx;
+        aux[(kAuxN + 1) * 128] = gy;
+        aux[(kAuxN + 2) * 128] = gz;
+        aux[(kAuxNB + 0) * 128] = nb0;
+        aux[(kAuxNB + 1) * 128] = nb1;
+        aux[(kAuxNB + 2) * 128] = nb2;
+      }
+      // ---------------- h_bar_D = W_cf^T u_bar_c + sdf_bar w_s -> slot HB;
+      //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
+      {
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][0]) + n0 * 2;
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int quad = Q0 + c * 4 + q;
+            float hb[4], cb[4], gb[4];
+            const float4 ar4 = OI_GS(kSlabArg + 0, quad);
+            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
+            const float4 g14 = OI_CTA(kCtaG + 0, quad);   // g_1
+            const float g1[4] = {g14.x, g14.y, g14.z, g14.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 16 + q * 4 + e;
+              hb[e] = fmaf(sdf_bar, sm.head[n0 + j].x * kInvWScale, __uint_as_float(u[q * 4 + e]));
+              const float4 w = sm.w0[n0 + j];
+              const float tb = fmaf(w.x, nb0, fmaf(w.y, nb1, w.z * nb2));   // t_bar_0 = W_0 normal_bar
+              const float c0 = flf[(j >> 1) * 4 + (j & 1)] * __cosf(ar[e]);  // gamma_0 cos a_0
+              cb[e] = tb * g1[e];
+              gb[e] = tb * c0;
+            }
+            OI_CTA(kCtaHB, quad) = make_float4(hb[0], hb[1], hb[2], hb[3]);
+            OI_CTA(kCtaG + 0, quad) = make_float4(cb[0], cb[1], cb[2], cb[3]);   // c_bar_0
+            OI_GS(kSlabGB + 1, quad) = make_float4(gb[0], gb[1], gb[2], gb[3]);
+            split2_bf16(gb[0], gb[1], hi[2 * q], lo[2 * q]);
+            split2_bf16(gb[2], gb[3], hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
+        }
+        OI_A_READY();
+      }
+      // ---------------- backward of the reverse sweep, l = 1..D-1: t_bar_l = W_l g_bar_l ----------------
+      for (int l = 1; l < D; ++l) {
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
+        const float2* fb = fb_inst + l * kW + n0;
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int quad = Q0 + c * 4 + q;
+            const float4 ar4 = OI_GS(kSlabArg + l, quad);
+            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
+            float o[4];
+            if (l < D - 1) {
+              const float4 g4 = OI_CTA(kCtaG + l, quad);   // g_{l+1}
+              const float gn[4] = {g4.x, g4.y, g4.z, g4.w};
+              float cb[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = c * 16 + q * 4 + e;
+                const float tb = __uint_as_float(u[q * 4 + e]);
+                cb[e] = tb * gn[e];                                                     // c_bar_l
+                o[e] = tb * (flf[(j >> 1) * 4 + (j & 1)] * kWScale) * __cosf(ar[e]);    // g_bar_{l+1}
+              }
+              OI_CTA(kCtaG + l, quad) = make_float4(cb[0], cb[1], cb[2], cb[3]);
+              OI_GS(kSlabGB + l + 1, quad) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+              // top: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
+              const float4 hb4 = OI_CTA(kCtaHB, quad);
+              const float hb[4] = {hb4.x, hb4.y, hb4.z, hb4.w};
+              float dws[4], dg[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = c * 16 + q * 4 + e;
+                const float tb = __uint_as_float(u[q * 4 + e]);
+                const float gam = flf[(j >> 1) * 4 + (j & 1)] * kWScale;
+                const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
+                dws[e] = tb * gam * cs;
+                const float cbar = tb * (sm.head[n0 + j].x * kInvWScale);
+                const float ab = hb[e] * cs - cbar * gam * sn;
+                const float2 bg = __ldg(fb + j);
+                dg[e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cbar * cs);
+                o[e] = ab * gam;   // u_bar_{D-1}
+              }
+              OI_GS(kSlabDWS, quad) = make_float4(dws[0], dws[1], dws[2], dws[3]);
+              OI_GS(kSlabDG + l, quad) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+              OI_GS(kSlabUB + l, quad) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
+            split2_bf16(o[2], o[3], hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          tc::tmem_st8(a_hi + c * 8, hi);
+          tc::tmem_st8(a_lo + c * 8, lo);
+        }
+        OI_A_READY();
+      }
+      // ---------------- backward of the forward sweep: h_bar_l = W_l^T u_bar_l, then layer k = l-1 ----------------
+      for (int l = D - 1; l >= 1; --l) {
+        const int k = l - 1;
+        const float* flf = reinterpret_cast<const float*>(sm.film[t][k]) + n0 * 2;
+        const float2* fb = fb_inst + k * kW + n0;
+        const float gsc = (k == 0) ? 1.0f : kWScale;
+        OI_WAIT_ACC();
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int quad = Q0 + c * 4 + q;
+            const float4 ar4 = OI_GS(kSlabArg + k, quad);
+            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
+            const float4 cb4 = OI_CTA(kCtaG + k, quad);   // c_bar_k
+            const float cb[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
+            float o[4], dg[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 16 + q * 4 + e;
+              const float gam = flf[(j >> 1) * 4 + (j & 1)] * gsc;
+              const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
+              const float ab = __uint_as_float(u[q * 4 + e]) * cs - cb[e] * gam * sn;
+              const float2 bg = __ldg(fb + j);
+              dg[e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cb[e] * cs);
+              o[e] = ab * gam;   // u_bar_k
+            }
+            OI_GS(kSlabDG + k, quad) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+            OI_GS(kSlabUB + k, quad) = make_float4(o[0], o[1], o[2], o[3]);
+            if (k >= 1) {
+              split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
+              split2_bf16(o[2], o[3], hi[2 * q + 1], lo[2 * q + 1]);
+            }
+          }
+          if (k >= 1) {
+            tc::tmem_st8(a_hi + c * 8, hi);
+            tc::tmem_st8(a_lo + c * 8, lo);
+          }
+        }
+        if (k >= 1) OI_A_READY();
+      }
+      named_bar_sync(1 + t, kEpiThreadsPerSlot);   // film table / exchange buffer of this slot may be reused now
+    }
+#undef OI_CTA
+#undef OI_GS
+#undef OI_A_READY
+#undef OI_WAIT_ACC
+  }
+
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == kProducerWarp) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// (beta, 1/gamma) per instance / FiLM layer / channel, from the (gamma, beta) table of film_kernel
+__global__ void film_b_kernel(const float* __restrict__ film, float2* __restrict__ film_b, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [inst][9][128]
+  if (i >= n) return;
+  const int ch = i % kW, il = i / kW;
+  const float g = film[(size_t)il * 2 * kW + ch], b = film[(size_t)il * 2 * kW + kW + ch];
+  film_b[i] = make_float2(b, 1.0f / g);
+}
+
+// TC variant of the finalize step: the (dgamma, db) table -> dbeta = db / gamma per instance, db summed over
+// instances, variance.
+__global__ void finalize_bwd_tc_kernel(int D, int n_inst, int R, const float* __restrict__ film,
+                                       const float* __restrict__ d_film, const float* __restrict__ invs_partial,
+                                       const float* __restrict__ blob, OiNetGrads g) {
+  const int n = threadIdx.x;
+  const int l = blockIdx.x;
+  if (l <= D) {
+    const int slot = (l < D) ? l : OI_MAX_DEPTH;
+    float s = 0.f;
+    for (int i = 0; i < n_inst; ++i) {
+      const size_t o = ((size_t)i * kFilm + slot) * 2 * kW;
+      const float db = d_film[o + kW + n];
+      s += db;
+      g.film_gamma[((size_t)i * kFilm + slot) * kW + n] += d_film[o + n];
+      g.film_beta[((size_t)i * kFilm + slot) * kW + n] += db / film[o + n];
+    }
+    float* dst = (l < D) ? g.pts_bias[l] : g.views_bias;
+    dst[n] += s;
+  } else {
+    __shared__ double red[4];
+    double s = 0.0;
+    for (int r = n; r < R; r += blockDim.x) s += (double)invs_partial[r];
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((n & 31) == 0) red[n >> 5] = s;
+    __syncthreads();
+    if (n == 0) {
+      const BlobLayout L = blob_layout(D);
+      const float inv_s = blob[L.const_off + BlobLayout::kScalars + 4];
+      const double tot = red[0] + red[1] + red[2] + red[3];
+      const bool inside = inv_s > 1e-6f && inv_s < 1e6f;
+      if (inside) g.variance[0] += (float)(tot * 10.0 * (double)inv_s);
+    }
+  }
+}
+
+}  // namespace
+
+int render_bwd_tc_ctas(int n_tiles) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_pairs = (n_tiles + 1) / 2;
+  int ctas = sms < n_pairs ? sms : n_pairs;
+  return ctas < 1 ? 1 : ctas;
+}
+size_t render_bwd_tc_scratch_floats() { return (size_t)2 * kCtaSlabs * kSlabFloats; }
+size_t render_bwd_tc_slab_floats_per_tile() { return (size_t)kSlabsPerTile * kSlabFloats + 16 * 128; }
+
+// Runs the two tensor-core kernels over tiles [0, n_tiles) in chunks of at most `chunk_tiles`.
+int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
+                         float* film_b, float* d_film, float* scratch, float* slabs, float* aux, int chunk_tiles,
+                         int n_ctas, cudaStream_t st) {
+  const int n_inst = geo.n_inst, D = geo.D;
+  {
+    const int n = n_inst * kFilm * kW;
+    film_b_kernel<<<(n + 255) / 256, 256, 0, st>>>(geo.film, reinterpret_cast<float2*>(film_b), n);
+    OI_CHECK_CUDA(cudaGetLastError());
+  }
+  OI_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(BwdTcSmem)));
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  if (d.evt_core_start) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d.evt_core_start), st));
+  for (int t0 = 0; t0 < geo.n_tiles; t0 += chunk_tiles) {
+    const int t1 = (t0 + chunk_tiles < geo.n_tiles) ? t0 + chunk_tiles : geo.n_tiles;
+    BwdTcArgs a;
+    a.r = geo;
+    a.adj = adj;
+    a.film_b = reinterpret_cast<const float2*>(film_b);
+    a.scratch = scratch;
+    a.scratch_stride = render_bwd_tc_scratch_floats();
+    a.slabs = slabs;
+    a.aux = aux;
+    a.tile_begin = t0;
+    a.tile_end = t1;
+    const int ctas = render_bwd_tc_ctas(t1 - t0) < n_ctas ? render_bwd_tc_ctas(t1 - t0) : n_ctas;
+    bwd_tc_kernel<<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+
+    // ---- contraction over the points of this chunk
+    WgArgs w;
+    memset(&w, 0, sizeof(w));
+    w.n_tiles = t1 - t0;
+    w.tiles_per_inst = geo.tiles_per_inst;
+    w.slabs_per_tile = kSlabsPerTile;
+    w.slabs = slabs;
+    w.aux = aux;
+    w.tile0 = t0;
+    float* dfilm0 = d_film;
+    auto dgam = [&](int slot) { return dfilm0 + (size_t)slot * 2 * kW; };
+    auto dbia = [&](int slot) { return dfilm0 + (size_t)slot * 2 * kW + kW; };
+    const int inst_stride = kFilm * 2 * kW;
+    auto col = [](int src, int slab, int tf, int mult, float* out, int inst_stride_, int ch_stride) {
+      WgCol c;
+      c.src = src; c.slab = slab; c.tf = tf; c.mult = mult; c.out = out; c.inst_stride = inst_stride_;
+      c.ch_stride = ch_stride;
+      return c;
+    };
+    int ng = 0;
+    for (int l = 1; l < D; ++l) {
+      WgGroup& g = w.groups[ng++];
+      g.n_pairs = 2;
+      g.pairs[0] = WgPair{kSlabUB + l, kSlabArg + l - 1, WG_TF_RAW, WG_TF_SIN};   // u_bar_l (x) h_l
+      g.pairs[1] = WgPair{kSlabT + l, kSlabGB + l, WG_TF_RAW, WG_TF_RAW};         // t_l (x) g_bar_l
+      g.n_cols = 2;
+      g.cols[0] = col(WG_SRC_PAIR_X, 0, 0, -1, dbia(l), inst_stride, 1);
+      g.cols[1] = col(WG_SRC_SLAB, kSlabDG + l, WG_TF_RAW, -1, dgam(l), inst_stride, 1);
+      g.out = d.grads.pts_weight[l];
+      g.out_ld = kW;
+    }
+    {  // colour layer: u_bar_c (x) h_D
+      WgGroup& g = w.groups[ng++];
+      g.n_pairs = 1;
+      g.pairs[0] = WgPair{kSlabUBC, kSlabArg + D - 1, WG_TF_RAW, WG_TF_SIN};
+      g.n_cols = 5;
+      g.cols[0] = col(WG_SRC_PAIR_X, 0, 0, -1, dbia(OI_MAX_DEPTH), inst_stride, 1);
+      for (int j = 0; j < 3; ++j)
+        g.cols[1 + j] = col(WG_SRC_PAIR_X, 0, 0, kAuxN + j, d.grads.views_weight + kW + j, 0, kW + 3);
+      g.cols[4] = col(WG_SRC_PAIR_Y, 0, 0, kAuxSB, d.grads.sigma_weight, 0, 1);   // d w_s += sdf_bar h_D
+      g.out = d.grads.views_weight;
+      g.out_ld = kW + 3;
+    }
+    {  // heads
+      WgGroup& g = w.groups[ng++];
+      g.n_pairs = 0;
+      g.n_cols = 5;
+      g.cols[0] = col(WG_SRC_SLAB, kSlabDGC, WG_TF_RAW, -1, dgam(OI_MAX_DEPTH), inst_stride, 1);
+      for (int j = 0; j < 3; ++j)
+        g.cols[1 + j] = col(WG_SRC_SLAB, kSlabArgC, WG_TF_SIN, kAuxZB + j, d.grads.rgb_weight + j * kW, 0, 1);
+      g.cols[4] = col(WG_SRC_SLAB, kSlabDWS, WG_TF_RAW, -1, d.grads.sigma_weight, 0, 1);
+    }
+    {  // layer 0, first part: d b_0, d gamma_0, dW_0 += u_bar_0 (x) x
+      WgGroup& g = w.groups[ng++];
+      g.n_pairs = 0;
+      g.n_cols = 5;
+      g.cols[0] = col(WG_SRC_SLAB, kSlabUB + 0, WG_TF_RAW, -1, dbia(0), inst_stride, 1);
+      g.cols[1] = col(WG_SRC_SLAB, kSlabDG + 0, WG_TF_RAW, -1, dgam(0), inst_stride, 1);
+      for (int j = 0; j < 3; ++j)
+        g.cols[2 + j] = col(WG_SRC_SLAB, kSlabUB + 0, WG_TF_RAW, kAuxX + j, d.grads.pts_weight[0] + j, 0, 3);
+    }
+    {  // layer 0, second part: dW_0 += t_0 (x) normal_bar
+      WgGroup& g = w.groups[ng++];
+      g.n_pairs = 0;
+      g.n_cols = 3;
+      for (int j = 0; j < 3; ++j)
+        g.cols[j] = col(WG_SRC_SLAB, kSlabT + 0, WG_TF_RAW, kAuxNB + j, d.grads.pts_weight[0] + j, 0, 3);
+    }
+    w.n_groups = ng;
+    w.n_splits = sms / ng < 1 ? 1 : sms / ng;
+    if (w.n_splits > w.n_tiles) w.n_splits = w.n_tiles;
+    int rc = launch_wgrad_tc(w, st);
+    if (rc) return rc;
+  }
+  if (d.evt_core_stop) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d.evt_core_stop), st));
+
+  finalize_bwd_tc_kernel<<<D + 2, kW, 0, st>>>(D, n_inst, d.n_rays, geo.film, d_film, invs_partial, geo.blob, d.grads);
+  OI_CHECK_CUDA(cudaGetLastError());
+  return OI_OK;
+}
+
+}  // namespace oi

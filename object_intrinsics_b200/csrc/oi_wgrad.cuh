@@ -47,6 +47,7 @@ struct WgGroup {
 };
 struct WgArgs {
   int n_tiles, tiles_per_inst, n_groups, n_splits, slabs_per_tile;
+  int tile0;           // global index of slab tile 0 (instance of slab tile t = (tile0 + t) / tiles_per_inst)
   const float* slabs;  // [n_tiles][slabs_per_tile][32][128] float4
   const float* aux;    // [n_tiles][16][128]
   WgGroup groups[WG_MAX_GROUPS];

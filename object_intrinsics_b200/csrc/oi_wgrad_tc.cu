@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
 #pragma unroll
     for (int c = 0; c < kMaxCol; ++c) col[c].zero();
     int it = 0;
-    int cur_inst = (t_begin < t_end) ? t_begin / a.tiles_per_inst : 0;
+    int cur_inst = (t_begin < t_end) ? (a.tile0 + t_begin) / a.tiles_per_inst : 0;
 
     auto flush_cols = [&](int inst) {
 #pragma unroll
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
     };
 
     for (int tile = t_begin; tile < t_end; ++tile) {
-      const int inst = tile / a.tiles_per_inst;
+      const int inst = (a.tile0 + tile) / a.tiles_per_inst;
       if (inst != cur_inst) {
         flush_cols(cur_inst);
         cur_inst = inst;

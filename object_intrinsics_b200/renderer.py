@@ -216,6 +216,7 @@ class _RenderFunction(torch.autograd.Function):
         d = _lib.OiRenderBwdDesc()
         d.n_rays, d.rays_per_instance, d.n_samples_total, d.n_samples = R, R // n_inst, S, r.n_samples
         d.depth, d.flags, d.cos_anneal_ratio = D, r.flags, ctx.cos_anneal_ratio
+        d.impl = _IMPL[r.bwd_impl]
         d.rays_o, d.rays_d, d.z_vals, d.style_w = rays_o.data_ptr(), rays_d.data_ptr(), z_vals.data_ptr(), w.data_ptr()
         d.packed_weights = ctx.blob.data_ptr()
         d.sdf, d.gradients, d.raw_color = sdf.data_ptr(), gradients.data_ptr(), raw_color.data_ptr()
@@ -275,6 +276,7 @@ class NeuSRenderer:
         if grad_impl not in ("cuda", "torch"):
             raise ValueError("grad_impl must be 'cuda' or 'torch'")
         self.grad_impl = os.environ.get("OI_GRAD_IMPL", grad_impl)
+        self.bwd_impl = os.environ.get("OI_BWD_IMPL", impl)   # core of oi_render_backward: auto/tcgen05 or ffma
         self._packed = PackedWeights()
         self._workspace: Optional[torch.Tensor] = None
         self._bwd_workspace: Optional[torch.Tensor] = None

@@ -94,10 +94,26 @@ def _inputs(name, n_rays, n_inst=1):
     return meta, c, w
 
 
+@pytest.mark.parametrize("impl", ["ffma", "tcgen05"])
 @pytest.mark.parametrize("name", ["cfg1_n16_m0", "cfgd_n16_m4_D8"])
-def test_all_adjoints_small(name):
+def test_all_adjoints_small(name, impl):
     meta, c, w = _inputs(name, 64)
-    _check(meta, c, w, ADJ_KEYS, 0.3)
+    _check(meta, c, w, ADJ_KEYS, 0.3, impl=impl)
+
+
+def test_adjoint_scale_invariance_tcgen05():
+    """bf16-split adjoint sweeps: gradients of 1e-6 * loss are 1e-6 * gradients (no fp16-style range loss)."""
+    meta, c, w = _inputs("cfgd_n16_m4_D8", 64)
+    r = _build(meta, n_importance=0, impl="tcgen05")
+    named = _params(r)
+    grads = []
+    for scale in (1.0, 1e-6):
+        out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0, perturb_overwrite=0, w=w)
+        loss = scale * (out["color_fine"].sum() + out["weight_sum"].sum() + out["gradient_error"])
+        grads.append(torch.autograd.grad(loss, [t for _, t in named]))
+    for (k, _), g1, g2 in zip(named, *grads):
+        s = float(g1.abs().max()) + 1e-30
+        assert float((g2 * 1e6 - g1).abs().max()) / s < 2e-4, k
 
 
 @pytest.mark.parametrize("impl", ["ffma", "tcgen05"])
