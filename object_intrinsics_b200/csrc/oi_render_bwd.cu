@@ -749,6 +749,8 @@ struct TailArgs {
   float* adj;               // [N][8]
   float* invs_partial;      // [R]
   unsigned int* relax_count;
+  float* d_sigma_bias;      // += sum sdf_bar, or NULL (the FFMA MLP kernel does it itself)
+  float* d_rgb_bias;        // [3] += sum zrgb_bar, or NULL
 };
 
 __device__ __forceinline__ float section_dist(const TailArgs& a, const float* zr, int i) {
@@ -789,9 +791,10 @@ __device__ __forceinline__ AlphaTerms alpha_terms(const TailArgs& a, const float
 }
 
 __global__ void tail_bwd_kernel(const TailArgs a) {
-  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= a.R) return;
-  const int S = a.S;
+  const int ray_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = ray_raw < a.R;
+  const int ray = live ? ray_raw : a.R - 1;   // dead threads shadow the last ray (no stores) for the warp sums
+  const int S = live ? a.S : 0;
   const BlobLayout L = blob_layout(a.depth);
   const float inv_s = a.blob[L.const_off + BlobLayout::kScalars + 4];
   const float* zr = a.z_vals + (size_t)ray * S;
@@ -827,6 +830,7 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
   }
   // pass 2 (back to front)
   float suffix = 0.f, invs_bar = 0.f;
+  float sum_sb = 0.f, sum_z0 = 0.f, sum_z1 = 0.f, sum_z2 = 0.f;
   for (int i = S - 1; i >= 0; --i) {
     const size_t gp = base + i;
     const float sdf = a.sdf[gp];
@@ -882,11 +886,30 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
       rb2 += a.g_raw_color[gp * 3 + 2];
     }
     float4* out = reinterpret_cast<float4*>(a.adj + gp * 8);
+    const float z0 = rb0 * r * (1.0f - r), z1 = rb1 * g * (1.0f - g), z2 = rb2 * b * (1.0f - b);
     out[0] = make_float4(sdf_bar, nb0, nb1, nb2);
-    out[1] = make_float4(rb0 * r * (1.0f - r), rb1 * g * (1.0f - g), rb2 * b * (1.0f - b), 0.f);
+    out[1] = make_float4(z0, z1, z2, 0.f);
+    sum_sb += sdf_bar;
+    sum_z0 += z0;
+    sum_z1 += z1;
+    sum_z2 += z2;
   }
-  if (a.g_s_val) invs_bar -= a.g_s_val[ray] / (inv_s * inv_s);
-  a.invs_partial[ray] = invs_bar;
+  if (live) {
+    if (a.g_s_val) invs_bar -= a.g_s_val[ray] / (inv_s * inv_s);
+    a.invs_partial[ray] = invs_bar;
+  }
+  if (a.d_sigma_bias) {
+    sum_sb = warp_sum(sum_sb);
+    sum_z0 = warp_sum(sum_z0);
+    sum_z1 = warp_sum(sum_z1);
+    sum_z2 = warp_sum(sum_z2);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(a.d_sigma_bias, sum_sb);
+      atomicAdd(a.d_rgb_bias + 0, sum_z0);
+      atomicAdd(a.d_rgb_bias + 1, sum_z1);
+      atomicAdd(a.d_rgb_bias + 2, sum_z2);
+    }
+  }
 }
 
 // db_l = sum_inst gamma * dbeta (u_bar = a_bar * gamma), d variance = inv_s_bar * 10 * inv_s (inside the clip).
@@ -941,7 +964,7 @@ size_t render_bwd_scratch_floats() { return (size_t)kNumSlots * kSlot; }
 
 // relax count + per-ray tail: fills adj [N][8] and invs_partial [R]; zeroes d_film.
 int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
-                    unsigned int* relax_count, float* d_film, cudaStream_t st) {
+                    unsigned int* relax_count, float* d_film, bool head_biases, cudaStream_t st) {
   TailArgs t;
   t.R = d.n_rays;
   t.S = d.n_samples_total;
@@ -969,6 +992,8 @@ int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj
   t.adj = adj;
   t.invs_partial = invs_partial;
   t.relax_count = relax_count;
+  t.d_sigma_bias = head_biases ? d.grads.sigma_bias : nullptr;
+  t.d_rgb_bias = head_biases ? d.grads.rgb_bias : nullptr;
   OI_CHECK_CUDA(cudaMemsetAsync(relax_count, 0, 256, st));
   OI_CHECK_CUDA(cudaMemsetAsync(d_film, 0, (size_t)geo.n_inst * kFilm * 2 * kW * sizeof(float), st));
   if (d.g_gradient_error) {
