@@ -405,7 +405,7 @@ int oi_selftest_wgrad(const float* slabs, const float* aux, int32_t n_tiles, int
   a.n_tiles = n_tiles;
   a.tiles_per_inst = n_tiles;
   a.n_groups = 1;
-  a.n_splits = n_splits;
+  a.n_ctas = n_splits;
   a.slabs_per_tile = slabs_per_tile;
   a.slabs = slabs;
   a.aux = aux;
@@ -420,6 +420,7 @@ int oi_selftest_wgrad(const float* slabs, const float* aux, int32_t n_tiles, int
   g.cols[0].ch_stride = 1;
   g.out = d;
   g.out_ld = 128;
+  g.weight = 1;
   return launch_wgrad_tc(a, static_cast<cudaStream_t>(stream));
 }
 

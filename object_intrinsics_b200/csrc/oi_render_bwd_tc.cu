@@ -48,6 +48,8 @@ struct BwdTcArgs {
   float* slabs;            // [tiles of this launch][kSlabsPerTile][32][128] float4
   float* aux;              // [tiles of this launch][16][128]
   int tile_begin, tile_end;
+  OiNetGrads g;            // per-channel sums over points are reduced here (warp butterflies + atomics)
+  float* d_film;           // [n_inst][9][2][128] (dgamma, db)
 };
 
 struct __align__(1024) BwdTcSmem {
@@ -86,6 +88,42 @@ __device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, ui
   const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Sum over the 32 lanes of a warp (= 32 sample points) of 16 per-lane values (= 16 channels), by recursive halving:
+// after the four exchange steps lane L holds channel 8 b4 + 4 b3 + 2 b2 + b1 (bits of L) summed over 16 lanes; one
+// more exchange completes the sum, and the even lanes add it to dst[channel * stride].  16 shuffles per call.
+__device__ __forceinline__ void colsum16(const float (&v)[16], float* dst, int stride, int lane) {
+  float a8[8], a4[4], a2[2];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
+      a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float keep = up ? a8[i + 4] : a8[i], send = up ? a8[i] : a8[i + 4];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float keep = up ? a4[i + 2] : a4[i], send = up ? a4[i] : a4[i + 2];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  const bool up = (lane & 2) != 0;
+  float a1 = (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  if ((lane & 1) == 0) atomicAdd(dst + (size_t)ch * stride, a1);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a) {
@@ -210,6 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       float4* gs4 = reinterpret_cast<float4*>(a.slabs + (size_t)lt * kSlabsPerTile * kSlabFloats) + m;
       float* aux = a.aux + (size_t)lt * 16 * 128 + m;
       const float2* fb_inst = a.film_b + (size_t)inst * kFilm * kW;
+      float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][dgamma | db][128]
       {
         const float2* src = reinterpret_cast<const float2*>(a.r.film_tc) + (size_t)inst * kFilm * kW;
         float2* dst = &sm.film[t][0][0];
@@ -229,15 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         }
         sdf_bar = q0.x; nb0 = q0.y; nb1 = q0.z; nb2 = q0.w;
         zb0 = q1.x; zb1 = q1.y; zb2 = q1.z;
-        if (h == 0) {
-          aux[(kAuxX + 0) * 128] = px;
-          aux[(kAuxX + 1) * 128] = py;
-          aux[(kAuxX + 2) * 128] = pz;
-          aux[(kAuxZB + 0) * 128] = zb0;
-          aux[(kAuxZB + 1) * 128] = zb1;
-          aux[(kAuxZB + 2) * 128] = zb2;
-          aux[kAuxSB * 128] = sdf_bar;
-        }
+        if (h == 0) aux[kAuxSB * 128] = sdf_bar;
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
 
@@ -360,8 +391,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               tv[e] = accv * (flf[(j >> 1) * 4 + (j & 1)] * gscale) * __cosf(ar[e]);  // g_l gamma cos = t_{l-1}
             }
             OI_CTA(kCtaG + l - 1, quad) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-            OI_GS(kSlabT + l - 1, quad) = make_float4(tv[0], tv[1], tv[2], tv[3]);
             if (l > 1) {
+              OI_GS(kSlabT + l - 1, quad) = make_float4(tv[0], tv[1], tv[2], tv[3]);
               tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
               tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
             } else {
@@ -404,6 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t hi[8], lo[8];
+          float dgs[16], sns[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
@@ -420,26 +452,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               const float gp = flf[(j >> 1) * 4 + (j & 1)];
               ar[e] = fmaf(gp, pre, flf[(j >> 1) * 4 + 2 + (j & 1)]);
               const float cs = __cosf(ar[e]);
+              sns[q * 4 + e] = __sinf(ar[e]);
               const float4 rw = sm.rgbw[n0 + j];
               const float hb = fmaf(rw.x, zb0, fmaf(rw.y, zb1, rw.z * zb2));
               const float ab = hb * cs;
               const float2 bg = __ldg(fb + j);                 // (beta, 1/gamma)
               dg[e] = ab * (ar[e] - bg.x) * bg.y;              // a_bar * u_c
+              dgs[q * 4 + e] = dg[e];
               ub_[e] = ab * (gp * kWScale);                    // u_bar_c = a_bar * gamma
               nc0 = fmaf(hd.y * kInvWScale, ub_[e], nc0);
               nc1 = fmaf(hd.z * kInvWScale, ub_[e], nc1);
               nc2 = fmaf(hd.w * kInvWScale, ub_[e], nc2);
             }
-            OI_GS(kSlabArgC, quad) = make_float4(ar[0], ar[1], ar[2], ar[3]);
-            OI_GS(kSlabDGC, quad) = make_float4(dg[0], dg[1], dg[2], dg[3]);
             OI_GS(kSlabUBC, quad) = make_float4(ub_[0], ub_[1], ub_[2], ub_[3]);
             split2_bf16(ub_[0], ub_[1], hi[2 * q], lo[2 * q]);
             split2_bf16(ub_[2], ub_[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
           tc::tmem_st8(a_hi + c * 8, hi);
           tc::tmem_st8(a_lo + c * 8, lo);
+          if (c == 3) OI_A_READY();   // the tensor core starts on W_cf^T u_bar_c while the column sums are reduced
+          const int nc = n0 + c * 16;
+          colsum16(dgs, dfilm + (size_t)OI_MAX_DEPTH * 2 * kW + nc, 1, lane);          // d gamma_c
+          {
+            float tmp[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = zb0 * sns[i];
+            colsum16(tmp, a.g.rgb_weight + 0 * kW + nc, 1, lane);                       // dW_rgb = z_bar (x) h_c
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = zb1 * sns[i];
+            colsum16(tmp, a.g.rgb_weight + 1 * kW + nc, 1, lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = zb2 * sns[i];
+            colsum16(tmp, a.g.rgb_weight + 2 * kW + nc, 1, lane);
+          }
         }
-        OI_A_READY();
       }
       // normal_bar = direct + W_cg^T u_bar_c (both halves)
       xch[h * 4 + 1] = nc0;
@@ -456,9 +502,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         aux[(kAuxN + 0) * 128] = gx;
         aux[(kAuxN + 1) * 128] = gy;
         aux[(kAuxN + 2) * 128] = gz;
-        aux[(kAuxNB + 0) * 128] = nb0;
-        aux[(kAuxNB + 1) * 128] = nb1;
-        aux[(kAuxNB + 2) * 128] = nb2;
       }
       // ---------------- h_bar_D = W_cf^T u_bar_c + sdf_bar w_s -> slot HB;
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
@@ -473,6 +516,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
           uint32_t hi[8], lo[8];
+          float t0s[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
@@ -490,6 +534,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               const float c0 = flf[(j >> 1) * 4 + (j & 1)] * __cosf(ar[e]);  // gamma_0 cos a_0
               cb[e] = tb * g1[e];
               gb[e] = tb * c0;
+              t0s[q * 4 + e] = g1[e] * c0;   // t_0
             }
             OI_CTA(kCtaHB, quad) = make_float4(hb[0], hb[1], hb[2], hb[3]);
             OI_CTA(kCtaG + 0, quad) = make_float4(cb[0], cb[1], cb[2], cb[3]);   // c_bar_0
@@ -499,8 +544,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           tc::tmem_st8(a_hi + c * 8, hi);
           tc::tmem_st8(a_lo + c * 8, lo);
+          if (c == 3) OI_A_READY();
+          {  // dW_0 += t_0 (x) normal_bar
+            float* dst = a.g.pts_weight[0] + (size_t)(n0 + c * 16) * 3;
+            float tmp[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = nb0 * t0s[i];
+            colsum16(tmp, dst + 0, 3, lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = nb1 * t0s[i];
+            colsum16(tmp, dst + 1, 3, lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = nb2 * t0s[i];
+            colsum16(tmp, dst + 2, 3, lane);
+          }
         }
-        OI_A_READY();
       }
       // ---------------- backward of the reverse sweep, l = 1..D-1: t_bar_l = W_l g_bar_l ----------------
       for (int l = 1; l < D; ++l) {
@@ -515,6 +573,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
           uint32_t hi[8], lo[8];
+          float dgs[16], dwss[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
@@ -538,22 +597,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               // top: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
               const float4 hb4 = OI_CTA(kCtaHB, quad);
               const float hb[4] = {hb4.x, hb4.y, hb4.z, hb4.w};
-              float dws[4], dg[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = c * 16 + q * 4 + e;
                 const float tb = __uint_as_float(u[q * 4 + e]);
                 const float gam = flf[(j >> 1) * 4 + (j & 1)] * kWScale;
                 const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
-                dws[e] = tb * gam * cs;
+                dwss[q * 4 + e] = fmaf(sdf_bar, sn, tb * gam * cs);   // d w_s = sdf_bar h_D + t_bar_{D-1} c_{D-1}
                 const float cbar = tb * (sm.head[n0 + j].x * kInvWScale);
                 const float ab = hb[e] * cs - cbar * gam * sn;
                 const float2 bg = __ldg(fb + j);
-                dg[e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cbar * cs);
+                dgs[q * 4 + e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cbar * cs);
                 o[e] = ab * gam;   // u_bar_{D-1}
               }
-              OI_GS(kSlabDWS, quad) = make_float4(dws[0], dws[1], dws[2], dws[3]);
-              OI_GS(kSlabDG + l, quad) = make_float4(dg[0], dg[1], dg[2], dg[3]);
               OI_GS(kSlabUB + l, quad) = make_float4(o[0], o[1], o[2], o[3]);
             }
             split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
@@ -561,8 +617,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           tc::tmem_st8(a_hi + c * 8, hi);
           tc::tmem_st8(a_lo + c * 8, lo);
+          if (c == 3) OI_A_READY();
+          if (l == D - 1) {
+            colsum16(dwss, a.g.sigma_weight + n0 + c * 16, 1, lane);
+            colsum16(dgs, dfilm + (size_t)l * 2 * kW + n0 + c * 16, 1, lane);   // d gamma_{D-1}
+          }
         }
-        OI_A_READY();
       }
       // ---------------- backward of the forward sweep: h_bar_l = W_l^T u_bar_l, then layer k = l-1 ----------------
       for (int l = D - 1; l >= 1; --l) {
@@ -579,6 +639,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
           uint32_t hi[8], lo[8];
+          float dgs[16], ubs[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
@@ -586,7 +647,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
             const float4 cb4 = OI_CTA(kCtaG + k, quad);   // c_bar_k
             const float cb[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
-            float o[4], dg[4];
+            float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = c * 16 + q * 4 + e;
@@ -594,12 +655,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
               const float ab = __uint_as_float(u[q * 4 + e]) * cs - cb[e] * gam * sn;
               const float2 bg = __ldg(fb + j);
-              dg[e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cb[e] * cs);
+              dgs[q * 4 + e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cb[e] * cs);
               o[e] = ab * gam;   // u_bar_k
+              ubs[q * 4 + e] = o[e];
             }
-            OI_GS(kSlabDG + k, quad) = make_float4(dg[0], dg[1], dg[2], dg[3]);
-            OI_GS(kSlabUB + k, quad) = make_float4(o[0], o[1], o[2], o[3]);
             if (k >= 1) {
+              OI_GS(kSlabUB + k, quad) = make_float4(o[0], o[1], o[2], o[3]);
               split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
               split2_bf16(o[2], o[3], hi[2 * q + 1], lo[2 * q + 1]);
             }
@@ -607,9 +668,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           if (k >= 1) {
             tc::tmem_st8(a_hi + c * 8, hi);
             tc::tmem_st8(a_lo + c * 8, lo);
+            if (c == 3) OI_A_READY();
+          }
+          const int nc = n0 + c * 16;
+          colsum16(dgs, dfilm + (size_t)k * 2 * kW + nc, 1, lane);   // d gamma_k
+          if (k == 0) {
+            colsum16(ubs, dfilm + kW + nc, 1, lane);                  // d b_0 = sum u_bar_0
+            float* dst = a.g.pts_weight[0] + (size_t)nc * 3;          // dW_0 += u_bar_0 (x) x
+            float tmp[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = px * ubs[i];
+            colsum16(tmp, dst + 0, 3, lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = py * ubs[i];
+            colsum16(tmp, dst + 1, 3, lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = pz * ubs[i];
+            colsum16(tmp, dst + 2, 3, lane);
           }
         }
-        if (k >= 1) OI_A_READY();
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);   // film table / exchange buffer of this slot may be reused now
     }
@@ -711,6 +788,8 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     a.aux = aux;
     a.tile_begin = t0;
     a.tile_end = t1;
+    a.g = d.grads;
+    a.d_film = d_film;
     const int ctas = render_bwd_tc_ctas(t1 - t0) < n_ctas ? render_bwd_tc_ctas(t1 - t0) : n_ctas;
     bwd_tc_kernel<<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
     OI_CHECK_CUDA(cudaGetLastError());
@@ -725,7 +804,6 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     w.aux = aux;
     w.tile0 = t0;
     float* dfilm0 = d_film;
-    auto dgam = [&](int slot) { return dfilm0 + (size_t)slot * 2 * kW; };
     auto dbia = [&](int slot) { return dfilm0 + (size_t)slot * 2 * kW + kW; };
     const int inst_stride = kFilm * 2 * kW;
     auto col = [](int src, int slab, int tf, int mult, float* out, int inst_stride_, int ch_stride) {
@@ -740,52 +818,26 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
       g.n_pairs = 2;
       g.pairs[0] = WgPair{kSlabUB + l, kSlabArg + l - 1, WG_TF_RAW, WG_TF_SIN};   // u_bar_l (x) h_l
       g.pairs[1] = WgPair{kSlabT + l, kSlabGB + l, WG_TF_RAW, WG_TF_RAW};         // t_l (x) g_bar_l
-      g.n_cols = 2;
-      g.cols[0] = col(WG_SRC_PAIR_X, 0, 0, -1, dbia(l), inst_stride, 1);
-      g.cols[1] = col(WG_SRC_SLAB, kSlabDG + l, WG_TF_RAW, -1, dgam(l), inst_stride, 1);
+      g.n_cols = 1;
+      g.cols[0] = col(WG_SRC_PAIR_X, 0, 0, -1, dbia(l), inst_stride, 1);          // d b_l = sum u_bar_l
       g.out = d.grads.pts_weight[l];
       g.out_ld = kW;
+      g.weight = 4;
     }
     {  // colour layer: u_bar_c (x) h_D
       WgGroup& g = w.groups[ng++];
       g.n_pairs = 1;
       g.pairs[0] = WgPair{kSlabUBC, kSlabArg + D - 1, WG_TF_RAW, WG_TF_SIN};
-      g.n_cols = 5;
+      g.n_cols = 4;
       g.cols[0] = col(WG_SRC_PAIR_X, 0, 0, -1, dbia(OI_MAX_DEPTH), inst_stride, 1);
       for (int j = 0; j < 3; ++j)
         g.cols[1 + j] = col(WG_SRC_PAIR_X, 0, 0, kAuxN + j, d.grads.views_weight + kW + j, 0, kW + 3);
-      g.cols[4] = col(WG_SRC_PAIR_Y, 0, 0, kAuxSB, d.grads.sigma_weight, 0, 1);   // d w_s += sdf_bar h_D
       g.out = d.grads.views_weight;
       g.out_ld = kW + 3;
-    }
-    {  // heads
-      WgGroup& g = w.groups[ng++];
-      g.n_pairs = 0;
-      g.n_cols = 5;
-      g.cols[0] = col(WG_SRC_SLAB, kSlabDGC, WG_TF_RAW, -1, dgam(OI_MAX_DEPTH), inst_stride, 1);
-      for (int j = 0; j < 3; ++j)
-        g.cols[1 + j] = col(WG_SRC_SLAB, kSlabArgC, WG_TF_SIN, kAuxZB + j, d.grads.rgb_weight + j * kW, 0, 1);
-      g.cols[4] = col(WG_SRC_SLAB, kSlabDWS, WG_TF_RAW, -1, d.grads.sigma_weight, 0, 1);
-    }
-    {  // layer 0, first part: d b_0, d gamma_0, dW_0 += u_bar_0 (x) x
-      WgGroup& g = w.groups[ng++];
-      g.n_pairs = 0;
-      g.n_cols = 5;
-      g.cols[0] = col(WG_SRC_SLAB, kSlabUB + 0, WG_TF_RAW, -1, dbia(0), inst_stride, 1);
-      g.cols[1] = col(WG_SRC_SLAB, kSlabDG + 0, WG_TF_RAW, -1, dgam(0), inst_stride, 1);
-      for (int j = 0; j < 3; ++j)
-        g.cols[2 + j] = col(WG_SRC_SLAB, kSlabUB + 0, WG_TF_RAW, kAuxX + j, d.grads.pts_weight[0] + j, 0, 3);
-    }
-    {  // layer 0, second part: dW_0 += t_0 (x) normal_bar
-      WgGroup& g = w.groups[ng++];
-      g.n_pairs = 0;
-      g.n_cols = 3;
-      for (int j = 0; j < 3; ++j)
-        g.cols[j] = col(WG_SRC_SLAB, kSlabT + 0, WG_TF_RAW, kAuxNB + j, d.grads.pts_weight[0] + j, 0, 3);
+      g.weight = 2;
     }
     w.n_groups = ng;
-    w.n_splits = sms / ng < 1 ? 1 : sms / ng;
-    if (w.n_splits > w.n_tiles) w.n_splits = w.n_tiles;
+    w.n_ctas = sms;
     int rc = launch_wgrad_tc(w, st);
     if (rc) return rc;
   }

@@ -111,10 +111,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int group = blockIdx.x % a.n_groups, split = blockIdx.x / a.n_groups;
+  int group = 0;
+  while (group + 1 < a.n_groups && (int)blockIdx.x >= a.groups[group + 1].cta0) ++group;
   const WgGroup& G = a.groups[group];
-  const int t_begin = (int)((long long)a.n_tiles * split / a.n_splits);
-  const int t_end = (int)((long long)a.n_tiles * (split + 1) / a.n_splits);
+  const int split = (int)blockIdx.x - G.cta0;
+  const int t_begin = (int)((long long)a.n_tiles * split / G.n_splits);
+  const int t_end = (int)((long long)a.n_tiles * (split + 1) / G.n_splits);
   const int n_pairs = G.n_pairs;                    // MMA operand pairs per 64-point step (0, 1 or 2)
   const int steps_total = (t_end - t_begin) * 2 * n_pairs;
 
@@ -284,12 +286,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
 
 }  // namespace
 
-int launch_wgrad_tc(const WgArgs& a, cudaStream_t st) {
-  if (a.n_groups < 1 || a.n_groups > WG_MAX_GROUPS || a.n_splits < 1)
-    return set_error(OI_ERR_INVALID_ARGUMENT, "wgrad: bad grouping (%d groups, %d splits)", a.n_groups, a.n_splits);
+int launch_wgrad_tc(const WgArgs& a_in, cudaStream_t st) {
+  WgArgs a = a_in;
+  if (a.n_groups < 1 || a.n_groups > WG_MAX_GROUPS || a.n_ctas < a.n_groups)
+    return set_error(OI_ERR_INVALID_ARGUMENT, "wgrad: bad grouping (%d groups, %d CTAs)", a.n_groups, a.n_ctas);
+  // share the CTAs out in proportion to the groups' work per tile; never more splits than tiles
+  int wsum = 0;
+  for (int g = 0; g < a.n_groups; ++g) wsum += a.groups[g].weight > 0 ? a.groups[g].weight : 1;
+  int cta = 0;
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int wg = a.groups[g].weight > 0 ? a.groups[g].weight : 1;
+    int n = a.n_ctas * wg / wsum;
+    if (n < 1) n = 1;
+    if (n > a.n_tiles) n = a.n_tiles;
+    a.groups[g].cta0 = cta;
+    a.groups[g].n_splits = n;
+    cta += n;
+  }
   OI_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(WgSmem)));
-  wgrad_tc_kernel<<<a.n_groups * a.n_splits, kWgThreads, sizeof(WgSmem), st>>>(a);
+  wgrad_tc_kernel<<<cta, kWgThreads, sizeof(WgSmem), st>>>(a);
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

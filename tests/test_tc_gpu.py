@@ -84,5 +84,6 @@ def test_wgrad_point_contraction(n_tiles, n_splits, x_tf, y_tf, mult):
     mm = aux[:, mult].double().reshape(-1, 1) if mult >= 0 else 1.0
     ref_col = (X * mm).sum(0)
     bound = (X.abs().T @ Y.abs())
-    assert float(((d.double() - ref).abs() / (bound + 1e-30)).max()) < 3e-5
-    assert float(((col.double() - ref_col).abs() / ((X * mm).abs().sum(0) + 1e-30)).max()) < 1e-5
+    # MUFU sin on |a| ~ 100 rad carries ~1e-5 absolute error (same as the forward core)
+    assert float(((d.double() - ref).abs() / (bound + 1e-30)).max()) < (1e-4 if (x_tf or y_tf) else 3e-5)
+    assert float(((col.double() - ref_col).abs() / ((X * mm).abs().sum(0) + 1e-30)).max()) < (1e-4 if x_tf else 1e-5)
