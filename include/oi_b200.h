@@ -353,13 +353,14 @@ int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, i
                    float* d, void* stream);
 
 /* Self-test of the point-contraction kernel of the tensor-core backward (csrc/oi_wgrad_tc.cu):
- *   d[i][j] += sum_m tf_x(X)[m][i] * tf_y(Y)[m][j],   col[i] += sum_m tf_x(X)[m][i] * aux[row col_mult][m]
- * over n_tiles tiles of 128 points.  slabs: [n_tiles][slabs_per_tile][32 channel-quads][128 points][4] fp32,
- * aux: [n_tiles][16][128] fp32; tf: 0 identity, 1 sin; col_mult < 0: no multiplier.  d [128,128] and col [128]
- * are accumulated into (zero them first).  The work is split over n_splits CTAs. */
+ *   d[i][j] += sum_m X[m][i] * Y[m][j]                      (TF32 tensor-core products, fp32 accumulation)
+ *   col[inst][i][c] += sum_{m in instance} X[m][i] * aux[m][c],  c < 4
+ * over n_tiles tiles of 128 points.  slabs: [n_tiles][slabs_per_tile][4 blocks][128 channels][32 points] fp32 with
+ * the 16-byte chunks of every 128-byte row XOR-permuted by (channel & 7) (values should be TF32-representable);
+ * aux: [n_tiles][4 blocks][4 columns][32 points] fp32, same permutation.  d [128,128] and
+ * col [n_instances,128,4] are accumulated into (zero them first).  The work is split over n_ctas CTAs. */
 int oi_selftest_wgrad(const float* slabs, const float* aux, int32_t n_tiles, int32_t slabs_per_tile, int32_t x_slab,
-                      int32_t y_slab, int32_t x_tf, int32_t y_tf, int32_t col_mult, int32_t n_splits, float* d,
-                      float* col, void* stream);
+                      int32_t y_slab, int32_t tiles_per_instance, int32_t n_ctas, float* d, float* col, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ */
 const char* oi_last_error(void);

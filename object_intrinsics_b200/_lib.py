@@ -158,7 +158,7 @@ def lib():
     L.oi_render_launch_count.argtypes = [C.POINTER(OiRenderDesc), C.POINTER(C.c_int32)]
     L.oi_render_backward_workspace_bytes.argtypes = [C.POINTER(OiRenderBwdDesc), C.POINTER(C.c_size_t)]
     L.oi_render_backward.argtypes = [C.POINTER(OiRenderBwdDesc), C.c_void_p]
-    L.oi_selftest_wgrad.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.oi_selftest_wgrad.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]
     L.oi_bias_act.argtypes = [C.POINTER(OiBiasActDesc), C.c_void_p]
     L.oi_fused_bias_act.argtypes = [C.POINTER(OiFusedBiasActDesc), C.c_void_p]

@@ -311,7 +311,7 @@ void plan_bwd(const OiRenderBwdDesc* d, BwdWorkspace* w) {
   if (w->tc) {
     w->scratch = take((size_t)w->n_ctas * render_bwd_tc_scratch_floats() * 4);
     w->slabs = take((size_t)w->chunk_tiles * kSlabsPerTile * kSlabFloats * 4);
-    w->aux = take((size_t)w->chunk_tiles * 16 * 128 * 4);
+    w->aux = take((size_t)w->chunk_tiles * 512 * 4);
   } else {
     w->scratch = take((size_t)w->n_ctas * render_bwd_scratch_floats() * 4);
     w->slabs = w->aux = 0;
@@ -394,30 +394,28 @@ int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, i
 }
 
 int oi_selftest_wgrad(const float* slabs, const float* aux, int32_t n_tiles, int32_t slabs_per_tile, int32_t x_slab,
-                      int32_t y_slab, int32_t x_tf, int32_t y_tf, int32_t col_mult, int32_t n_splits, float* d,
-                      float* col, void* stream) {
+                      int32_t y_slab, int32_t tiles_per_instance, int32_t n_ctas, float* d, float* col, void* stream) {
   OI_CHECK_ARG(slabs && aux && d && col, "NULL pointer");
-  OI_CHECK_ARG(n_tiles > 0 && slabs_per_tile > 0 && n_splits > 0, "bad sizes");
+  OI_CHECK_ARG(n_tiles > 0 && slabs_per_tile > 0 && n_ctas > 0 && tiles_per_instance > 0, "bad sizes");
   OI_CHECK_ARG(x_slab >= 0 && x_slab < slabs_per_tile && y_slab >= 0 && y_slab < slabs_per_tile, "bad slab index");
-  OI_CHECK_ARG(col_mult < 16, "col_mult must be an aux row (< 16) or negative");
   WgArgs a;
   memset(&a, 0, sizeof(a));
   a.n_tiles = n_tiles;
-  a.tiles_per_inst = n_tiles;
+  a.tiles_per_inst = tiles_per_instance;
   a.n_groups = 1;
-  a.n_ctas = n_splits;
+  a.n_ctas = n_ctas;
   a.slabs_per_tile = slabs_per_tile;
   a.slabs = slabs;
   a.aux = aux;
   WgGroup& g = a.groups[0];
   g.n_pairs = 1;
-  g.pairs[0] = WgPair{x_slab, y_slab, x_tf, y_tf};
-  g.n_cols = 1;
-  g.cols[0].src = WG_SRC_PAIR_X;
-  g.cols[0].mult = col_mult;
-  g.cols[0].out = col;
-  g.cols[0].inst_stride = 0;
-  g.cols[0].ch_stride = 1;
+  g.pairs[0] = WgPair{x_slab, y_slab};
+  g.use_aux = 1;
+  for (int c = 0; c < 4; ++c) {
+    g.aux_out[c] = col + c;
+    g.aux_inst_stride[c] = 128 * 4;
+    g.aux_ch_stride[c] = 4;
+  }
   g.out = d;
   g.out_ld = 128;
   g.weight = 1;

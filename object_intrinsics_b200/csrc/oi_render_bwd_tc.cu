@@ -90,6 +90,16 @@ __device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, ui
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// round-to-nearest TF32 (the contraction kernel feeds these values to kind::tf32 MMAs, which ignore the low bits)
+__device__ __forceinline__ float tf32r(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32r4(float a, float b, float c, float d) {
+  return make_float4(tf32r(a), tf32r(b), tf32r(c), tf32r(d));
+}
+
 // Sum over the 32 lanes of a warp (= 32 sample points) of 16 per-lane values (= 16 channels), by recursive halving:
 // after the four exchange steps lane L holds channel 8 b4 + 4 b3 + 2 b2 + b1 (bits of L) summed over 16 lanes; one
 // more exchange completes the sum, and the even lanes add it to dst[channel * stride].  16 shuffles per call.
@@ -225,7 +235,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
                                              (size_t)t * kCtaSlabs * kSlabFloats) + m;
     uint32_t af_phase = 0u;
 #define OI_CTA(slab, quad) scr4[((size_t)(slab) * 32 + (quad)) * 128]
-#define OI_GS(slab, quad) gs4[((size_t)(slab) * 32 + (quad)) * 128]
+#define OI_GS(slab, quad) gs4[((size_t)(slab) * 32 + (quad)) * 128]   /* ARG slabs: [quad][128 points] float4 */
+/* operand slabs: K-major SWIZZLE_128B tf32 image [32-point block][channel][32 points], 16-byte chunks XOR (ch & 7) */
+#define OI_OP(slab, j, v) gso[(size_t)(slab) * kSlabFloats + (n0 + (j)) * 32 + ((mc ^ ((j) & 7)) << 2)] = tf32r(v)
+#define OI_OP4(slab, j0, a0, a1, a2, a3) \
+  do {                                   \
+    OI_OP(slab, (j0) + 0, a0);           \
+    OI_OP(slab, (j0) + 1, a1);           \
+    OI_OP(slab, (j0) + 2, a2);           \
+    OI_OP(slab, (j0) + 3, a3);           \
+  } while (0)
 #define OI_A_READY()               \
   do {                             \
     tc::wait_st();                 \
@@ -245,8 +264,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       const int tile = a.tile_begin + lt;
       const int inst = tile / a.r.tiles_per_inst;
       const int tin = tile - inst * a.r.tiles_per_inst;
-      float4* gs4 = reinterpret_cast<float4*>(a.slabs + (size_t)lt * kSlabsPerTile * kSlabFloats) + m;
-      float* aux = a.aux + (size_t)lt * 16 * 128 + m;
+      float* slab_tile = a.slabs + (size_t)lt * kSlabsPerTile * kSlabFloats;
+      float4* gs4 = reinterpret_cast<float4*>(slab_tile) + m;
+      float* gso = slab_tile + (m >> 5) * 4096 + (m & 3);
+      const int mc = (m & 31) >> 2;
+      // aux operand (N = 16, rows 0..3 used): [32-point block][4 rows][32 points], same swizzle
+      float* auxo = a.aux + (size_t)lt * 512 + (m >> 5) * 128 + (m & 3);
       const float2* fb_inst = a.film_b + (size_t)inst * kFilm * kW;
       float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][dgamma | db][128]
       {
@@ -268,7 +291,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         }
         sdf_bar = q0.x; nb0 = q0.y; nb1 = q0.z; nb2 = q0.w;
         zb0 = q1.x; zb1 = q1.y; zb2 = q1.z;
-        if (h == 0) aux[kAuxSB * 128] = sdf_bar;
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
 
@@ -291,6 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               s[e] = __sinf(ar[e]);
             }
             OI_GS(kSlabArg + 0, Q0 + c * 4 + q) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+            OI_OP4(kSlabH + 1, c * 16 + q * 4, s[0], s[1], s[2], s[3]);
             tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
             tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
@@ -321,6 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               s[e] = __sinf(ar[e]);
             }
             OI_GS(kSlabArg + l, Q0 + c * 4 + q) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+            OI_OP4(kSlabH + l + 1, c * 16 + q * 4, s[0], s[1], s[2], s[3]);
             tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
             tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
@@ -354,7 +378,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               const int j = c * 16 + q * 4 + e;
               tv[e] = sm.head[n0 + j].x * flf[(j >> 1) * 4 + (j & 1)] * __cosf(ar[e]);  // 2^8 w_s * gamma/2^8 * cos
             }
-            OI_GS(kSlabT + D - 1, quad) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+            OI_OP4(kSlabT + D - 1, c * 16 + q * 4, tv[0], tv[1], tv[2], tv[3]);
             tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
             tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
@@ -392,7 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             }
             OI_CTA(kCtaG + l - 1, quad) = make_float4(gv[0], gv[1], gv[2], gv[3]);
             if (l > 1) {
-              OI_GS(kSlabT + l - 1, quad) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+              OI_OP4(kSlabT + l - 1, c * 16 + q * 4, tv[0], tv[1], tv[2], tv[3]);
               tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
               tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
             } else {
@@ -464,7 +488,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               nc1 = fmaf(hd.z * kInvWScale, ub_[e], nc1);
               nc2 = fmaf(hd.w * kInvWScale, ub_[e], nc2);
             }
-            OI_GS(kSlabUBC, quad) = make_float4(ub_[0], ub_[1], ub_[2], ub_[3]);
+            OI_OP4(kSlabUBC, c * 16 + q * 4, ub_[0], ub_[1], ub_[2], ub_[3]);
             split2_bf16(ub_[0], ub_[1], hi[2 * q], lo[2 * q]);
             split2_bf16(ub_[2], ub_[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
@@ -499,9 +523,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         nb2 += nc2 + xch[o + 3];
       }
       if (h == 0) {
-        aux[(kAuxN + 0) * 128] = gx;
-        aux[(kAuxN + 1) * 128] = gy;
-        aux[(kAuxN + 2) * 128] = gz;
+        auxo[0 * 32 + ((mc ^ 0) << 2)] = tf32r(gx);
+        auxo[1 * 32 + ((mc ^ 1) << 2)] = tf32r(gy);
+        auxo[2 * 32 + ((mc ^ 2) << 2)] = tf32r(gz);
+        auxo[3 * 32 + ((mc ^ 3) << 2)] = 1.0f;
       }
       // ---------------- h_bar_D = W_cf^T u_bar_c + sdf_bar w_s -> slot HB;
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
@@ -538,7 +563,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             }
             OI_CTA(kCtaHB, quad) = make_float4(hb[0], hb[1], hb[2], hb[3]);
             OI_CTA(kCtaG + 0, quad) = make_float4(cb[0], cb[1], cb[2], cb[3]);   // c_bar_0
-            OI_GS(kSlabGB + 1, quad) = make_float4(gb[0], gb[1], gb[2], gb[3]);
+            OI_OP4(kSlabGB + 1, c * 16 + q * 4, gb[0], gb[1], gb[2], gb[3]);
             split2_bf16(gb[0], gb[1], hi[2 * q], lo[2 * q]);
             split2_bf16(gb[2], gb[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
@@ -592,7 +617,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
                 o[e] = tb * (flf[(j >> 1) * 4 + (j & 1)] * kWScale) * __cosf(ar[e]);    // g_bar_{l+1}
               }
               OI_CTA(kCtaG + l, quad) = make_float4(cb[0], cb[1], cb[2], cb[3]);
-              OI_GS(kSlabGB + l + 1, quad) = make_float4(o[0], o[1], o[2], o[3]);
+              OI_OP4(kSlabGB + l + 1, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
             } else {
               // top: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
               const float4 hb4 = OI_CTA(kCtaHB, quad);
@@ -610,7 +635,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
                 dgs[q * 4 + e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cbar * cs);
                 o[e] = ab * gam;   // u_bar_{D-1}
               }
-              OI_GS(kSlabUB + l, quad) = make_float4(o[0], o[1], o[2], o[3]);
+              OI_OP4(kSlabUB + l, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
             }
             split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
             split2_bf16(o[2], o[3], hi[2 * q + 1], lo[2 * q + 1]);
@@ -660,7 +685,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               ubs[q * 4 + e] = o[e];
             }
             if (k >= 1) {
-              OI_GS(kSlabUB + k, quad) = make_float4(o[0], o[1], o[2], o[3]);
+              OI_OP4(kSlabUB + k, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
               split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
               split2_bf16(o[2], o[3], hi[2 * q + 1], lo[2 * q + 1]);
             }
@@ -692,6 +717,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     }
 #undef OI_CTA
 #undef OI_GS
+#undef OI_OP
+#undef OI_OP4
 #undef OI_A_READY
 #undef OI_WAIT_ACC
   }
@@ -757,7 +784,7 @@ int render_bwd_tc_ctas(int n_tiles) {
   return ctas < 1 ? 1 : ctas;
 }
 size_t render_bwd_tc_scratch_floats() { return (size_t)2 * kCtaSlabs * kSlabFloats; }
-size_t render_bwd_tc_slab_floats_per_tile() { return (size_t)kSlabsPerTile * kSlabFloats + 16 * 128; }
+size_t render_bwd_tc_slab_floats_per_tile() { return (size_t)kSlabsPerTile * kSlabFloats + 512; }
 
 // Runs the two tensor-core kernels over tiles [0, n_tiles) in chunks of at most `chunk_tiles`.
 int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
@@ -806,32 +833,33 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     float* dfilm0 = d_film;
     auto dbia = [&](int slot) { return dfilm0 + (size_t)slot * 2 * kW + kW; };
     const int inst_stride = kFilm * 2 * kW;
-    auto col = [](int src, int slab, int tf, int mult, float* out, int inst_stride_, int ch_stride) {
-      WgCol c;
-      c.src = src; c.slab = slab; c.tf = tf; c.mult = mult; c.out = out; c.inst_stride = inst_stride_;
-      c.ch_stride = ch_stride;
-      return c;
-    };
     int ng = 0;
     for (int l = 1; l < D; ++l) {
       WgGroup& g = w.groups[ng++];
       g.n_pairs = 2;
-      g.pairs[0] = WgPair{kSlabUB + l, kSlabArg + l - 1, WG_TF_RAW, WG_TF_SIN};   // u_bar_l (x) h_l
-      g.pairs[1] = WgPair{kSlabT + l, kSlabGB + l, WG_TF_RAW, WG_TF_RAW};         // t_l (x) g_bar_l
-      g.n_cols = 1;
-      g.cols[0] = col(WG_SRC_PAIR_X, 0, 0, -1, dbia(l), inst_stride, 1);          // d b_l = sum u_bar_l
+      g.pairs[0] = WgPair{kSlabUB + l, kSlabH + l};     // u_bar_l (x) h_l
+      g.pairs[1] = WgPair{kSlabT + l, kSlabGB + l};     // t_l (x) g_bar_l
+      g.use_aux = 1;
+      g.aux_out[3] = dbia(l);                           // d b_l = sum u_bar_l  (aux column 3 = 1)
+      g.aux_inst_stride[3] = inst_stride;
+      g.aux_ch_stride[3] = 1;
       g.out = d.grads.pts_weight[l];
       g.out_ld = kW;
       g.weight = 4;
     }
-    {  // colour layer: u_bar_c (x) h_D
+    {  // colour layer: u_bar_c (x) h_D, u_bar_c (x) normal, sum u_bar_c
       WgGroup& g = w.groups[ng++];
       g.n_pairs = 1;
-      g.pairs[0] = WgPair{kSlabUBC, kSlabArg + D - 1, WG_TF_RAW, WG_TF_SIN};
-      g.n_cols = 4;
-      g.cols[0] = col(WG_SRC_PAIR_X, 0, 0, -1, dbia(OI_MAX_DEPTH), inst_stride, 1);
-      for (int j = 0; j < 3; ++j)
-        g.cols[1 + j] = col(WG_SRC_PAIR_X, 0, 0, kAuxN + j, d.grads.views_weight + kW + j, 0, kW + 3);
+      g.pairs[0] = WgPair{kSlabUBC, kSlabH + D};
+      g.use_aux = 1;
+      for (int j = 0; j < 3; ++j) {
+        g.aux_out[j] = d.grads.views_weight + kW + j;
+        g.aux_inst_stride[j] = 0;
+        g.aux_ch_stride[j] = kW + 3;
+      }
+      g.aux_out[3] = dbia(OI_MAX_DEPTH);
+      g.aux_inst_stride[3] = inst_stride;
+      g.aux_ch_stride[3] = 1;
       g.out = d.grads.views_weight;
       g.out_ld = kW + 3;
       g.weight = 2;

@@ -1,20 +1,17 @@
 // Point-contraction kernel of the tensor-core backward (second kernel of oi_render_backward, OI_IMPL_TCGEN05):
-//     dW[i][j] = sum over sample points m of X[m][i] * Y[m][j]
-// for the 128x128 weight matrices of the SDF / colour networks, and the per-channel sums over points that give
-// the bias, FiLM (gamma, beta), head and layer-0 gradients.  The first kernel (oi_render_bwd_tc.cu) leaves, per
-// 128-point tile, its per-point quantities as fp32 "slabs" [32 channel-quads][128 points] float4 in global
-// scratch; this kernel streams them once:
-//   * 8 loader warps read a 64-point step of an (X, Y) slab pair (coalesced 16-byte loads), apply the operand
-//     transform (identity or sin), split every value into two bf16 terms (x = hi + lo, |err| <= 2^-17 |x|; bf16
-//     because adjoints have no bounded range) and write the four images {X,Y} x {hi,lo} into shared memory in the
-//     canonical MN-major SWIZZLE_128B layout ([point][64 channels] rows of 128 bytes, two channel blocks);
-//   * one thread issues tcgen05.mma.kind::f16 (bf16 inputs, fp32 accumulation in TMEM) with BOTH operands MN-major:
-//     D[i][j] += Xhi^T Yhi + Xlo^T Yhi + Xhi^T Ylo, K = 16 points per instruction; the accumulator stays in TMEM for
-//     the whole point range of the CTA and is flushed once with vector reductions (red.global.add.v4.f32);
-//   * the loader threads own fixed channels, so the per-channel sums are plain register accumulations.
-// Grid: n_groups x n_splits CTAs; group = which matrix / which set of column sums, split = contiguous tile range.
-#include <cuda_bf16.h>
-
+//     dW[i][j] = sum over sample points m of X[m][i] * Y[m][j]          (128 x 128 weight gradients)
+//     dv[i][c] = sum over sample points m of X[m][i] * aux[m][c]        (c < 4: bias / narrow-column gradients)
+// The first kernel (oi_render_bwd_tc.cu) leaves every operand as an fp32 "slab" per 128-point tile whose memory
+// layout IS the canonical K-major SWIZZLE_128B UMMA operand image for kind::tf32 (the contraction index K = points:
+// blocks of 32 points, each [128 channels][32 points] with 128-byte rows whose 16-byte chunks are XOR-permuted by
+// channel & 7): 64 points of an operand are one contiguous 32 KB TMA bulk copy straight into shared memory, consumed
+// by tcgen05.mma.kind::tf32 as it lands -- no register staging, no conversion instructions.  (On this part the
+// MN-major form of kind::tf32 returned zeros in the selftest, hence the point-contiguous layout.)  (The producer
+// rounds the values to TF32 with round-to-nearest when it stores them, so the tensor core's truncation of the low
+// mantissa bits is exact.)  The accumulators stay in TMEM for the whole point range of the CTA and are flushed
+// once per instance segment with vector reductions (red.global.add.v4.f32).
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 accumulator flush.  Grid: CTAs are shared out over the groups
+// (one group = one weight matrix) in proportion to their work per tile; a CTA owns a contiguous tile range.
 #include "oi_internal.cuh"
 #include "oi_tc.cuh"
 #include "oi_wgrad.cuh"
@@ -23,89 +20,35 @@ namespace oi {
 
 namespace {
 
-constexpr int kWgThreads = 288;        // 8 loader/epilogue warps + 1 MMA warp
-constexpr int kLoaders = 256;
-constexpr int kStepPts = 64;           // points per pipeline stage
-constexpr int kImgBytes = 16384;       // one operand image: [2 channel blocks][64 points][128 B]
-constexpr int kStageBytes = 4 * kImgBytes;  // Xhi, Xlo, Yhi, Ylo
+constexpr int kWgThreads = 192;
+constexpr int kHalfBytes = 32768;            // one operand, 64 points: 2 blocks of [128 channels][32 points] fp32
+constexpr int kAuxBytes = 4096;              // N = 16 operand: 2 blocks of [16 rows][32 points]; rows 0..3 = aux
 constexpr int kWgStages = 3;
-// instruction descriptor: D fp32, A = B = bf16, both MN-major, M = N = 128
-constexpr uint32_t kIdescWg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) |
-                              ((128u >> 4) << 24);
+// instruction descriptors: D fp32, A = B = tf32, both K-major; M = 128, N = 128 / 16
+__host__ __device__ constexpr uint32_t idesc_tf32(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 struct __align__(1024) WgSmem {
-  unsigned char img[kWgStages][kStageBytes];
-  unsigned long long full[kWgStages], empty[kWgStages], acc_done;
+  unsigned char x[kWgStages][kHalfBytes];
+  unsigned char y[kWgStages][kHalfBytes];
+  unsigned char aux[kWgStages][kAuxBytes];
+  unsigned long long full[kWgStages], empty[kWgStages], acc_done, acc_free;
   uint32_t tmem_base;
 };
 static_assert(sizeof(WgSmem) <= 227 * 1024, "WgSmem exceeds the per-CTA limit");
 
-// MN-major SWIZZLE_128B operand: 64 channels (128 B) contiguous per point row, 8-row groups 1024 B apart
-// (stride byte offset), the second 64-channel block 8192 B further (leading byte offset).
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)(8192 >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+__device__ __forceinline__ void mma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
-
-__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
-// Writes the 4 channels of quad q at point row r (0..63 inside the stage) into a hi and a lo image.
-__device__ __forceinline__ void store_quad(unsigned char* img_hi, unsigned char* img_lo, int q, int r, float4 v) {
-  uint32_t h0, l0, h1, l1;
-  split_bf16x2(v.x, v.y, h0, l0);
-  split_bf16x2(v.z, v.w, h1, l1);
-  const int block = q >> 4, chunk = ((q & 15) >> 1) ^ (r & 7);
-  const int off = block * 8192 + r * 128 + chunk * 16 + (q & 1) * 8;
-  *reinterpret_cast<uint2*>(img_hi + off) = make_uint2(h0, h1);
-  *reinterpret_cast<uint2*>(img_lo + off) = make_uint2(l0, l1);
-}
-
-__device__ __forceinline__ float4 tf_apply(float4 v, int tf) {
-  if (tf == WG_TF_SIN) return make_float4(__sinf(v.x), __sinf(v.y), __sinf(v.z), __sinf(v.w));
-  return v;
-}
-
-struct ColAcc {
-  float v[4][4];  // [local quad][channel in quad]
-  __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) v[a][b] = 0.f;
-  }
-  __device__ __forceinline__ void add(int lq, float4 x, float m) {
-    v[lq][0] = fmaf(x.x, m, v[lq][0]);
-    v[lq][1] = fmaf(x.y, m, v[lq][1]);
-    v[lq][2] = fmaf(x.z, m, v[lq][2]);
-    v[lq][3] = fmaf(x.w, m, v[lq][3]);
-  }
-  // sum over the 32 lanes (points) and add to dst[channel * stride]; this warp owns channels 16*warp..16*warp+15
-  __device__ __forceinline__ void flush(float* dst, int stride, int warp, int lane) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        float s = v[a][b];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0 && dst != nullptr) atomicAdd(dst + (size_t)(16 * warp + 4 * a + b) * stride, s);
-        v[a][b] = 0.f;
-      }
-  }
-};
-
-constexpr int kMaxCol = 5;  // column-sum accumulators per thread (80 registers)
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -117,19 +60,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
   const int split = (int)blockIdx.x - G.cta0;
   const int t_begin = (int)((long long)a.n_tiles * split / G.n_splits);
   const int t_end = (int)((long long)a.n_tiles * (split + 1) / G.n_splits);
-  const int n_pairs = G.n_pairs;                    // MMA operand pairs per 64-point step (0, 1 or 2)
-  const int steps_total = (t_end - t_begin) * 2 * n_pairs;
+  const int n_pairs = G.n_pairs;
+  const bool use_aux = G.use_aux != 0;
 
   if (tid == 0) {
     for (int s = 0; s < kWgStages; ++s) {
-      mbar_init(&sm.full[s], kLoaders);
+      mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
     mbar_init(&sm.acc_done, 1);
+    mbar_init(&sm.acc_free, 128);
     mbar_fence_init();
   }
-  if (warp == 8) {
-    tc::tmem_alloc(&sm.tmem_base, 128);
+  for (int i = tid; i < kWgStages * kAuxBytes / 16; i += kWgThreads)
+    reinterpret_cast<float4*>(&sm.aux[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) {
+    tc::tmem_alloc(&sm.tmem_base, 256);
     tc::tmem_relinquish();
   }
   tc::fence_before_thread_sync();
@@ -137,133 +84,89 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_base;
 
-  if (warp == 8) {
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const unsigned char* slabs = reinterpret_cast<const unsigned char*>(a.slabs) +
+                                     (size_t)tile * a.slabs_per_tile * (2 * kHalfBytes);
+        const unsigned char* aux = reinterpret_cast<const unsigned char*>(a.aux) + (size_t)tile * 2048;   // 4 x 512 B
+        for (int half = 0; half < 2; ++half) {
+          for (int p = 0; p < n_pairs; ++p, ++it) {
+            const int stage = it % kWgStages;
+            if (it >= kWgStages) mbar_wait_sleep(&sm.empty[stage], ((it / kWgStages) - 1) & 1, 1000u);
+            const bool with_aux = (p == 0) && use_aux;
+            mbar_expect_tx(&sm.full[stage], 2 * kHalfBytes + (with_aux ? 1024 : 0));
+            tma_bulk_g2s(sm.x[stage], slabs + ((size_t)G.pairs[p].x_slab * 2 + half) * kHalfBytes, kHalfBytes,
+                         &sm.full[stage]);
+            tma_bulk_g2s(sm.y[stage], slabs + ((size_t)G.pairs[p].y_slab * 2 + half) * kHalfBytes, kHalfBytes,
+                         &sm.full[stage]);
+            if (with_aux) {   // rows 0..3 of each 32-point block; rows 4..15 stay zero
+              tma_bulk_g2s(sm.aux[stage], aux + (half * 2) * 512, 512, &sm.full[stage]);
+              tma_bulk_g2s(sm.aux[stage] + 2048, aux + (half * 2 + 1) * 512, 512, &sm.full[stage]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      for (int it = 0; it < steps_total; ++it) {
-        const int stage = it % kWgStages;
-        mbar_wait_sleep(&sm.full[stage], (it / kWgStages) & 1, 2000u);
-        tc::fence_after_thread_sync();
-        const uint32_t base = smem_u32(sm.img[stage]);
-#pragma unroll
-        for (int k = 0; k < kStepPts / 16; ++k) {
-          const uint32_t ko = (uint32_t)k * 16u * 128u;  // 16 point rows
-          const uint64_t xhi = make_desc_mn_sw128(base + 0 * kImgBytes + ko);
-          const uint64_t xlo = make_desc_mn_sw128(base + 1 * kImgBytes + ko);
-          const uint64_t yhi = make_desc_mn_sw128(base + 2 * kImgBytes + ko);
-          const uint64_t ylo = make_desc_mn_sw128(base + 3 * kImgBytes + ko);
-          tc::mma_ss(tmem_base, xhi, yhi, kIdescWg, (it > 0 || k > 0) ? 1u : 0u);
-          tc::mma_ss(tmem_base, xlo, yhi, kIdescWg, 1u);
-          tc::mma_ss(tmem_base, xhi, ylo, kIdescWg, 1u);
+      int it = 0, seg = 0;
+      int cur_inst = (t_begin < t_end) ? (a.tile0 + t_begin) / a.tiles_per_inst : 0;
+      bool fresh = true;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int inst = (a.tile0 + tile) / a.tiles_per_inst;
+        if (inst != cur_inst) {
+          // instance boundary: hand the accumulators to the flush warps, wait until they have been read
+          tc::mma_commit(&sm.acc_done);
+          mbar_wait_sleep(&sm.acc_free, seg & 1, 1000u);
+          tc::fence_after_thread_sync();
+          ++seg;
+          cur_inst = inst;
+          fresh = true;
         }
-        tc::mma_commit(&sm.empty[stage]);
-      }
-      tc::mma_commit(&sm.acc_done);
-    }
-  } else {
-    // ===================== loaders (and, at the end, the accumulator flush) =====================
-    ColAcc col[kMaxCol];
+        for (int half = 0; half < 2; ++half) {
+          for (int p = 0; p < n_pairs; ++p, ++it) {
+            const int stage = it % kWgStages;
+            mbar_wait_sleep(&sm.full[stage], (it / kWgStages) & 1, 1000u);
+            tc::fence_after_thread_sync();
+            const uint32_t xb = smem_u32(sm.x[stage]), yb = smem_u32(sm.y[stage]), ab = smem_u32(sm.aux[stage]);
+            const bool with_aux = (p == 0) && use_aux;
 #pragma unroll
-    for (int c = 0; c < kMaxCol; ++c) col[c].zero();
-    int it = 0;
-    int cur_inst = (t_begin < t_end) ? (a.tile0 + t_begin) / a.tiles_per_inst : 0;
-
-    auto flush_cols = [&](int inst) {
-#pragma unroll
-      for (int c = 0; c < kMaxCol; ++c) {
-        if (c < G.n_cols) {
-          const WgCol& C = G.cols[c];
-          col[c].flush(C.out + (size_t)inst * C.inst_stride, C.ch_stride, warp, lane);
-        }
-      }
-    };
-
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      const int inst = (a.tile0 + tile) / a.tiles_per_inst;
-      if (inst != cur_inst) {
-        flush_cols(cur_inst);
-        cur_inst = inst;
-      }
-      const float4* slabs = reinterpret_cast<const float4*>(a.slabs) + (size_t)tile * a.slabs_per_tile * 4096;
-      const float* aux = a.aux + (size_t)tile * 16 * 128;
-      for (int half = 0; half < 2; ++half) {
-        const int m0 = half * 64 + lane, m1 = m0 + 32;
-        // ---- MMA operand pairs (with the column sums that ride on the X / Y operand)
-        for (int p = 0; p < n_pairs; ++p, ++it) {
-          const WgPair& P = G.pairs[p];
-          const int stage = it % kWgStages;
-          if (it >= kWgStages) mbar_wait_sleep(&sm.empty[stage], ((it / kWgStages) - 1) & 1, 2000u);
-          unsigned char* base = sm.img[stage];
-          const float4* xs = slabs + (size_t)P.x_slab * 4096;
-          const float4* ys = slabs + (size_t)P.y_slab * 4096;
-          float4 xv[8], yv[8];
-#pragma unroll
-          for (int lq = 0; lq < 4; ++lq) {
-            const int q = warp * 4 + lq;
-            xv[2 * lq] = xs[q * 128 + m0];
-            xv[2 * lq + 1] = xs[q * 128 + m1];
-            yv[2 * lq] = ys[q * 128 + m0];
-            yv[2 * lq + 1] = ys[q * 128 + m1];
-          }
-#pragma unroll
-          for (int lq = 0; lq < 4; ++lq) {
-            const int q = warp * 4 + lq;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int r = lane + 32 * e;
-              const float4 x = tf_apply(xv[2 * lq + e], P.x_tf), y = tf_apply(yv[2 * lq + e], P.y_tf);
-              store_quad(base + 0 * kImgBytes, base + 1 * kImgBytes, q, r, x);
-              store_quad(base + 2 * kImgBytes, base + 3 * kImgBytes, q, r, y);
-#pragma unroll
-              for (int c = 0; c < kMaxCol; ++c) {
-                if (c < G.n_cols) {
-                  const WgCol& C = G.cols[c];
-                  if (C.src == WG_SRC_PAIR_X + 2 * p || C.src == WG_SRC_PAIR_Y + 2 * p) {
-                    const float mult = (C.mult < 0) ? 1.0f : aux[C.mult * 128 + half * 64 + r];
-                    col[c].add(lq, (C.src == WG_SRC_PAIR_X + 2 * p) ? x : y, mult);
-                  }
-                }
-              }
+            for (int k = 0; k < 8; ++k) {   // 8 points per instruction: block k / 4, 32-byte step k % 4 in the row
+              const uint32_t xo = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
+              const uint64_t xd = tc::make_desc_k_sw128(xb + xo);
+              mma_ss_tf32(tmem_base, xd, tc::make_desc_k_sw128(yb + xo), idesc_tf32(128),
+                          (fresh && k == 0) ? 0u : 1u);
+              if (with_aux)
+                mma_ss_tf32(tmem_base + 128, xd,
+                            tc::make_desc_k_sw128(ab + (uint32_t)(k >> 2) * 2048u + (uint32_t)(k & 3) * 32u),
+                            idesc_tf32(16), (fresh && k == 0) ? 0u : 1u);
             }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> UMMA (async proxy) reads
-          mbar_arrive(&sm.full[stage]);
-        }
-        // ---- stand-alone column sums
-#pragma unroll
-        for (int c = 0; c < kMaxCol; ++c) {
-          if (c < G.n_cols) {
-            const WgCol& C = G.cols[c];
-            if (C.src == WG_SRC_SLAB) {
-              const float4* ss = slabs + (size_t)C.slab * 4096;
-#pragma unroll
-              for (int lq = 0; lq < 4; ++lq) {
-                const int q = warp * 4 + lq;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int r = lane + 32 * e;
-                  const float4 x = tf_apply(ss[q * 128 + half * 64 + r], C.tf);
-                  const float mult = (C.mult < 0) ? 1.0f : aux[C.mult * 128 + half * 64 + r];
-                  col[c].add(lq, x, mult);
-                }
-              }
-            }
+            fresh = false;
+            tc::mma_commit(&sm.empty[stage]);
           }
         }
       }
+      if (t_begin < t_end) tc::mma_commit(&sm.acc_done);
     }
-    if (t_begin < t_end) flush_cols(cur_inst);
-
-    // ---- flush the TMEM accumulator: warp w reads lanes 32 (w % 4) .. +31, columns 64 (w / 4) .. +63
-    if (n_pairs > 0 && steps_total > 0) {
-      mbar_wait_sleep(&sm.acc_done, 0u, 2000u);
+  } else if (t_begin < t_end && n_pairs > 0) {
+    // ===================== accumulator flush: warp w reads TMEM lanes 32 (w % 4) .. +31 =====================
+    const int lq = warp & 3;
+    const int i = lq * 32 + lane;   // row of the accumulator = channel of X
+    const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16);
+    int seg = 0;
+    int cur_inst = (a.tile0 + t_begin) / a.tiles_per_inst;
+    for (int tile = t_begin; tile <= t_end; ++tile) {
+      const int inst = (tile < t_end) ? (a.tile0 + tile) / a.tiles_per_inst : -1;
+      if (inst == cur_inst) continue;
+      mbar_wait_sleep(&sm.acc_done, seg & 1, 1000u);
       tc::fence_after_thread_sync();
-      const int i = (warp & 3) * 32 + lane;
-      const int j0 = (warp >> 2) * 64;
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + j0;
-      float* row = G.out + (size_t)i * G.out_ld + j0;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      float* row = G.out + (size_t)i * G.out_ld;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
         float u[32];
         tc::tmem_ld32(taddr + c * 32, u);
         if ((G.out_ld & 3) == 0) {
@@ -277,11 +180,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
           for (int j = 0; j < 32; ++j) atomicAdd(row + c * 32 + j, u[j]);
         }
       }
+      if (use_aux) {
+        uint32_t r[16];
+        tc::tmem_ld16_async(taddr + 128, r);
+        tc::wait_ld();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float* dst = G.aux_out[c];
+          if (dst != nullptr)
+            atomicAdd(dst + (size_t)cur_inst * G.aux_inst_stride[c] + (size_t)i * G.aux_ch_stride[c],
+                      __uint_as_float(r[c]));
+        }
+      }
+      tc::fence_before_thread_sync();
+      mbar_arrive(&sm.acc_free);
+      ++seg;
+      cur_inst = inst;
     }
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem_base, 128);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace

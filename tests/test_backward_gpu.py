@@ -113,7 +113,7 @@ def test_adjoint_scale_invariance_tcgen05():
         grads.append(torch.autograd.grad(loss, [t for _, t in named]))
     for (k, _), g1, g2 in zip(named, *grads):
         s = float(g1.abs().max()) + 1e-30
-        assert float((g2 * 1e6 - g1).abs().max()) / s < 2e-4, k
+        assert float((g2 * 1e6 - g1).abs().max()) / s < 2e-3, k   # TF32 operand rounding differs between the two scales
 
 
 @pytest.mark.parametrize("impl", ["ffma", "tcgen05"])

@@ -55,35 +55,45 @@ def test_packed_panels_match_network_weights():
         assert err <= 2e-6 * float(ref.abs().max()), (panel, err)
 
 
-@pytest.mark.parametrize("n_tiles,n_splits,x_tf,y_tf,mult", [(1, 1, 0, 0, -1), (5, 2, 0, 1, 3), (7, 7, 1, 0, -1)])
-def test_wgrad_point_contraction(n_tiles, n_splits, x_tf, y_tf, mult):
-    """MN-major bf16x2-split UMMA contraction over points + column sums (csrc/oi_wgrad_tc.cu) vs fp64 einsum."""
-    import ctypes as C
+@pytest.mark.parametrize("n_tiles,n_ctas,tiles_per_inst", [(1, 1, 1), (5, 2, 5), (12, 3, 4), (7, 7, 7)])
+def test_wgrad_point_contraction(n_tiles, n_ctas, tiles_per_inst):
+    """TMA-fed MN-major TF32 UMMA contraction over points + narrow aux products (csrc/oi_wgrad_tc.cu) vs fp64."""
     from object_intrinsics_b200 import _lib
     L = _lib.lib()
     g = torch.Generator(device="cuda").manual_seed(n_tiles)
     spt = 3
+
+    def tf32(t):   # round-to-nearest-even to 10 mantissa bits (what the producer kernel stores)
+        i = t.view(torch.int32)
+        return ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+
+    def image(t):   # logical [tile, 128 points, rows] -> [tile, 4 blocks, rows, 32 points] with the 128B swizzle
+        nt, _, rows = t.shape
+        b = t.reshape(nt, 4, 32, rows).permute(0, 1, 3, 2).contiguous()          # [tile, block, row, 32 pts]
+        b = b.reshape(nt, 4, rows, 8, 4)                                          # 8 chunks of 4 points
+        r = torch.arange(rows, device=t.device)
+        src = torch.arange(8, device=t.device)[None, :] ^ (r[:, None] & 7)        # chunk c' holds logical chunk c' ^ (r&7)
+        return torch.gather(b, 3, src[None, None, :, :, None].expand(nt, 4, rows, 8, 4)).reshape(nt, 4, rows, 32)
+
     # values spanning many binades: adjoint-like dynamic range
-    slabs = torch.randn(n_tiles, spt, 32, 128, 4, device="cuda", generator=g) * \
-        torch.exp(4.0 * torch.randn(n_tiles, spt, 1, 128, 1, device="cuda", generator=g))
-    if x_tf:      # sin operands are FiLM pre-activations: |a| up to ~100 rad (MUFU sin, as in the forward core)
-        slabs[:, 2] = 30.0 * torch.randn(n_tiles, 32, 128, 4, device="cuda", generator=g)
-    if y_tf:
-        slabs[:, 0] = 30.0 * torch.randn(n_tiles, 32, 128, 4, device="cuda", generator=g)
-    aux = torch.randn(n_tiles, 16, 128, device="cuda", generator=g)
+    logical = tf32(torch.randn(n_tiles, spt, 128, 128, device="cuda", generator=g) *
+                   torch.exp(4.0 * torch.randn(n_tiles, spt, 128, 1, device="cuda", generator=g)))
+    slabs = torch.stack([image(logical[:, i]) for i in range(spt)], 1).contiguous()
+    A32 = tf32(torch.randn(n_tiles, 128, 4, device="cuda", generator=g))
+    aux = image(A32).contiguous()
+    n_inst = (n_tiles + tiles_per_inst - 1) // tiles_per_inst
     d = torch.zeros(128, 128, device="cuda")
-    col = torch.zeros(128, device="cuda")
-    _lib.check(L.oi_selftest_wgrad(slabs.data_ptr(), aux.data_ptr(), n_tiles, spt, 2, 0, x_tf, y_tf, mult, n_splits,
+    col = torch.zeros(n_inst, 128, 4, device="cuda")
+    _lib.check(L.oi_selftest_wgrad(slabs.data_ptr(), aux.data_ptr(), n_tiles, spt, 2, 0, tiles_per_inst, n_ctas,
                                    d.data_ptr(), col.data_ptr(), None), "oi_selftest_wgrad")
     torch.cuda.synchronize()
-    tf = lambda t, k: torch.sin(t) if k else t
-    # [tile, q, m, 4] -> [tile*m, channel]
-    X = tf(slabs[:, 2].double(), x_tf).permute(0, 2, 1, 3).reshape(n_tiles * 128, 128)
-    Y = tf(slabs[:, 0].double(), y_tf).permute(0, 2, 1, 3).reshape(n_tiles * 128, 128)
-    ref = X.T @ Y
-    mm = aux[:, mult].double().reshape(-1, 1) if mult >= 0 else 1.0
-    ref_col = (X * mm).sum(0)
-    bound = (X.abs().T @ Y.abs())
-    # MUFU sin on |a| ~ 100 rad carries ~1e-5 absolute error (same as the forward core)
-    assert float(((d.double() - ref).abs() / (bound + 1e-30)).max()) < (1e-4 if (x_tf or y_tf) else 3e-5)
-    assert float(((col.double() - ref_col).abs() / ((X * mm).abs().sum(0) + 1e-30)).max()) < (1e-4 if x_tf else 1e-5)
+    X, Y, A = logical[:, 2].double(), logical[:, 0].double(), A32.double()
+    ref = torch.einsum("tmi,tmj->ij", X, Y)
+    bound = torch.einsum("tmi,tmj->ij", X.abs(), Y.abs())
+    assert float(((d.double() - ref).abs() / (bound + 1e-30)).max()) < 1e-5   # exact products, fp32 accumulation
+    inst = torch.arange(n_tiles, device="cuda") // tiles_per_inst
+    for b in range(n_inst):
+        sel = inst == b
+        ref_c = torch.einsum("tmi,tmc->ic", X[sel], A[sel])
+        bnd_c = torch.einsum("tmi,tmc->ic", X[sel].abs(), A[sel].abs())
+        assert float(((col[b].double() - ref_c).abs() / (bnd_c + 1e-30)).max()) < 1e-5
