@@ -245,6 +245,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     OI_OP(slab, (j0) + 2, a2);           \
     OI_OP(slab, (j0) + 3, a3);           \
   } while (0)
+/* pull a slab back from DRAM into L2 one epilogue ahead of its use (one lane per 128-byte line) */
+#define OI_PF_GS(slab)                                                        \
+  do {                                                                        \
+    if ((m & 7) == 0) {                                                       \
+      _Pragma("unroll 4") for (int q_ = 0; q_ < 16; ++q_) l2_prefetch(&OI_GS(slab, Q0 + q_)); \
+    }                                                                         \
+  } while (0)
+#define OI_PF_CTA(slab)                                                       \
+  do {                                                                        \
+    if ((m & 7) == 0) {                                                       \
+      _Pragma("unroll 4") for (int q_ = 0; q_ < 16; ++q_) l2_prefetch(&OI_CTA(slab, Q0 + q_)); \
+    }                                                                         \
+  } while (0)
 #define OI_A_READY()               \
   do {                             \
     tc::wait_st();                 \
@@ -392,6 +405,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = D - 1; l >= 1; --l) {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][l - 1]) + n0 * 2;
         const float gscale = (l - 1 == 0) ? kInvWScale : 1.0f;   // gamma'_0 is unscaled
+        if (l >= 2) OI_PF_GS(kSlabArg + l - 2);
+        else OI_PF_CTA(kCtaUC);
+        float4 arn[4];   // one-chunk look-ahead of a_{l-1}, issued before the MMA wait
+#pragma unroll
+        for (int q = 0; q < 4; ++q) arn[q] = OI_GS(kSlabArg + l - 1, Q0 + q);
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -400,11 +418,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
+          float4 arc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) arc[q] = arn[q];
+          if (c < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) arn[q] = OI_GS(kSlabArg + l - 1, Q0 + (c + 1) * 4 + q);
+          }
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = OI_GS(kSlabArg + l - 1, quad);
+            const float4 ar4 = arc[q];
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
             float gv[4], tv[4];
 #pragma unroll
@@ -456,6 +481,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][OI_MAX_DEPTH]) + n0 * 2;
         const float2* fb = fb_inst + OI_MAX_DEPTH * kW + n0;
+        OI_PF_GS(kSlabArg + 0);
+        OI_PF_CTA(kCtaG + 0);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t hi[8], lo[8];
@@ -532,6 +559,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
       {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][0]) + n0 * 2;
+        OI_PF_GS(kSlabArg + 1);
+        if (D > 2) OI_PF_CTA(kCtaG + 1);
+        else OI_PF_CTA(kCtaHB);
+        float4 arn[4], gn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          arn[q] = OI_GS(kSlabArg + 0, Q0 + q);
+          gn[q] = OI_CTA(kCtaG + 0, Q0 + q);
+        }
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -540,15 +576,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
+          float4 arc[4], gc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            arc[q] = arn[q];
+            gc[q] = gn[q];
+          }
+          if (c < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              arn[q] = OI_GS(kSlabArg + 0, Q0 + (c + 1) * 4 + q);
+              gn[q] = OI_CTA(kCtaG + 0, Q0 + (c + 1) * 4 + q);
+            }
+          }
           uint32_t hi[8], lo[8];
           float t0s[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
             float hb[4], cb[4], gb[4];
-            const float4 ar4 = OI_GS(kSlabArg + 0, quad);
+            const float4 ar4 = arc[q];
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            const float4 g14 = OI_CTA(kCtaG + 0, quad);   // g_1
+            const float4 g14 = gc[q];   // g_1
             const float g1[4] = {g14.x, g14.y, g14.z, g14.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -589,6 +638,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = 1; l < D; ++l) {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
         const float2* fb = fb_inst + l * kW + n0;
+        if (l + 1 < D) {           // next: backward of the reverse sweep, layer l+1
+          OI_PF_GS(kSlabArg + l + 1);
+          if (l + 1 < D - 1) OI_PF_CTA(kCtaG + l + 1);
+          else OI_PF_CTA(kCtaHB);
+        } else {                   // next: backward of the forward sweep, layer D-2
+          OI_PF_GS(kSlabArg + D - 2);
+          OI_PF_CTA(kCtaG + D - 2);
+        }
+        const int gslab = (l < D - 1) ? kCtaG + l : kCtaHB;   // g_{l+1}, or h_bar_D at the top
+        float4 arn[4], gn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          arn[q] = OI_GS(kSlabArg + l, Q0 + q);
+          gn[q] = OI_CTA(gslab, Q0 + q);
+        }
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -597,16 +661,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
+          float4 arc[4], gc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            arc[q] = arn[q];
+            gc[q] = gn[q];
+          }
+          if (c < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              arn[q] = OI_GS(kSlabArg + l, Q0 + (c + 1) * 4 + q);
+              gn[q] = OI_CTA(gslab, Q0 + (c + 1) * 4 + q);
+            }
+          }
           uint32_t hi[8], lo[8];
           float dgs[16], dwss[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = OI_GS(kSlabArg + l, quad);
+            const float4 ar4 = arc[q];
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
             float o[4];
             if (l < D - 1) {
-              const float4 g4 = OI_CTA(kCtaG + l, quad);   // g_{l+1}
+              const float4 g4 = gc[q];   // g_{l+1}
               const float gn[4] = {g4.x, g4.y, g4.z, g4.w};
               float cb[4];
 #pragma unroll
@@ -620,7 +697,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               OI_OP4(kSlabGB + l + 1, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
             } else {
               // top: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
-              const float4 hb4 = OI_CTA(kCtaHB, quad);
+              const float4 hb4 = gc[q];
               const float hb[4] = {hb4.x, hb4.y, hb4.z, hb4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -655,6 +732,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         const float* flf = reinterpret_cast<const float*>(sm.film[t][k]) + n0 * 2;
         const float2* fb = fb_inst + k * kW + n0;
         const float gsc = (k == 0) ? 1.0f : kWScale;
+        if (k >= 1) {
+          OI_PF_GS(kSlabArg + k - 1);
+          OI_PF_CTA(kCtaG + k - 1);
+        }
+        float4 arn[4], gn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          arn[q] = OI_GS(kSlabArg + k, Q0 + q);
+          gn[q] = OI_CTA(kCtaG + k, Q0 + q);
+        }
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -663,14 +750,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
+          float4 arc[4], gc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            arc[q] = arn[q];
+            gc[q] = gn[q];
+          }
+          if (c < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              arn[q] = OI_GS(kSlabArg + k, Q0 + (c + 1) * 4 + q);
+              gn[q] = OI_CTA(kCtaG + k, Q0 + (c + 1) * 4 + q);
+            }
+          }
           uint32_t hi[8], lo[8];
           float dgs[16], ubs[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = OI_GS(kSlabArg + k, quad);
+            const float4 ar4 = arc[q];
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            const float4 cb4 = OI_CTA(kCtaG + k, quad);   // c_bar_k
+            const float4 cb4 = gc[q];   // c_bar_k
             const float cb[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
             float o[4];
 #pragma unroll
@@ -719,6 +819,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
 #undef OI_GS
 #undef OI_OP
 #undef OI_OP4
+#undef OI_PF_GS
+#undef OI_PF_CTA
 #undef OI_A_READY
 #undef OI_WAIT_ACC
   }
