@@ -169,3 +169,27 @@ def test_rays_requiring_grad_raise():
     with pytest.raises(NotImplementedError):
         r.render(c["rays_o"].requires_grad_(True), c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0,
                  perturb_overwrite=0, w=w)
+
+
+def test_tcgen05_matches_ffma_across_chunks_and_instances():
+    """2 instances x 4096 rays x 40 samples = 2560 tiles: two slab chunks (2048 + 512 tiles) with the instance
+    boundary inside the first chunk's contraction ranges; the tensor-core backward must agree with the FP32 one."""
+    meta, inp, _, _ = load_case("cfg2_n64_m0")
+    meta = dict(meta, n_samples=40, n_importance=0)
+    from oracle import neus_oracle as O
+    c = dict(zip(("rays_o", "rays_d", "near", "far"), (t.cuda() for t in O.synthetic_rays(2, 64, seed=11))))
+    w = inp["w"][:1].cuda().repeat(2, 1)
+    w[1] += 0.2
+    grads = {}
+    for impl in ("ffma", "tcgen05"):
+        r = _build(meta, impl=impl)
+        named = _params(r)
+        wk = w.clone().requires_grad_(True)
+        out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0, perturb_overwrite=0, w=wk)
+        img = out["color_fine"] + (1.0 - out["weight_sum"])
+        loss = (img ** 2).mean() + 0.1 * out["gradient_error"] + (out["weights"][..., None] * out["gradients"]).sum() * 1e-3
+        grads[impl] = torch.autograd.grad(loss, [t for _, t in named] + [wk])
+    torch.cuda.synchronize()
+    for (k, _), a, b in zip(_params(r) + [("w", None)], grads["ffma"], grads["tcgen05"]):
+        s = float(a.abs().max()) + 1e-30
+        assert float((a - b).abs().max()) / s < 2e-3, (k, float((a - b).abs().max()) / s)
