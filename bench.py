@@ -271,6 +271,42 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- side measurement (rank 0, outside every timed region): the grad-mode render of the generator update,
+    # forward + loss + hand-written backward (oi_render_backward), one instance of the workload
+    r1 = R // bs
+    bwd_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for e in bwd_ev:
+        e.record()
+    renderer.bwd_events = bwd_ev
+    gparams = list(sdf.parameters()) + list(col.parameters()) + list(devn.parameters())
+
+    def grad_step():
+        for p_ in gparams:
+            p_.grad = None
+        w = sdf.style(d_z[:1])
+        out = renderer.render(d_ro[:r1], d_rd[:r1], d_near[:r1], d_far[:r1], cos_anneal_ratio=1.0,
+                              perturb_overwrite=0, z=d_z[:1], w=w)
+        img = out["color_fine"] + (1.0 - out["weight_sum"])
+        ((img ** 2).mean() + 0.1 * out["gradient_error"]).backward()
+
+    for _ in range(3):
+        grad_step()
+    torch.cuda.synchronize()
+    gs = []
+    for i in range(5):
+        flush.fill_(i)
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        grad_step()
+        b_.record()
+        b_.synchronize()
+        gs.append(a_.elapsed_time(b_))
+    renderer.bwd_events = None
+    gs.sort()
+    grad_info = {"ms": gs[len(gs) // 2], "rays": r1, "bwd_kernels_ms": bwd_ev[0].elapsed_time(bwd_ev[1]),
+                 "what": "grad-mode render of 1 instance: forward + loss + oi_render_backward (sweep kernel on tcgen05 "
+                         "+ TMA-fed TF32 point-contraction), gradients on every nn.Parameter"}
+
     peaks = load_peaks()
     core_avg_ms = sum(core_ms) / len(core_ms)
     used_tc = args.kernel in ("auto", "tcgen05")   # auto resolves to the tcgen05 core for depth >= 2
@@ -308,6 +344,7 @@ def main():
                              "frac": hbm_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "path is compute-bound (8100 FLOP/B); reported because BASELINE north_star asks"}},
         "clocks": clocks,
+        "grad_step": grad_info,
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(P)
