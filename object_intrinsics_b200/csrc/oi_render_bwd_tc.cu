@@ -245,19 +245,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     OI_OP(slab, (j0) + 2, a2);           \
     OI_OP(slab, (j0) + 3, a3);           \
   } while (0)
-/* pull a slab back from DRAM into L2 one epilogue ahead of its use (one lane per 128-byte line) */
-#define OI_PF_GS(slab)                                                        \
-  do {                                                                        \
-    if ((m & 7) == 0) {                                                       \
-      _Pragma("unroll 4") for (int q_ = 0; q_ < 16; ++q_) l2_prefetch(&OI_GS(slab, Q0 + q_)); \
-    }                                                                         \
-  } while (0)
-#define OI_PF_CTA(slab)                                                       \
-  do {                                                                        \
-    if ((m & 7) == 0) {                                                       \
-      _Pragma("unroll 4") for (int q_ = 0; q_ < 16; ++q_) l2_prefetch(&OI_CTA(slab, Q0 + q_)); \
-    }                                                                         \
-  } while (0)
 #define OI_A_READY()               \
   do {                             \
     tc::wait_st();                 \
@@ -405,8 +392,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = D - 1; l >= 1; --l) {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][l - 1]) + n0 * 2;
         const float gscale = (l - 1 == 0) ? kInvWScale : 1.0f;   // gamma'_0 is unscaled
-        if (l >= 2) OI_PF_GS(kSlabArg + l - 2);
-        else OI_PF_CTA(kCtaUC);
         float4 arn[4];   // one-chunk look-ahead of a_{l-1}, issued before the MMA wait
 #pragma unroll
         for (int q = 0; q < 4; ++q) arn[q] = OI_GS(kSlabArg + l - 1, Q0 + q);
@@ -481,8 +466,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][OI_MAX_DEPTH]) + n0 * 2;
         const float2* fb = fb_inst + OI_MAX_DEPTH * kW + n0;
-        OI_PF_GS(kSlabArg + 0);
-        OI_PF_CTA(kCtaG + 0);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t hi[8], lo[8];
@@ -559,9 +542,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
       {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][0]) + n0 * 2;
-        OI_PF_GS(kSlabArg + 1);
-        if (D > 2) OI_PF_CTA(kCtaG + 1);
-        else OI_PF_CTA(kCtaHB);
         float4 arn[4], gn[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -638,14 +618,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = 1; l < D; ++l) {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
         const float2* fb = fb_inst + l * kW + n0;
-        if (l + 1 < D) {           // next: backward of the reverse sweep, layer l+1
-          OI_PF_GS(kSlabArg + l + 1);
-          if (l + 1 < D - 1) OI_PF_CTA(kCtaG + l + 1);
-          else OI_PF_CTA(kCtaHB);
-        } else {                   // next: backward of the forward sweep, layer D-2
-          OI_PF_GS(kSlabArg + D - 2);
-          OI_PF_CTA(kCtaG + D - 2);
-        }
         const int gslab = (l < D - 1) ? kCtaG + l : kCtaHB;   // g_{l+1}, or h_bar_D at the top
         float4 arn[4], gn[4];
 #pragma unroll
@@ -732,10 +704,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         const float* flf = reinterpret_cast<const float*>(sm.film[t][k]) + n0 * 2;
         const float2* fb = fb_inst + k * kW + n0;
         const float gsc = (k == 0) ? 1.0f : kWScale;
-        if (k >= 1) {
-          OI_PF_GS(kSlabArg + k - 1);
-          OI_PF_CTA(kCtaG + k - 1);
-        }
         float4 arn[4], gn[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -819,8 +787,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
 #undef OI_GS
 #undef OI_OP
 #undef OI_OP4
-#undef OI_PF_GS
-#undef OI_PF_CTA
 #undef OI_A_READY
 #undef OI_WAIT_ACC
   }
