@@ -346,6 +346,29 @@ typedef struct OiRenderMapsDesc {
 } OiRenderMapsDesc;
 int oi_render_maps(const OiRenderMapsDesc* desc, void* stream);
 
+/* Geometric path of the ADA AugmentPipe (src/third_party/ada/augment.py:270-301): reflect-pad by `margins`,
+ * 2x up-sample with the separable low-pass `filter` (gain 4), bilinear affine resample (affine_grid + grid_sample,
+ * align_corners = False, zeros outside) onto a [(H + 2 hz_pad) * 2, (W + 2 hz_pad) * 2] grid, 2x down-sample
+ * (correlation) with crop; hz_pad = filter_taps / 4.  `theta` are the final affine_grid matrices of augment.py:297
+ * and `margins` the integers of augment.py:283, both DEVICE tensors (the reference reads the margins back to the
+ * host; here nothing synchronises).  The map x -> y is linear: oi_augment_geom_backward applies its adjoint
+ * (x = dL/dy in, y = dL/dx out), and the double backward of the R1 penalty is oi_augment_geom_forward again. */
+typedef struct OiAugmentGeomDesc {
+  int32_t batch, channels, height, width;
+  int32_t filter_taps;    /* even, <= 16 (12 = sym6) */
+  int32_t reserved;
+  const float* filter;    /* HOST pointer: [filter_taps] taps (normalised to unit DC by the caller) */
+  const float* theta;     /* [batch,2,3] */
+  const int32_t* margins; /* [4] = mx0, my0, mx1, my1, each in [0, size-1] */
+  const float* x;         /* [batch,channels,height,width] */
+  float* y;               /* [batch,channels,height,width] */
+  void* workspace;        /* >= oi_augment_geom_workspace_bytes(desc) */
+  size_t workspace_bytes;
+} OiAugmentGeomDesc;
+int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* desc, size_t* bytes);
+int oi_augment_geom_forward(const OiAugmentGeomDesc* desc, void* stream);
+int oi_augment_geom_backward(const OiAugmentGeomDesc* desc, void* stream);
+
 /* Self-test of the tcgen05 building blocks: d[128,128] = a[128,128] * B^T through the split-fp16 UMMA path.
  * B = b[128,128] ([n][k] row-major) when packed_weights is NULL, else panel `panel` of the packed blob
  * (order: forward l=1..D-1, colour features, reverse l=D-1..1; each is 2^8 * W in [n][k] orientation). */

@@ -115,6 +115,15 @@ class OiGenRaysDesc(C.Structure):
     ]
 
 
+class OiAugmentGeomDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("filter_taps", C.c_int32), ("reserved", C.c_int32),
+        ("filter", C.POINTER(C.c_float)), ("theta", f32p), ("margins", C.c_void_p), ("x", f32p), ("y", f32p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class OiRenderMapsDesc(C.Structure):
     _fields_ = [
         ("n_rays", C.c_int32), ("rays_per_instance", C.c_int32), ("n_samples", C.c_int32), ("reserved", C.c_int32),
@@ -132,7 +141,8 @@ class OiRenderMapsDesc(C.Structure):
 EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_render_workspace_bytes",
            "oi_render_forward", "oi_render_launch_count", "oi_upfirdn2d", "oi_bias_act", "oi_fused_bias_act",
            "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps",
-           "oi_render_backward_workspace_bytes", "oi_render_backward", "oi_selftest_wgrad"]
+           "oi_render_backward_workspace_bytes", "oi_render_backward", "oi_selftest_wgrad",
+           "oi_augment_geom_workspace_bytes", "oi_augment_geom_forward", "oi_augment_geom_backward"]
 
 _lib = None
 
@@ -159,6 +169,9 @@ def lib():
     L.oi_render_backward_workspace_bytes.argtypes = [C.POINTER(OiRenderBwdDesc), C.POINTER(C.c_size_t)]
     L.oi_render_backward.argtypes = [C.POINTER(OiRenderBwdDesc), C.c_void_p]
     L.oi_selftest_wgrad.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.oi_augment_geom_workspace_bytes.argtypes = [C.POINTER(OiAugmentGeomDesc), C.POINTER(C.c_size_t)]
+    L.oi_augment_geom_forward.argtypes = [C.POINTER(OiAugmentGeomDesc), C.c_void_p]
+    L.oi_augment_geom_backward.argtypes = [C.POINTER(OiAugmentGeomDesc), C.c_void_p]
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]
     L.oi_bias_act.argtypes = [C.POINTER(OiBiasActDesc), C.c_void_p]
     L.oi_fused_bias_act.argtypes = [C.POINTER(OiFusedBiasActDesc), C.c_void_p]

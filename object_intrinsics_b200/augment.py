@@ -1,0 +1,207 @@
+"""Drop-in for the reference's `AugmentPipe` (src/third_party/ada/augment.py:113-421) for the options its configs
+enable (configs/train.yaml:80-100: `scale`, `xint`; all pixel-blitting / general geometric options are supported).
+
+    model.discriminator.kwargs.aug.__target__=object_intrinsics_b200.augment.AugmentPipe
+
+Same constructor keywords, the `p` buffer (overall probability multiplier, updated by ADA controllers), the same
+order of random draws (augment.py:196-264), and `forward(images)` returns the same image as the reference under the
+same torch seed (tests/test_augment_gpu.py).  The geometric execution (augment.py:270-301: reflect-pad, 2x
+up-sample, affine resample, 2x down-sample) runs as two CUDA kernels through `oi_augment_geom_forward` with the
+padding margins kept on the device -- the reference's `margin.ceil().to(torch.int32)` + `F.pad(pad=[...])`
+(augment.py:283,286) is a device->host sync on every discriminator forward.  The map is linear in the images:
+backward = `oi_augment_geom_backward` (the adjoint), double backward (R1, src/loss/gan.py:5-14) = the forward.
+Colour / image-space filtering / noise / cutout (augment.py:303-421) are disabled in the reference's configs and
+raise NotImplementedError when enabled.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+SYM6 = [0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.048311742585633, 0.4910559419267466,
+        0.787641141030194, 0.3379294217276218, -0.07263752278646252, -0.021060292512300564, 0.04472490177066578,
+        0.0017677118642428036, -0.007800708325034148]   # augment.py:24 wavelets['sym6']
+
+_WS = {}
+
+
+def _workspace(dev, nbytes):
+    t = _WS.get(dev)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WS[dev] = t
+    return t
+
+
+def _geom_call(x, theta, margins, taps, backward):
+    if not x.is_cuda:
+        raise RuntimeError("object_intrinsics_b200.augment has no CPU path: images must be CUDA tensors")
+    L = _lib.lib()
+    x = x.to(torch.float32).contiguous()
+    y = torch.empty_like(x)
+    d = _lib.OiAugmentGeomDesc()
+    d.batch, d.channels, d.height, d.width = x.shape
+    d.filter_taps = len(taps)
+    farr = (C.c_float * len(taps))(*taps)
+    d.filter = C.cast(farr, C.POINTER(C.c_float))
+    d.theta, d.margins, d.x, d.y = theta.data_ptr(), margins.data_ptr(), x.data_ptr(), y.data_ptr()
+    nbytes = C.c_size_t(0)
+    with torch.cuda.device(x.device):
+        _lib.check(L.oi_augment_geom_workspace_bytes(C.byref(d), C.byref(nbytes)), "oi_augment_geom_workspace_bytes")
+        ws = _workspace(x.device, nbytes.value)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        fn = L.oi_augment_geom_backward if backward else L.oi_augment_geom_forward
+        _lib.check(fn(C.byref(d), _lib.current_stream_ptr(x.device)), "oi_augment_geom")
+    return y
+
+
+class _GeomForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, theta, margins, taps):
+        ctx.save_for_backward(theta, margins)
+        ctx.taps = taps
+        return _geom_call(x, theta, margins, taps, False)
+
+    @staticmethod
+    def backward(ctx, gy):
+        theta, margins = ctx.saved_tensors
+        return _GeomAdjoint.apply(gy, theta, margins, ctx.taps), None, None, None
+
+
+class _GeomAdjoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gy, theta, margins, taps):
+        ctx.save_for_backward(theta, margins)
+        ctx.taps = taps
+        return _geom_call(gy, theta, margins, taps, True)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        theta, margins = ctx.saved_tensors
+        return _GeomForward.apply(ggx, theta, margins, ctx.taps), None, None, None
+
+
+def _mat(rows, like):
+    elems = [x if isinstance(x, torch.Tensor) else torch.full_like(like, float(x)) for row in rows for x in row]
+    return torch.stack(elems, dim=-1).reshape(like.shape + (3, 3))
+
+
+def _translate(tx, ty, like):
+    return _mat([[1, 0, tx], [0, 1, ty], [0, 0, 1]], like)
+
+
+def _scale(sx, sy, like):
+    return _mat([[sx, 0, 0], [0, sy, 0], [0, 0, 1]], like)
+
+
+def _rotate(theta):
+    return _mat([[torch.cos(theta), torch.sin(-theta), 0], [torch.sin(theta), torch.cos(theta), 0], [0, 0, 1]], theta)
+
+
+def geometric_setup(G_inv, height, width, hz_pad):
+    """Padding margins [4] int32 (augment.py:274-283) and affine_grid matrices theta [B,2,3] (augment.py:287-297)
+    from the inverse transform, as device tensors: a handful of [B,3,3] torch ops, no host read-back."""
+    H, W = height, width
+    dev, dt = G_inv.device, torch.float32
+    G_inv = G_inv.to(dt)
+    B = G_inv.shape[0]
+    like = torch.ones([B], device=dev, dtype=dt)
+    cx, cy = (W - 1) / 2, (H - 1) / 2
+    cp = torch.tensor([[-cx, -cy, 1], [cx, -cy, 1], [cx, cy, 1], [-cx, cy, 1]], device=dev, dtype=dt)
+    cp = G_inv @ cp.t()
+    m = cp[:, :2, :].permute(1, 0, 2).flatten(1)
+    m = torch.cat([-m, m]).max(dim=1).values
+    m = m + torch.tensor([hz_pad * 2 - cx, hz_pad * 2 - cy] * 2, device=dev, dtype=dt)
+    m = m.max(torch.zeros(4, device=dev, dtype=dt)).min(torch.tensor([W - 1, H - 1] * 2, device=dev, dtype=dt))
+    margins = m.ceil().to(torch.int32)                      # [mx0, my0, mx1, my1], stays on the device
+    mf = margins.to(dt)
+    Wp, Hp = W + mf[0] + mf[2], H + mf[1] + mf[3]           # padded size, device scalars
+    G = _translate((mf[0] - mf[2]) / 2 * like, (mf[1] - mf[3]) / 2 * like, like) @ G_inv
+    G = _scale(2, 2, like) @ G @ _scale(1 / 2, 1 / 2, like)
+    G = _translate(-0.5, -0.5, like) @ G @ _translate(0.5, 0.5, like)
+    Wr, Hr = (W + hz_pad * 2) * 2, (H + hz_pad * 2) * 2
+    G = _scale(2 / (2 * Wp) * like, 2 / (2 * Hp) * like, like) @ G @ _scale(1 / (2 / Wr), 1 / (2 / Hr), like)
+    return G[:, :2, :].contiguous(), margins
+
+
+def geometric_transform(images, G_inv, taps=None):
+    """augment.py:270-301 for a given inverse transform G_inv [B,3,3] (pixel_out -> pixel_in)."""
+    taps = tuple(taps) if taps is not None else tuple(t / sum(SYM6) for t in SYM6)
+    theta, margins = geometric_setup(G_inv, images.shape[2], images.shape[3], len(taps) // 4)
+    return _GeomForward.apply(images, theta, margins, taps)
+
+
+class AugmentPipe(torch.nn.Module):
+    """Constructor keywords of the reference class (augment.py:114-121)."""
+
+    def __init__(self, xflip=0, rotate90=0, xint=0, xint_max=0.125, scale=0, rotate=0, aniso=0, xfrac=0,
+                 scale_std=0.2, rotate_max=1, aniso_std=0.2, xfrac_std=0.125, brightness=0, contrast=0, lumaflip=0,
+                 hue=0, saturation=0, brightness_std=0.2, contrast_std=0.5, hue_max=1, saturation_std=1, imgfilter=0,
+                 imgfilter_bands=(1, 1, 1, 1), imgfilter_std=1, noise=0, cutout=0, noise_std=0.1, cutout_size=0.5):
+        super().__init__()
+        if any(float(v) > 0 for v in (brightness, contrast, lumaflip, hue, saturation, imgfilter, noise, cutout)):
+            raise NotImplementedError("colour / filtering / noise / cutout augmentations (augment.py:303-421) are "
+                                      "disabled in the reference's configs and are not implemented")
+        self.register_buffer("p", torch.ones([]))
+        self.xflip, self.rotate90, self.xint, self.xint_max = float(xflip), float(rotate90), float(xint), float(xint_max)
+        self.scale, self.rotate, self.aniso, self.xfrac = float(scale), float(rotate), float(aniso), float(xfrac)
+        self.scale_std, self.rotate_max = float(scale_std), float(rotate_max)
+        self.aniso_std, self.xfrac_std = float(aniso_std), float(xfrac_std)
+        f = torch.tensor(SYM6, dtype=torch.float32)
+        self.register_buffer("Hz_geom", f / f.sum())          # upfirdn2d.setup_filter(wavelets['sym6']), augment.py:116
+        self._taps = tuple(float(v) for v in (f / f.sum()))
+
+    def sample_inverse_transform(self, batch, width, height, device):
+        """G_inv [B,3,3] (pixel_out -> pixel_in), random draws in the reference's order (augment.py:196-264)."""
+        G = torch.eye(3, device=device)
+        ones = torch.ones([batch], device=device)
+        p = self.p
+        enabled = False
+        if self.xflip > 0:
+            i = torch.floor(torch.rand([batch], device=device) * 2)
+            i = torch.where(torch.rand([batch], device=device) < self.xflip * p, i, torch.zeros_like(i))
+            G, enabled = G @ _scale(1 / (1 - 2 * i), 1 / ones, ones), True
+        if self.rotate90 > 0:
+            i = torch.floor(torch.rand([batch], device=device) * 4)
+            i = torch.where(torch.rand([batch], device=device) < self.rotate90 * p, i, torch.zeros_like(i))
+            G, enabled = G @ _rotate(-(-math.pi / 2 * i)), True
+        if self.xint > 0:
+            t = (torch.rand([batch, 2], device=device) * 2 - 1) * self.xint_max
+            t = torch.where(torch.rand([batch, 1], device=device) < self.xint * p, t, torch.zeros_like(t))
+            G, enabled = G @ _translate(-torch.round(t[:, 0] * width), -torch.round(t[:, 1] * height), ones), True
+        if self.scale > 0:
+            s = torch.exp2(torch.randn([batch], device=device) * self.scale_std)
+            s = torch.where(torch.rand([batch], device=device) < self.scale * p, s, torch.ones_like(s))
+            G, enabled = G @ _scale(1 / s, 1 / s, ones), True
+        p_rot = 1 - torch.sqrt((1 - self.rotate * p).clamp(0, 1))
+        if self.rotate > 0:
+            th = (torch.rand([batch], device=device) * 2 - 1) * math.pi * self.rotate_max
+            th = torch.where(torch.rand([batch], device=device) < p_rot, th, torch.zeros_like(th))
+            G, enabled = G @ _rotate(-(-th)), True
+        if self.aniso > 0:
+            s = torch.exp2(torch.randn([batch], device=device) * self.aniso_std)
+            s = torch.where(torch.rand([batch], device=device) < self.aniso * p, s, torch.ones_like(s))
+            G, enabled = G @ _scale(1 / s, 1 / (1 / s), ones), True
+        if self.rotate > 0:
+            th = (torch.rand([batch], device=device) * 2 - 1) * math.pi * self.rotate_max
+            th = torch.where(torch.rand([batch], device=device) < p_rot, th, torch.zeros_like(th))
+            G, enabled = G @ _rotate(-(-th)), True
+        if self.xfrac > 0:
+            t = torch.randn([batch, 2], device=device) * self.xfrac_std
+            t = torch.where(torch.rand([batch, 1], device=device) < self.xfrac * p, t, torch.zeros_like(t))
+            G, enabled = G @ _translate(-(t[:, 0] * width), -(t[:, 1] * height), ones), True
+        return G if enabled else None
+
+    def forward(self, images, debug_percentile=None):
+        if debug_percentile is not None:
+            raise NotImplementedError("debug_percentile is a debugging aid of the reference and is not implemented")
+        assert isinstance(images, torch.Tensor) and images.ndim == 4
+        B, _, H, W = images.shape
+        G_inv = self.sample_inverse_transform(B, W, H, images.device)
+        if G_inv is None:
+            return images
+        return geometric_transform(images, G_inv, self._taps)

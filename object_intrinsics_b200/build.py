@@ -16,7 +16,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liboi_b200.so")
 SOURCES = ["oi_api.cu", "oi_render_ffma.cu", "oi_render_tc.cu", "oi_render_bwd.cu", "oi_wgrad_tc.cu", "oi_render_bwd_tc.cu",
            "oi_render_aux.cu", "oi_ops.cu",
-           "oi_generator.cu"]
+           "oi_generator.cu", "oi_augment.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 # NOTE: --use_fast_math is deliberately NOT wanted for the render path (expf/div accuracy); see below.

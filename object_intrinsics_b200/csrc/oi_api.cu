@@ -422,6 +422,39 @@ int oi_selftest_wgrad(const float* slabs, const float* aux, int32_t n_tiles, int
   return launch_wgrad_tc(a, static_cast<cudaStream_t>(stream));
 }
 
+static int check_augment(const OiAugmentGeomDesc* d, bool need_ws) {
+  OI_CHECK_ARG(d != nullptr, "desc is NULL");
+  OI_CHECK_ARG(d->batch > 0 && d->channels > 0 && d->height >= 2 && d->width >= 2, "bad image sizes");
+  OI_CHECK_ARG(d->filter_taps >= 4 && d->filter_taps <= 16 && d->filter_taps % 4 == 0,
+               "filter_taps must be a multiple of 4 in [4, 16] (got %d)", d->filter_taps);
+  if (!need_ws) return OI_OK;
+  OI_CHECK_ARG(d->filter && d->theta && d->margins && d->x && d->y, "NULL pointer");
+  const size_t need = (augment_u_floats(*d) + augment_r_floats(*d)) * sizeof(float);
+  OI_CHECK_ARG(d->workspace != nullptr, "workspace is NULL");
+  if (d->workspace_bytes < need) return set_error(OI_ERR_WORKSPACE, "workspace too small: %zu < %zu", d->workspace_bytes, need);
+  return OI_OK;
+}
+
+int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* d, size_t* bytes) {
+  int rc = check_augment(d, false);
+  if (rc) return rc;
+  OI_CHECK_ARG(bytes != nullptr, "bytes is NULL");
+  *bytes = (augment_u_floats(*d) + augment_r_floats(*d)) * sizeof(float);
+  return OI_OK;
+}
+
+int oi_augment_geom_forward(const OiAugmentGeomDesc* d, void* stream) {
+  int rc = check_augment(d, true);
+  if (rc) return rc;
+  return launch_augment_geom(*d, false, static_cast<cudaStream_t>(stream));
+}
+
+int oi_augment_geom_backward(const OiAugmentGeomDesc* d, void* stream) {
+  int rc = check_augment(d, true);
+  if (rc) return rc;
+  return launch_augment_geom(*d, true, static_cast<cudaStream_t>(stream));
+}
+
 int oi_gen_rays(const OiGenRaysDesc* d, void* stream) {
   OI_CHECK_ARG(d != nullptr, "desc is NULL");
   OI_CHECK_ARG(d->n_instances > 0 && d->resolution >= 2 && d->scene_resolution > 0, "bad sizes");

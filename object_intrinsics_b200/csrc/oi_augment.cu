@@ -1,0 +1,287 @@
+// Geometric path of the ADA AugmentPipe (src/third_party/ada/augment.py:270-301 of the reference) without the
+// reference's intermediate tensors and without its device->host sync:
+//     reflect-pad (margins)  ->  2x up-sample (sym6 FIR, gain 4)  ->  bilinear affine resample (zeros outside)
+//     ->  2x down-sample (sym6 FIR, correlation) + crop
+// The reference materialises the padded image, the up-sampled image, the sampling grid and the resampled image
+// (augment.py:286-301) and reads the padding margins back to the host (`margin.ceil().to(torch.int32)`, :283).
+// Here the margins stay on the device (a [4] int32 tensor read by the kernels), and the chain is two kernels:
+//   augment_up_kernel       : U = upsample(reflect_pad(x)) evaluated polyphase straight from x (36 taps / pixel)
+//   augment_resample_kernel : y = downsample(resample(U)) per output pixel: 12x12 FIR taps, each a bilinear lookup
+// The map x -> y is linear, so the backward is its adjoint and the double backward (R1 regularisation,
+// src/loss/gan.py:5-14) is the forward again:
+//   augment_down_adj_kernel     : dR = downsample^T dy            (gather, 6x6 taps)
+//   augment_resample_adj_kernel : dU += resample^T dR             (4 reductions per resampled pixel)
+//   augment_up_adj_kernel       : dx = (upsample o reflect_pad)^T dU   (gather over the <= 3x3 reflected pre-images)
+// Filters are separable with an even number of taps T (T = 12, hz_pad = T / 4 = 3 in the reference).
+#include "oi_internal.cuh"
+
+namespace oi {
+
+namespace {
+
+constexpr int kMaxTaps = 16;
+
+struct AugArgs {
+  int B, C, H, W, T;
+  int HzPad;               // T / 4
+  const float* theta;      // [B,2,3] affine_grid matrices (normalised output coords -> normalised U coords)
+  const int* margins;      // [4] mx0, my0, mx1, my1
+  float f[kMaxTaps];       // filter taps
+  const float* x;          // forward: images; backward: dy
+  float* y;                // forward: output; backward: dx
+  float* U;                // workspace [B,C,Hu_max,Wu_max] with row stride Wu (actual), plane stride Hu*Wu (actual)
+  float* R;                // backward workspace [B,C,Hr,Wr]
+};
+
+__device__ __forceinline__ int reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// U[u] = 2 * sum_k f[T-1-k] z[u + k - p0], z[2i] = P[i]  (per dimension; p0 = (T + 1) / 2)
+__global__ void augment_up_kernel(const AugArgs a) {
+  const int mx0 = a.margins[0], my0 = a.margins[1], mx1 = a.margins[2], my1 = a.margins[3];
+  const int Wp = a.W + mx0 + mx1, Hp = a.H + my0 + my1;
+  const int Wu = 2 * Wp, Hu = 2 * Hp;
+  const int p0 = (a.T + 1) / 2;   // (fw + up - 1) // 2
+  const int nc = blockIdx.z;
+  const float* src = a.x + (size_t)nc * a.H * a.W;
+  float* dst = a.U + (size_t)nc * Hu * Wu;
+  for (int uy = blockIdx.y * blockDim.y + threadIdx.y; uy < Hu; uy += gridDim.y * blockDim.y) {
+    for (int ux = blockIdx.x * blockDim.x + threadIdx.x; ux < Wu; ux += gridDim.x * blockDim.x) {
+      // taps with (u + k - p0) even: k = k0, k0 + 2, ...
+      const int kx0 = (ux + p0) & 1, ky0 = (uy + p0) & 1;
+      float acc = 0.f;
+      for (int ky = ky0; ky < a.T; ky += 2) {
+        const int zy = uy + ky - p0;
+        if (zy < 0 || zy >= Hu) continue;
+        const int iy = reflect((zy >> 1) - my0, a.H);
+        const float fy = a.f[a.T - 1 - ky];
+        float row = 0.f;
+        for (int kx = kx0; kx < a.T; kx += 2) {
+          const int zx = ux + kx - p0;
+          if (zx < 0 || zx >= Wu) continue;
+          const int ix = reflect((zx >> 1) - mx0, a.W);
+          row = fmaf(a.f[a.T - 1 - kx], src[iy * a.W + ix], row);
+        }
+        acc = fmaf(fy, row, acc);
+      }
+      dst[(size_t)uy * Wu + ux] = 4.0f * acc;
+    }
+  }
+}
+
+struct SamplePos {
+  int x0, y0;
+  float wx, wy;
+};
+// source position in U of resampled pixel (rx, ry): affine_grid + grid_sample, align_corners = False
+__device__ __forceinline__ SamplePos sample_pos(const float* th, int rx, int ry, int Wr, int Hr, int Wu, int Hu) {
+  const float xn = (2.0f * rx + 1.0f) / Wr - 1.0f;
+  const float yn = (2.0f * ry + 1.0f) / Hr - 1.0f;
+  const float xs = th[0] * xn + th[1] * yn + th[2];
+  const float ys = th[3] * xn + th[4] * yn + th[5];
+  const float sx = ((xs + 1.0f) * Wu - 1.0f) * 0.5f;
+  const float sy = ((ys + 1.0f) * Hu - 1.0f) * 0.5f;
+  SamplePos p;
+  const float fx = floorf(sx), fy = floorf(sy);
+  p.x0 = (int)fx;
+  p.y0 = (int)fy;
+  p.wx = sx - fx;
+  p.wy = sy - fy;
+  return p;
+}
+
+// y[o] = sum_k f[k] R[2 o + k + c0], c0 = -((T - 1) / 2 - 2 hz_pad)  (downsample2d padding, correlation)
+__global__ void augment_resample_kernel(const AugArgs a) {
+  const int mx0 = a.margins[0], my0 = a.margins[1], mx1 = a.margins[2], my1 = a.margins[3];
+  const int Wu = 2 * (a.W + mx0 + mx1), Hu = 2 * (a.H + my0 + my1);
+  const int Wr = 2 * (a.W + 2 * a.HzPad), Hr = 2 * (a.H + 2 * a.HzPad);
+  const int c0 = 2 * a.HzPad - (a.T - 1) / 2;   // R index of tap 0 for output 0 (= 1 for T = 12)
+  const int n = blockIdx.z;
+  const float* th = a.theta + n * 6;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ox >= a.W || oy >= a.H) return;
+  float acc[8];
+  for (int c0_ = 0; c0_ < a.C; c0_ += 8) {
+    const int cn = min(8, a.C - c0_);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int ky = 0; ky < a.T; ++ky) {
+      const int ry = 2 * oy + ky + c0;
+      for (int kx = 0; kx < a.T; ++kx) {
+        const int rx = 2 * ox + kx + c0;
+        const SamplePos p = sample_pos(th, rx, ry, Wr, Hr, Wu, Hu);
+        const float wgt = a.f[ky] * a.f[kx];
+        const bool x0in = p.x0 >= 0 && p.x0 < Wu, x1in = p.x0 + 1 >= 0 && p.x0 + 1 < Wu;
+        const bool y0in = p.y0 >= 0 && p.y0 < Hu, y1in = p.y0 + 1 >= 0 && p.y0 + 1 < Hu;
+        const float w00 = (1.f - p.wx) * (1.f - p.wy), w01 = p.wx * (1.f - p.wy);
+        const float w10 = (1.f - p.wx) * p.wy, w11 = p.wx * p.wy;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < cn) {
+            const float* u = a.U + ((size_t)(n * a.C + c0_ + c) * Hu) * Wu;
+            float v = 0.f;
+            if (y0in && x0in) v = fmaf(w00, u[(size_t)p.y0 * Wu + p.x0], v);
+            if (y0in && x1in) v = fmaf(w01, u[(size_t)p.y0 * Wu + p.x0 + 1], v);
+            if (y1in && x0in) v = fmaf(w10, u[(size_t)(p.y0 + 1) * Wu + p.x0], v);
+            if (y1in && x1in) v = fmaf(w11, u[(size_t)(p.y0 + 1) * Wu + p.x0 + 1], v);
+            acc[c] = fmaf(wgt, v, acc[c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < cn) a.y[((size_t)(n * a.C + c0_ + c) * a.H + oy) * a.W + ox] = acc[c];
+  }
+}
+
+// dR[r] = sum over (o, k) with 2 o + k + c0 = r of f[k] dy[o]
+__global__ void augment_down_adj_kernel(const AugArgs a) {
+  const int Wr = 2 * (a.W + 2 * a.HzPad), Hr = 2 * (a.H + 2 * a.HzPad);
+  const int c0 = 2 * a.HzPad - (a.T - 1) / 2;
+  const int nc = blockIdx.z;
+  const float* dy = a.x + (size_t)nc * a.H * a.W;
+  const int rx = blockIdx.x * blockDim.x + threadIdx.x, ry = blockIdx.y * blockDim.y + threadIdx.y;
+  if (rx >= Wr || ry >= Hr) return;
+  float acc = 0.f;
+  for (int ky = (ry - c0) & 1; ky < a.T; ky += 2) {
+    const int oy = (ry - c0 - ky) / 2;
+    if (ry - c0 - ky < 0 || oy >= a.H) continue;
+    float row = 0.f;
+    for (int kx = (rx - c0) & 1; kx < a.T; kx += 2) {
+      const int ox = (rx - c0 - kx) / 2;
+      if (rx - c0 - kx < 0 || ox >= a.W) continue;
+      row = fmaf(a.f[kx], dy[oy * a.W + ox], row);
+    }
+    acc = fmaf(a.f[ky], row, acc);
+  }
+  a.R[((size_t)nc * Hr + ry) * Wr + rx] = acc;
+}
+
+// dU += resample^T dR (U must be zeroed)
+__global__ void augment_resample_adj_kernel(const AugArgs a) {
+  const int mx0 = a.margins[0], my0 = a.margins[1], mx1 = a.margins[2], my1 = a.margins[3];
+  const int Wu = 2 * (a.W + mx0 + mx1), Hu = 2 * (a.H + my0 + my1);
+  const int Wr = 2 * (a.W + 2 * a.HzPad), Hr = 2 * (a.H + 2 * a.HzPad);
+  const int n = blockIdx.z;
+  const float* th = a.theta + n * 6;
+  const int rx = blockIdx.x * blockDim.x + threadIdx.x, ry = blockIdx.y * blockDim.y + threadIdx.y;
+  if (rx >= Wr || ry >= Hr) return;
+  const SamplePos p = sample_pos(th, rx, ry, Wr, Hr, Wu, Hu);
+  const bool x0in = p.x0 >= 0 && p.x0 < Wu, x1in = p.x0 + 1 >= 0 && p.x0 + 1 < Wu;
+  const bool y0in = p.y0 >= 0 && p.y0 < Hu, y1in = p.y0 + 1 >= 0 && p.y0 + 1 < Hu;
+  const float w00 = (1.f - p.wx) * (1.f - p.wy), w01 = p.wx * (1.f - p.wy);
+  const float w10 = (1.f - p.wx) * p.wy, w11 = p.wx * p.wy;
+  for (int c = 0; c < a.C; ++c) {
+    const float g = a.R[((size_t)(n * a.C + c) * Hr + ry) * Wr + rx];
+    float* u = a.U + ((size_t)(n * a.C + c) * Hu) * Wu;
+    if (y0in && x0in) atomicAdd(u + (size_t)p.y0 * Wu + p.x0, w00 * g);
+    if (y0in && x1in) atomicAdd(u + (size_t)p.y0 * Wu + p.x0 + 1, w01 * g);
+    if (y1in && x0in) atomicAdd(u + (size_t)(p.y0 + 1) * Wu + p.x0, w10 * g);
+    if (y1in && x1in) atomicAdd(u + (size_t)(p.y0 + 1) * Wu + p.x0 + 1, w11 * g);
+  }
+}
+
+// dx[i] = sum over padded positions p with reflect(p - m0) = i of dP[p];
+// dP[p] = 4 sum_k f[T-1-ky] f[T-1-kx] dU[2 py + p0 - ky][2 px + p0 - kx]
+__global__ void augment_up_adj_kernel(const AugArgs a) {
+  const int mx0 = a.margins[0], my0 = a.margins[1], mx1 = a.margins[2], my1 = a.margins[3];
+  const int Wp = a.W + mx0 + mx1, Hp = a.H + my0 + my1;
+  const int Wu = 2 * Wp, Hu = 2 * Hp;
+  const int p0 = (a.T + 1) / 2;
+  const int nc = blockIdx.z;
+  const float* dU = a.U + (size_t)nc * Hu * Wu;
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ix >= a.W || iy >= a.H) return;
+  // pre-images of i under the reflect padding: i + m0; m0 - i (i >= 1, left margin); 2(n-1) - i + m0 (i <= n-2, right)
+  int pys[3], pxs[3], ny = 0, nx = 0;
+  pys[ny++] = iy + my0;
+  if (iy >= 1 && iy <= my0) pys[ny++] = my0 - iy;
+  if (iy <= a.H - 2 && (a.H - 1 - iy) <= my1) pys[ny++] = 2 * (a.H - 1) - iy + my0;
+  pxs[nx++] = ix + mx0;
+  if (ix >= 1 && ix <= mx0) pxs[nx++] = mx0 - ix;
+  if (ix <= a.W - 2 && (a.W - 1 - ix) <= mx1) pxs[nx++] = 2 * (a.W - 1) - ix + mx0;
+  float acc = 0.f;
+  for (int a_ = 0; a_ < ny; ++a_) {
+    const int py = pys[a_];
+    for (int b_ = 0; b_ < nx; ++b_) {
+      const int px = pxs[b_];
+      for (int ky = 0; ky < a.T; ++ky) {
+        const int uy = 2 * py + p0 - ky;
+        if (uy < 0 || uy >= Hu) continue;
+        float row = 0.f;
+        for (int kx = 0; kx < a.T; ++kx) {
+          const int ux = 2 * px + p0 - kx;
+          if (ux < 0 || ux >= Wu) continue;
+          row = fmaf(a.f[a.T - 1 - kx], dU[(size_t)uy * Wu + ux], row);
+        }
+        acc = fmaf(a.f[a.T - 1 - ky], row, acc);
+      }
+    }
+  }
+  a.y[((size_t)nc * a.H + iy) * a.W + ix] = 4.0f * acc;
+}
+
+int fill_args(const OiAugmentGeomDesc& d, AugArgs* a) {
+  a->B = d.batch;
+  a->C = d.channels;
+  a->H = d.height;
+  a->W = d.width;
+  a->T = d.filter_taps;
+  a->HzPad = d.filter_taps / 4;
+  a->theta = d.theta;
+  a->margins = d.margins;
+  for (int i = 0; i < kMaxTaps; ++i) a->f[i] = i < d.filter_taps ? d.filter[i] : 0.f;
+  a->x = d.x;
+  a->y = d.y;
+  return OI_OK;
+}
+
+}  // namespace
+
+size_t augment_u_floats(const OiAugmentGeomDesc& d) {
+  // margins are clamped to [0, n-1] per side (augment.py:282): padded size <= 3n - 2
+  return (size_t)d.batch * d.channels * (2 * (size_t)(3 * d.height - 2)) * (2 * (size_t)(3 * d.width - 2));
+}
+size_t augment_r_floats(const OiAugmentGeomDesc& d) {
+  const int hp = d.filter_taps / 4;
+  return (size_t)d.batch * d.channels * (2 * (size_t)(d.height + 2 * hp)) * (2 * (size_t)(d.width + 2 * hp));
+}
+
+int launch_augment_geom(const OiAugmentGeomDesc& d, bool backward, cudaStream_t st) {
+  AugArgs a;
+  fill_args(d, &a);
+  a.U = static_cast<float*>(d.workspace);
+  a.R = a.U + augment_u_floats(d);
+  const dim3 blk(32, 8);
+  const int Hu_max = 2 * (3 * d.height - 2), Wu_max = 2 * (3 * d.width - 2);
+  const int Hr = 2 * (d.height + 2 * a.HzPad), Wr = 2 * (d.width + 2 * a.HzPad);
+  if (!backward) {
+    // grid-stride over the (data-dependent) up-sampled extent: sized for a typical margin, loops cover the rest
+    const dim3 g1((2 * 2 * d.width + 31) / 32, (2 * 2 * d.height + 7) / 8, d.batch * d.channels);
+    augment_up_kernel<<<g1, blk, 0, st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+    const dim3 g2((d.width + 31) / 32, (d.height + 7) / 8, d.batch);
+    augment_resample_kernel<<<g2, blk, 0, st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+  } else {
+    OI_CHECK_CUDA(cudaMemsetAsync(a.U, 0, augment_u_floats(d) * sizeof(float), st));
+    const dim3 g1((Wr + 31) / 32, (Hr + 7) / 8, d.batch * d.channels);
+    augment_down_adj_kernel<<<g1, blk, 0, st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+    const dim3 g2((Wr + 31) / 32, (Hr + 7) / 8, d.batch);
+    augment_resample_adj_kernel<<<g2, blk, 0, st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+    const dim3 g3((d.width + 31) / 32, (d.height + 7) / 8, d.batch * d.channels);
+    augment_up_adj_kernel<<<g3, blk, 0, st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+  }
+  (void)Hu_max;
+  (void)Wu_max;
+  return OI_OK;
+}
+
+}  // namespace oi

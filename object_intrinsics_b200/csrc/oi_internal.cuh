@@ -130,6 +130,9 @@ int launch_upfirdn2d(const OiUpfirdnDesc& d, cudaStream_t s);
 int launch_bias_act(const OiBiasActDesc& d, cudaStream_t s);
 int launch_fused_bias_act(const OiFusedBiasActDesc& d, cudaStream_t s);
 int launch_gen_rays(const OiGenRaysDesc& d, cudaStream_t st);
+int launch_augment_geom(const OiAugmentGeomDesc& d, bool backward, cudaStream_t st);
+size_t augment_u_floats(const OiAugmentGeomDesc& d);
+size_t augment_r_floats(const OiAugmentGeomDesc& d);
 int launch_render_maps(const OiRenderMapsDesc& d, cudaStream_t st);
 int launch_render_ffma(const RenderKArgs& a, cudaStream_t st);
 int launch_render_tc(const RenderKArgs& a, cudaStream_t st);

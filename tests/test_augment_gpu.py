@@ -1,0 +1,78 @@
+"""GPU parity tests of the AugmentPipe geometric path (oi_augment_geom_forward / _backward through
+object_intrinsics_b200.augment) against the unmodified reference's outputs (tests/golden/augment_golden.npz) and
+against fp64 autograd through the oracle.  CUDA and CPU generators draw different numbers, so the inverse transform
+is sampled on the CPU under the fixture's seed (the drop-in's own sampler, pinned to the oracle's by
+tests/test_augment_oracle.py) and handed to the CUDA path."""
+import pytest
+import torch
+
+from oracle import augment_oracle as AO
+from test_augment_oracle import CASES, load
+
+pytestmark = pytest.mark.gpu
+
+
+def _G(meta, B, W, H):
+    from object_intrinsics_b200.augment import AugmentPipe
+    torch.manual_seed(meta["seed"])
+    return AugmentPipe(**meta["kwargs"]).sample_inverse_transform(B, W, H, torch.device("cpu"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference(name):
+    from object_intrinsics_b200.augment import geometric_transform
+    meta, x, y_ref = load(name)
+    B, C, H, W = x.shape
+    y = geometric_transform(x.cuda(), _G(meta, B, W, H).cuda()).cpu()
+    # bilinear weights are differences of fp32 pixel coordinates of magnitude ~100: 1e-5 absolute on O(1) images
+    assert float((y - y_ref).abs().max()) < 5e-5, (name, float((y - y_ref).abs().max()))
+
+
+@pytest.mark.parametrize("name", ["train_rgb", "general", "all_geom"])
+def test_backward_and_double_backward(name):
+    from object_intrinsics_b200.augment import geometric_transform
+    meta, x, _ = load(name)
+    B, C, H, W = x.shape
+    G = _G(meta, B, W, H)
+    g = torch.Generator().manual_seed(1)
+    gy = torch.randn(x.shape, generator=g)
+    v = torch.randn(x.shape, generator=g)
+    # oracle in fp64 (autograd through pad / conv / grid_sample)
+    x64 = x.double().requires_grad_(True)
+    gy64 = gy.double().requires_grad_(True)
+    y64 = AO.geometric_path(x64, G.double())
+    (dx64,) = torch.autograd.grad(y64, x64, gy64, create_graph=True)
+    (ggy64,) = torch.autograd.grad((dx64 * v.double()).sum(), gy64)
+    # CUDA path
+    xc = x.cuda().requires_grad_(True)
+    gyc = gy.cuda().requires_grad_(True)
+    yc = geometric_transform(xc, G.cuda())
+    (dxc,) = torch.autograd.grad(yc, xc, gyc, create_graph=True)
+    (ggyc,) = torch.autograd.grad((dxc * v.cuda()).sum(), gyc)
+    torch.cuda.synchronize()
+    s1, s2 = float(dx64.abs().max()), float(ggy64.abs().max())
+    assert float((dxc.cpu().double() - dx64.detach()).abs().max()) < 1e-4 * s1
+    assert float((ggyc.cpu().double() - ggy64).abs().max()) < 1e-4 * s2
+    # adjoint identity <A x, gy> == <x, A^T gy>
+    lhs = float((yc.detach().double() * gyc.detach().double()).sum())
+    rhs = float((xc.detach().double() * dxc.detach().double()).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+
+
+def test_pipe_end_to_end_and_r1_penalty():
+    """The module as the discriminators use it (configs/train.yaml:80-100), incl. the R1 gradient penalty of
+    src/loss/gan.py:5-14 (grad of the output w.r.t. the input image with create_graph, then backward again)."""
+    from object_intrinsics_b200.augment import AugmentPipe
+    pipe = AugmentPipe(scale=1, xint=1).cuda()
+    x = torch.rand(4, 3, 128, 128, device="cuda", requires_grad=True)
+    wgt = torch.nn.Parameter(torch.randn(3, 128, 128, device="cuda") * 0.01)
+    torch.manual_seed(0)
+    y = pipe(x)
+    assert y.shape == x.shape and torch.isfinite(y).all()
+    d_out = (y * wgt).sum((1, 2, 3))                       # a linear stand-in for D(aug(x))
+    (grad_x,) = torch.autograd.grad(d_out.sum(), x, create_graph=True)
+    reg = grad_x.pow(2).reshape(4, -1).sum(1).mean()
+    reg.backward()
+    assert wgt.grad is not None and torch.isfinite(wgt.grad).all() and float(wgt.grad.abs().max()) > 0
+    # identity when nothing is enabled
+    assert AugmentPipe()(x) is x
