@@ -365,6 +365,10 @@ typedef struct OiAugmentGeomDesc {
   void* workspace;        /* >= oi_augment_geom_workspace_bytes(desc) */
   size_t workspace_bytes;
 } OiAugmentGeomDesc;
+/* Margins [4] (augment.py:274-283) and affine_grid matrices theta [batch,2,3] (augment.py:287-297) from the inverse
+ * transforms g_inv [batch,3,3] (pixel_out -> pixel_in, centred pixel coordinates); everything on the device. */
+int oi_augment_geom_setup(const float* g_inv, int32_t batch, int32_t height, int32_t width, int32_t filter_taps,
+                          float* theta, int32_t* margins, void* stream);
 int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* desc, size_t* bytes);
 int oi_augment_geom_forward(const OiAugmentGeomDesc* desc, void* stream);
 int oi_augment_geom_backward(const OiAugmentGeomDesc* desc, void* stream);

@@ -142,7 +142,8 @@ EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_ren
            "oi_render_forward", "oi_render_launch_count", "oi_upfirdn2d", "oi_bias_act", "oi_fused_bias_act",
            "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps",
            "oi_render_backward_workspace_bytes", "oi_render_backward", "oi_selftest_wgrad",
-           "oi_augment_geom_workspace_bytes", "oi_augment_geom_forward", "oi_augment_geom_backward"]
+           "oi_augment_geom_workspace_bytes", "oi_augment_geom_forward", "oi_augment_geom_backward",
+           "oi_augment_geom_setup"]
 
 _lib = None
 
@@ -170,6 +171,8 @@ def lib():
     L.oi_render_backward.argtypes = [C.POINTER(OiRenderBwdDesc), C.c_void_p]
     L.oi_selftest_wgrad.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
     L.oi_augment_geom_workspace_bytes.argtypes = [C.POINTER(OiAugmentGeomDesc), C.POINTER(C.c_size_t)]
+    L.oi_augment_geom_setup.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
     L.oi_augment_geom_forward.argtypes = [C.POINTER(OiAugmentGeomDesc), C.c_void_p]
     L.oi_augment_geom_backward.argtypes = [C.POINTER(OiAugmentGeomDesc), C.c_void_p]
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]

@@ -128,10 +128,26 @@ def geometric_setup(G_inv, height, width, hz_pad):
     return G[:, :2, :].contiguous(), margins
 
 
+def geometric_setup_cuda(G_inv, height, width, n_taps):
+    """`geometric_setup` as one tiny kernel (oi_augment_geom_setup) instead of ~40 torch launches."""
+    L = _lib.lib()
+    G_inv = G_inv.detach().to(torch.float32).contiguous()
+    B = G_inv.shape[0]
+    theta = torch.empty((B, 2, 3), dtype=torch.float32, device=G_inv.device)
+    margins = torch.empty(4, dtype=torch.int32, device=G_inv.device)
+    with torch.cuda.device(G_inv.device):
+        _lib.check(L.oi_augment_geom_setup(G_inv.data_ptr(), B, height, width, n_taps, theta.data_ptr(),
+                                           margins.data_ptr(), _lib.current_stream_ptr(G_inv.device)),
+                   "oi_augment_geom_setup")
+    return theta, margins
+
+
 def geometric_transform(images, G_inv, taps=None):
     """augment.py:270-301 for a given inverse transform G_inv [B,3,3] (pixel_out -> pixel_in)."""
+    if not images.is_cuda:
+        raise RuntimeError("object_intrinsics_b200.augment has no CPU path: images must be CUDA tensors")
     taps = tuple(taps) if taps is not None else tuple(t / sum(SYM6) for t in SYM6)
-    theta, margins = geometric_setup(G_inv, images.shape[2], images.shape[3], len(taps) // 4)
+    theta, margins = geometric_setup_cuda(G_inv.to(images.device), images.shape[2], images.shape[3], len(taps))
     return _GeomForward.apply(images, theta, margins, taps)
 
 

@@ -435,6 +435,14 @@ static int check_augment(const OiAugmentGeomDesc* d, bool need_ws) {
   return OI_OK;
 }
 
+int oi_augment_geom_setup(const float* g_inv, int32_t batch, int32_t height, int32_t width, int32_t filter_taps,
+                          float* theta, int32_t* margins, void* stream) {
+  OI_CHECK_ARG(g_inv && theta && margins, "NULL pointer");
+  OI_CHECK_ARG(batch > 0 && height >= 2 && width >= 2 && filter_taps >= 4 && filter_taps % 4 == 0, "bad sizes");
+  return launch_augment_setup(g_inv, batch, height, width, filter_taps / 4, theta, margins,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* d, size_t* bytes) {
   int rc = check_augment(d, false);
   if (rc) return rc;

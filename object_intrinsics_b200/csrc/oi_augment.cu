@@ -225,6 +225,67 @@ __global__ void augment_up_adj_kernel(const AugArgs a) {
   a.y[((size_t)nc * a.H + iy) * a.W + ix] = 4.0f * acc;
 }
 
+// Margins (augment.py:274-283) and affine_grid matrices (augment.py:287-297) from the inverse transforms: one
+// block; replaces ~40 tiny torch launches and the reference's host read-back of the margins.
+struct M3 {
+  double m[9];
+};
+__device__ __forceinline__ M3 mul3(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[i * 3 + j] = a.m[i * 3] * b.m[j] + a.m[i * 3 + 1] * b.m[3 + j] + a.m[i * 3 + 2] * b.m[6 + j];
+  return r;
+}
+__device__ __forceinline__ M3 scale3(double sx, double sy) { return M3{{sx, 0, 0, 0, sy, 0, 0, 0, 1}}; }
+__device__ __forceinline__ M3 trans3(double tx, double ty) { return M3{{1, 0, tx, 0, 1, ty, 0, 0, 1}}; }
+
+__global__ void augment_setup_kernel(const float* __restrict__ G_inv, int B, int H, int W, int hz_pad,
+                                     float* __restrict__ theta, int* __restrict__ margins) {
+  __shared__ float red[4][32];
+  __shared__ int marg[4];
+  const int tid = threadIdx.x;   // 32 threads
+  const float cx = (W - 1) * 0.5f, cy = (H - 1) * 0.5f;
+  float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, m3 = -1e30f;   // max(-x), max(-y), max(x), max(y)
+  for (int b = tid; b < B; b += 32) {
+    const float* g = G_inv + b * 9;
+    const float xs[4] = {-cx, cx, cx, -cx}, ys[4] = {-cy, -cy, cy, cy};
+    for (int k = 0; k < 4; ++k) {
+      const float px = g[0] * xs[k] + g[1] * ys[k] + g[2];
+      const float py = g[3] * xs[k] + g[4] * ys[k] + g[5];
+      m0 = fmaxf(m0, -px);
+      m1 = fmaxf(m1, -py);
+      m2 = fmaxf(m2, px);
+      m3 = fmaxf(m3, py);
+    }
+  }
+  red[0][tid] = m0;
+  red[1][tid] = m1;
+  red[2][tid] = m2;
+  red[3][tid] = m3;
+  __syncthreads();
+  if (tid < 4) {
+    float v = -1e30f;
+    for (int i = 0; i < 32; ++i) v = fmaxf(v, red[tid][i]);
+    v += (tid & 1) ? (hz_pad * 2 - cy) : (hz_pad * 2 - cx);
+    v = fminf(fmaxf(v, 0.f), (tid & 1) ? (float)(H - 1) : (float)(W - 1));
+    marg[tid] = (int)ceilf(v);
+    margins[tid] = marg[tid];
+  }
+  __syncthreads();
+  const int mx0 = marg[0], my0 = marg[1], mx1 = marg[2], my1 = marg[3];
+  const double Wu = 2.0 * (W + mx0 + mx1), Hu = 2.0 * (H + my0 + my1);
+  const double Wr = 2.0 * (W + 2 * hz_pad), Hr = 2.0 * (H + 2 * hz_pad);
+  for (int b = tid; b < B; b += 32) {
+    M3 G;
+    for (int i = 0; i < 9; ++i) G.m[i] = G_inv[b * 9 + i];
+    G = mul3(trans3((mx0 - mx1) * 0.5, (my0 - my1) * 0.5), G);
+    G = mul3(mul3(scale3(2, 2), G), scale3(0.5, 0.5));
+    G = mul3(mul3(trans3(-0.5, -0.5), G), trans3(0.5, 0.5));
+    G = mul3(mul3(scale3(2.0 / Wu, 2.0 / Hu), G), scale3(Wr * 0.5, Hr * 0.5));
+    for (int i = 0; i < 6; ++i) theta[b * 6 + i] = (float)G.m[i];
+  }
+}
+
 int fill_args(const OiAugmentGeomDesc& d, AugArgs* a) {
   a->B = d.batch;
   a->C = d.channels;
@@ -249,6 +310,13 @@ size_t augment_u_floats(const OiAugmentGeomDesc& d) {
 size_t augment_r_floats(const OiAugmentGeomDesc& d) {
   const int hp = d.filter_taps / 4;
   return (size_t)d.batch * d.channels * (2 * (size_t)(d.height + 2 * hp)) * (2 * (size_t)(d.width + 2 * hp));
+}
+
+int launch_augment_setup(const float* G_inv, int B, int H, int W, int hz_pad, float* theta, int* margins,
+                         cudaStream_t st) {
+  augment_setup_kernel<<<1, 32, 0, st>>>(G_inv, B, H, W, hz_pad, theta, margins);
+  OI_CHECK_CUDA(cudaGetLastError());
+  return OI_OK;
 }
 
 int launch_augment_geom(const OiAugmentGeomDesc& d, bool backward, cudaStream_t st) {

@@ -131,6 +131,8 @@ int launch_bias_act(const OiBiasActDesc& d, cudaStream_t s);
 int launch_fused_bias_act(const OiFusedBiasActDesc& d, cudaStream_t s);
 int launch_gen_rays(const OiGenRaysDesc& d, cudaStream_t st);
 int launch_augment_geom(const OiAugmentGeomDesc& d, bool backward, cudaStream_t st);
+int launch_augment_setup(const float* G_inv, int B, int H, int W, int hz_pad, float* theta, int* margins,
+                         cudaStream_t st);
 size_t augment_u_floats(const OiAugmentGeomDesc& d);
 size_t augment_r_floats(const OiAugmentGeomDesc& d);
 int launch_render_maps(const OiRenderMapsDesc& d, cudaStream_t st);
