@@ -790,11 +790,15 @@ __device__ __forceinline__ AlphaTerms alpha_terms(const TailArgs& a, const float
   return t;
 }
 
+// One warp per ray, lanes = consecutive samples (coalesced): pass 1 front to back (alpha, exclusive transmittance
+// by a warp product scan with carry -- the same scan as composite_kernel --, argmax of the weights), pass 2 back to
+// front (suffix sums by a reverse warp scan with carry).
 __global__ void tail_bwd_kernel(const TailArgs a) {
-  const int ray_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int ray_raw = blockIdx.x * wpb + wib;
   const bool live = ray_raw < a.R;
-  const int ray = live ? ray_raw : a.R - 1;   // dead threads shadow the last ray (no stores) for the warp sums
-  const int S = live ? a.S : 0;
+  const int ray = live ? ray_raw : a.R - 1;   // dead warps shadow the last ray (no stores)
+  const int S = a.S;
   const BlobLayout L = blob_layout(a.depth);
   const float inv_s = a.blob[L.const_off + BlobLayout::kScalars + 4];
   const float* zr = a.z_vals + (size_t)ray * S;
@@ -811,40 +815,78 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
   }
   const float ge_coef = a.g_gradient_error ? a.g_gradient_error[0] / ((float)(*a.relax_count) + 1e-5f) : 0.f;
   const float sl_coef = a.g_surface_loss ? a.g_surface_loss[0] / ((float)a.R * (float)S) : 0.f;
+  const int n_blk = (S + 31) / 32;
 
-  // pass 1 (front to back): alpha_i, T_i, argmax of the weights; parked in adj[.][0] / adj[.][7]
-  float T = 1.0f, wmax = -1e30f;
+  // ---- pass 1: alpha_i and T_i parked in adj[.][0] / adj[.][7]; argmax of w_i = alpha_i T_i (first maximum)
+  float carry = 1.0f, wmax = -1e30f;
   int imax = 0;
-  for (int i = 0; i < S; ++i) {
-    const size_t gp = base + i;
-    const AlphaTerms t = alpha_terms(a, zr, i, a.sdf[gp], a.gradients[gp * 3], a.gradients[gp * 3 + 1],
+  for (int blk = 0; blk < n_blk; ++blk) {
+    const int i = blk * 32 + lane;
+    const bool ok = i < S;
+    const size_t gp = base + (ok ? i : S - 1);
+    const AlphaTerms t = alpha_terms(a, zr, ok ? i : S - 1, a.sdf[gp], a.gradients[gp * 3], a.gradients[gp * 3 + 1],
                                      a.gradients[gp * 3 + 2], dx, dy, dz, inv_s);
-    a.adj[gp * 8 + 0] = t.alpha;
-    a.adj[gp * 8 + 7] = T;
-    const float w = t.alpha * T;
+    const float alpha = ok ? t.alpha : 0.f;
+    float incl = ok ? (1.0f - alpha + 1e-7f) : 1.0f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl *= o;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = carry * excl;
+    carry = carry * __shfl_sync(0xffffffffu, incl, 31);
+    if (ok && live) {
+      a.adj[gp * 8 + 0] = alpha;
+      a.adj[gp * 8 + 7] = T;
+    }
+    const float w = ok ? alpha * T : -1e30f;
     if (w > wmax) {
       wmax = w;
       imax = i;
     }
-    T *= (1.0f - t.alpha + 1e-7f);
   }
-  // pass 2 (back to front)
-  float suffix = 0.f, invs_bar = 0.f;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const float ow = __shfl_xor_sync(0xffffffffu, wmax, d);
+    const int oi = __shfl_xor_sync(0xffffffffu, imax, d);
+    if (ow > wmax || (ow == wmax && oi < imax)) {
+      wmax = ow;
+      imax = oi;
+    }
+  }
+  __syncwarp();
+
+  // ---- pass 2: back to front
+  float suffix_carry = 0.f, invs_bar = 0.f;
   float sum_sb = 0.f, sum_z0 = 0.f, sum_z1 = 0.f, sum_z2 = 0.f;
-  for (int i = S - 1; i >= 0; --i) {
-    const size_t gp = base + i;
+  for (int blk = n_blk - 1; blk >= 0; --blk) {
+    const int i = blk * 32 + lane;
+    const bool ok = i < S;
+    const size_t gp = base + (ok ? i : S - 1);
     const float sdf = a.sdf[gp];
     const float gx = a.gradients[gp * 3], gy = a.gradients[gp * 3 + 1], gz = a.gradients[gp * 3 + 2];
     const float r = a.raw_color[gp * 3], g = a.raw_color[gp * 3 + 1], b = a.raw_color[gp * 3 + 2];
-    const AlphaTerms t = alpha_terms(a, zr, i, sdf, gx, gy, gz, dx, dy, dz, inv_s);
-    const float alpha = a.adj[gp * 8 + 0], Ti = a.adj[gp * 8 + 7];
+    const AlphaTerms t = alpha_terms(a, zr, ok ? i : S - 1, sdf, gx, gy, gz, dx, dy, dz, inv_s);
+    const float alpha = live ? a.adj[gp * 8 + 0] : 0.f, Ti = live ? a.adj[gp * 8 + 7] : 0.f;
     const float w = alpha * Ti;
     float wbar = gws + gc0 * r + gc1 * g + gc2 * b;
     if (a.g_weights) wbar += a.g_weights[gp];
     if (i == imax) wbar += gwm;
+    // suffix_i = sum_{k > i} wbar_k w_k: reverse exclusive scan inside the block + carry from the later blocks
+    const float ww = ok ? wbar * w : 0.f;
+    float incl = ww;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_down_sync(0xffffffffu, incl, d);
+      if (lane + d < 32) incl += o;
+    }
+    const float suffix = suffix_carry + (incl - ww);
+    suffix_carry += __shfl_sync(0xffffffffu, incl, 0);
+    if (!ok) continue;
     const float f = 1.0f - alpha + 1e-7f;
     const float alpha_bar = wbar * Ti - suffix / f;
-    suffix = fmaf(wbar, w, suffix);
     const float raw_bar = (t.raw >= 0.f && t.raw <= 1.f) ? alpha_bar : 0.f;
     const float pe = t.p + 1e-5f;
     float p_bar = raw_bar * t.q / (pe * pe);
@@ -885,16 +927,20 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
       rb1 += a.g_raw_color[gp * 3 + 1];
       rb2 += a.g_raw_color[gp * 3 + 2];
     }
-    float4* out = reinterpret_cast<float4*>(a.adj + gp * 8);
     const float z0 = rb0 * r * (1.0f - r), z1 = rb1 * g * (1.0f - g), z2 = rb2 * b * (1.0f - b);
-    out[0] = make_float4(sdf_bar, nb0, nb1, nb2);
-    out[1] = make_float4(z0, z1, z2, 0.f);
-    sum_sb += sdf_bar;
-    sum_z0 += z0;
-    sum_z1 += z1;
-    sum_z2 += z2;
+    if (live) {
+      float4* out = reinterpret_cast<float4*>(a.adj + gp * 8);
+      out[0] = make_float4(sdf_bar, nb0, nb1, nb2);
+      out[1] = make_float4(z0, z1, z2, 0.f);
+      sum_sb += sdf_bar;
+      sum_z0 += z0;
+      sum_z1 += z1;
+      sum_z2 += z2;
+    }
   }
-  if (live) {
+  __syncwarp();
+  invs_bar = warp_sum(invs_bar);
+  if (live && lane == 0) {
     if (a.g_s_val) invs_bar -= a.g_s_val[ray] / (inv_s * inv_s);
     a.invs_partial[ray] = invs_bar;
   }
@@ -903,7 +949,7 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
     sum_z0 = warp_sum(sum_z0);
     sum_z1 = warp_sum(sum_z1);
     sum_z2 = warp_sum(sum_z2);
-    if ((threadIdx.x & 31) == 0) {
+    if (live && lane == 0) {
       atomicAdd(a.d_sigma_bias, sum_sb);
       atomicAdd(a.d_rgb_bias + 0, sum_z0);
       atomicAdd(a.d_rgb_bias + 1, sum_z1);
@@ -1000,7 +1046,7 @@ int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj
     relax_count_kernel<<<296, 256, 0, st>>>(t);
     OI_CHECK_CUDA(cudaGetLastError());
   }
-  tail_bwd_kernel<<<(t.R + 63) / 64, 64, 0, st>>>(t);
+  tail_bwd_kernel<<<(t.R + 7) / 8, 256, 0, st>>>(t);   // 8 warps per block, one ray per warp
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

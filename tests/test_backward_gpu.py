@@ -193,3 +193,28 @@ def test_tcgen05_matches_ffma_across_chunks_and_instances():
     for (k, _), a, b in zip(_params(r) + [("w", None)], grads["ffma"], grads["tcgen05"]):
         s = float(a.abs().max()) + 1e-30
         assert float((a - b).abs().max()) / s < 2e-3, (k, float((a - b).abs().max()) / s)
+
+
+def test_cfg4_full_patch_backward_tcgen05_vs_ffma():
+    """BASELINE config 4 shape: 128x128 patch, 64 + 64 hierarchical samples (16 384 tiles = 8 slab chunks).  Both
+    backward cores on the same rendered z-values; finite, and in agreement."""
+    meta, inp, _, _ = load_case("cfg4_n64_m64")
+    from oracle import neus_oracle as O
+    c = dict(zip(("rays_o", "rays_d", "near", "far"), (t.cuda() for t in O.synthetic_rays(1, 128, seed=5))))
+    w = inp["w"][:1].cuda()
+    grads, z_vals = {}, None
+    for impl in ("tcgen05", "ffma"):
+        r = _build(meta, impl=impl)
+        named = _params(r)
+        out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0, perturb_overwrite=0, w=w,
+                       z_vals=z_vals, return_z_vals=True)
+        if z_vals is None:
+            z_vals = out["z_vals"].detach()          # the second core renders the same (hierarchically sampled) z
+        img = out["color_fine"] + (1.0 - out["weight_sum"])
+        loss = (img ** 2).mean() + 0.1 * out["gradient_error"]
+        grads[impl] = torch.autograd.grad(loss, [t for _, t in named])
+    torch.cuda.synchronize()
+    for (k, _), a, b in zip(_params(r), grads["ffma"], grads["tcgen05"]):
+        assert torch.isfinite(b).all(), k
+        s = float(a.abs().max()) + 1e-30
+        assert float((a - b).abs().max()) / s < 2e-3, (k, float((a - b).abs().max()) / s)
