@@ -238,9 +238,11 @@ class _RenderFunction(torch.autograd.Function):
                 r._bwd_workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             d.workspace, d.workspace_bytes = r._bwd_workspace.data_ptr(), r._bwd_workspace.numel()
             _lib.check(L.oi_render_backward(C.byref(d), _lib.current_stream_ptr(dev)), "oi_render_backward")
-        film_slots = list(range(D)) + [_lib.OI_MAX_DEPTH]
-        g_gam = G["film_gamma"][:, film_slots]
-        g_bet = G["film_beta"][:, film_slots]
+        # slots 0..D-1 and OI_MAX_DEPTH (slices, not a list index: that would copy an index tensor host->device
+        # and stall the host until the kernels above have finished)
+        last = _lib.OI_MAX_DEPTH
+        g_gam = torch.cat([G["film_gamma"][:, :D], G["film_gamma"][:, last:last + 1]], 1)
+        g_bet = torch.cat([G["film_beta"][:, :D], G["film_beta"][:, last:last + 1]], 1)
         direct = [G["pts_weight%d" % l] for l in range(D)] + [G["pts_bias%d" % l] for l in range(D)] + \
                  [G[k] for k in ("sigma_weight", "sigma_bias", "views_weight", "views_bias", "rgb_weight", "rgb_bias",
                                  "variance")]
