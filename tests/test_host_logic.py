@@ -55,6 +55,49 @@ def test_argument_validation_without_gpu():
     assert L.oi_pack_weights(C.byref(p), None, 0, None) == -2          # W != 128 unsupported
 
 
+def test_backward_and_augment_argument_validation_without_gpu():
+    from object_intrinsics_b200 import _lib
+    L = _lib.lib()
+    n = C.c_size_t(0)
+    b = _lib.OiRenderBwdDesc()
+    assert L.oi_render_backward(C.byref(b), None) == -1                       # n_rays == 0
+    b.n_rays, b.rays_per_instance, b.n_samples_total, b.n_samples, b.depth = 64, 64, 16, 16, 1
+    assert L.oi_render_backward_workspace_bytes(C.byref(b), C.byref(n)) == -2   # depth < 2: OI_ERR_UNSUPPORTED
+    b.depth = 8
+    assert L.oi_render_backward_workspace_bytes(C.byref(b), C.byref(n)) == -1 and b"NULL" in L.oi_last_error()
+    b.n_samples_total = 8                                                      # S < n
+    assert L.oi_render_backward(C.byref(b), None) == -1 and b"n_samples" in L.oi_last_error()
+    a = _lib.OiAugmentGeomDesc()
+    assert L.oi_augment_geom_forward(C.byref(a), None) == -1
+    a.batch, a.channels, a.height, a.width, a.filter_taps = 4, 3, 128, 128, 10
+    assert L.oi_augment_geom_workspace_bytes(C.byref(a), C.byref(n)) == -1 and b"filter_taps" in L.oi_last_error()
+    a.filter_taps = 12
+    assert L.oi_augment_geom_workspace_bytes(C.byref(a), C.byref(n)) == 0
+    # worst-case up-sampled extent (margins <= size - 1 per side) + the backward's resampled gradient
+    assert n.value == 4 * (4 * 3 * (2 * 382) ** 2 + 4 * 3 * (2 * 134) ** 2)
+    assert L.oi_augment_geom_backward(C.byref(a), None) == -1 and b"NULL" in L.oi_last_error()
+    assert L.oi_augment_geom_setup(None, 4, 128, 128, 12, None, None, None) == -1
+    assert L.oi_selftest_wgrad(None, None, 1, 1, 0, 0, 1, 1, None, None, None) == -1
+
+
+def test_grad_mode_renderer_rejects_ray_gradients_and_bad_grad_impl():
+    from object_intrinsics_b200 import fields
+    from object_intrinsics_b200.renderer import NeuSRenderer, film_tables
+    sdf = fields.ShapeNetwork(D=2)
+    col, dev = fields.ColorNetwork(D=2), fields.SingleVarianceNetwork()
+    with pytest.raises(ValueError):
+        NeuSRenderer(None, sdf, dev, col, 8, 0, 0, 1, 0, grad_impl="jax")
+    # the FiLM-table graph that routes dL/dgamma, dL/dbeta to the FiLM linears and to w (pure torch, runs anywhere)
+    w = torch.randn(2, 64, requires_grad=True)
+    gam, bet = film_tables(sdf, col, w)
+    assert gam.shape == (2, 3, 128) and bet.shape == (2, 3, 128)
+    (gam.sum() + bet.sum()).backward()
+    assert w.grad is not None and sdf.pts_linears[1].gamma.weight.grad is not None
+    assert col.views_linears.beta.bias.grad is not None
+    ref = 15.0 * (w.detach() @ sdf.pts_linears[0].gamma.weight.T + sdf.pts_linears[0].gamma.bias) + 30.0
+    assert float((gam[:, 0].detach() - ref).abs().max()) < 1e-4
+
+
 def test_renderer_rejects_cpu_and_unsupported_arguments():
     from object_intrinsics_b200 import fields
     from object_intrinsics_b200.renderer import NeuSRenderer
