@@ -218,3 +218,47 @@ def test_cfg4_full_patch_backward_tcgen05_vs_ffma():
         assert torch.isfinite(b).all(), k
         s = float(a.abs().max()) + 1e-30
         assert float((a - b).abs().max()) / s < 2e-3, (k, float((a - b).abs().max()) / s)
+
+
+def test_backward_under_ddp_single_rank_nccl():
+    """The reference trains under DDP (tu/ddp.py): gradients produced by oi_render_backward must land on the wrapped
+    nn.Parameters through DDP's reducer hooks (NCCL, world_size 1 here; the all-reduce itself is torch's)."""
+    import os
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from object_intrinsics_b200.renderer import NeuSRenderer
+    meta, c, w = _inputs("cfgd_n16_m4_D8", 64)
+    r0 = _build(meta, n_importance=0)
+
+    class Gen(torch.nn.Module):      # the three networks the reference Generator registers (generator.py:51-57)
+        def __init__(self, r):
+            super().__init__()
+            self.sdf_network, self.color_network, self.deviation_network = r.sdf_network, r.color_network, r.deviation_network
+            self.sdf_network.style = torch.nn.Sequential()      # w is given: the style MLP takes no part
+            self.renderer = NeuSRenderer(None, self.sdf_network, self.deviation_network, self.color_network,
+                                         n_samples=meta["n_samples"], n_importance=0, n_outside=0, up_sample_steps=1,
+                                         perturb=0)
+
+        def forward(self, c, w):
+            out = self.renderer.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0,
+                                       perturb_overwrite=0, w=w)
+            return out["color_fine"].sum() + out["weight_sum"].sum() + 10.0 * out["gradient_error"]
+
+    gen = Gen(r0).cuda()
+    gen(c, w).backward()
+    ref = {k: p.grad.clone() for k, p in gen.named_parameters() if p.grad is not None}
+    gen.zero_grad(set_to_none=True)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        ddp = DDP(gen, device_ids=[0])
+        ddp(c, w).backward()
+        torch.cuda.synchronize()
+        got = {k: p.grad for k, p in gen.named_parameters() if p.grad is not None}
+        assert set(got) == set(ref) and len(got) >= 50
+        for k in ref:
+            s = float(ref[k].abs().max()) + 1e-30
+            assert float((got[k] - ref[k]).abs().max()) / s < 1e-4, k   # atomics: not bit-wise reproducible
+    finally:
+        dist.destroy_process_group()
