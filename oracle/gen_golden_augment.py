@@ -26,6 +26,8 @@ CASES = [
     ("blit", dict(xflip=1, rotate90=1, xint=1), 4, 2, 24, 13),
     ("general", dict(scale=1, rotate=1, aniso=1, xfrac=1), 4, 3, 40, 14),
     ("all_geom", dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1), 5, 3, 32, 15),
+    ("nonsquare", dict(xint=1, scale=1, rotate=1, xfrac=1), 3, 2, (24, 40), 16),   # H != W
+    ("single", dict(scale=1, xint=1, xint_max=0.4), 1, 4, 16, 17),                # large integer shifts, B = 1
 ]
 
 
@@ -40,7 +42,8 @@ def main():
     blob = {}
     for name, kw, b, c, s, seed in CASES:
         pipe = A.AugmentPipe(**kw)
-        x = torch.randn(b, c, s, s, generator=torch.Generator().manual_seed(seed))
+        hh, ww = (s, s) if isinstance(s, int) else s
+        x = torch.randn(b, c, hh, ww, generator=torch.Generator().manual_seed(seed))
         torch.manual_seed(seed)
         y = pipe(x)
         blob[f"{name}/x"], blob[f"{name}/y"] = x.numpy(), y.numpy()

@@ -10,7 +10,7 @@ import torch
 from helpers import GOLDEN
 from oracle import augment_oracle as AO
 
-CASES = ["train_rgb", "train_mask", "blit", "general", "all_geom"]
+CASES = ["train_rgb", "train_mask", "blit", "general", "all_geom", "nonsquare", "single"]
 
 
 def load(name):

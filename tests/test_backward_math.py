@@ -53,3 +53,27 @@ def test_manual_backward_matches_autograd(name, cos_anneal):
         scale = float(ga.abs().max()) + 1e-30
         err = float((gm - ga).abs().max()) / scale
         assert err < 1e-9, (k, err, scale)
+
+
+def test_manual_backward_two_instances():
+    """Per-instance FiLM tables: rays of instance b are rows [b R/bs, (b+1) R/bs) (fields.py:55)."""
+    torch.manual_seed(1)
+    meta, P, r, a, w1, z_vals = _setup("cfg1_n16_m0", 24, 1.0)
+    w = torch.cat([w1.detach(), w1.detach() + 0.3 * torch.randn(1, 64, dtype=torch.float64)]).requires_grad_(True)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        out = torch_graph.render_differentiable(r, a["rays_o"], a["rays_d"], a["near"], a["far"], w, 1.0, z_vals=z_vals)
+        keys_adj = ["color_fine", "weight_sum", "gradient_error", "weights"]
+        adj = {k: torch.randn_like(out[k]) for k in keys_adj}
+        loss = sum((adj[k] * out[k]).sum() for k in keys_adj)
+        named = dict(torch_graph.collect_params(r.sdf_network, r.color_network, r.deviation_network, with_style=False))
+        keys = list(named)
+        g_auto = torch.autograd.grad(loss, [named[k] for k in keys] + [w])
+        g_man = B.manual_backward({k: v.detach() for k, v in named.items()}, meta["D"], a["rays_o"], a["rays_d"], z_vals,
+                                  w.detach(), 1.0, meta["n_samples"], adj)
+    finally:
+        torch.set_default_dtype(old)
+    for k, ga in zip(keys + ["w"], g_auto):
+        scale = float(ga.abs().max()) + 1e-30
+        assert float((g_man[k].reshape(ga.shape) - ga).abs().max()) / scale < 1e-9, k
