@@ -103,7 +103,7 @@ __device__ __forceinline__ float4 tf32r4(float a, float b, float c, float d) {
 // Sum over the 32 lanes of a warp (= 32 sample points) of 16 per-lane values (= 16 channels), by recursive halving:
 // after the four exchange steps lane L holds channel 8 b4 + 4 b3 + 2 b2 + b1 (bits of L) summed over 16 lanes; one
 // more exchange completes the sum, and the even lanes add it to dst[channel * stride].  16 shuffles per call.
-__device__ __forceinline__ void colsum16(const float (&v)[16], float* dst, int stride, int lane) {
+__device__ __forceinline__ void colsum16_impl(const float (&v)[16], float* dst, int stride, int lane) {
   float a8[8], a4[4], a2[2];
   {
     const bool up = (lane & 16) != 0;
@@ -135,6 +135,11 @@ __device__ __forceinline__ void colsum16(const float (&v)[16], float* dst, int s
   const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
   if ((lane & 1) == 0) atomicAdd(dst + (size_t)ch * stride, a1);
 }
+
+#define colsum16(v, dst, stride, lane)                  \
+  do {                                                  \
+    if (!skip_cols) colsum16_impl(v, dst, stride, lane); \
+  } while (0)
 
 __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -234,10 +239,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
                                              (size_t)t * kCtaSlabs * kSlabFloats) + m;
     uint32_t af_phase = 0u;
+    // timing experiments only (results invalid): OiRenderBwdDesc.flags bit 3 / bit 4
+    const bool skip_ops = (a.r.flags & 8) != 0, skip_cols = (a.r.flags & 16) != 0;
 #define OI_CTA(slab, quad) scr4[((size_t)(slab) * 32 + (quad)) * 128]
 #define OI_GS(slab, quad) gs4[((size_t)(slab) * 32 + (quad)) * 128]   /* ARG slabs: [quad][128 points] float4 */
 /* operand slabs: K-major SWIZZLE_128B tf32 image [32-point block][channel][32 points], 16-byte chunks XOR (ch & 7) */
-#define OI_OP(slab, j, v) gso[(size_t)(slab) * kSlabFloats + (n0 + (j)) * 32 + ((mc ^ ((j) & 7)) << 2)] = tf32r(v)
+#define OI_OP(slab, j, v)                                                                                  \
+  do {                                                                                                    \
+    if (!skip_ops) gso[(size_t)(slab) * kSlabFloats + (n0 + (j)) * 32 + ((mc ^ ((j) & 7)) << 2)] = tf32r(v); \
+  } while (0)
 #define OI_OP4(slab, j0, a0, a1, a2, a3) \
   do {                                   \
     OI_OP(slab, (j0) + 0, a0);           \
