@@ -11,12 +11,14 @@
 // Contractions over POINTS (weight gradients, per-channel sums) are not done here: every per-point quantity they
 // need is left as an fp32 slab [32 channel-quads][128 points] float4 per tile (oi_wgrad.cuh) and contracted by
 // wgrad_tc_kernel.  Warp roles: 0-7 / 8-15 epilogue of slot 0 / 1, 16 TMA producer, 17 MMA issuer.
-#include <cuda_bf16.h>
-
 #include "oi_internal.cuh"
 #include "oi_render_common.cuh"
 #include "oi_tc.cuh"
 #include "oi_wgrad.cuh"
+
+#ifndef OI_BWD_TIMING_FLAGS
+#define OI_BWD_TIMING_FLAGS 0
+#endif
 
 namespace oi {
 
@@ -65,30 +67,9 @@ struct __align__(1024) BwdTcSmem {
 };
 static_assert(sizeof(BwdTcSmem) <= 227 * 1024, "BwdTcSmem exceeds the 227 KB per-CTA limit");
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ void issue_layer_mmas(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase,
-                                                 uint32_t idesc) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int kb = k >> 2, ks = k & 3;
-    const uint64_t bhi = tc::make_desc_k_sw128(wbase + kb * kSubPanelBytes + ks * 32);
-    const uint64_t blo = tc::make_desc_k_sw128(wbase + 2 * kSubPanelBytes + kb * kSubPanelBytes + ks * 32);
-    tc::mma_ts(acc, a_hi + k * 8, bhi, idesc, k > 0 ? 1u : 0u);
-    tc::mma_ts(acc, a_lo + k * 8, bhi, idesc, 1u);
-    tc::mma_ts(acc, a_hi + k * 8, blo, idesc, 1u);
-  }
-}
-
-__device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+using tc::issue_split_layer_mmas;
+using tc::named_bar_sync;
+using tc::split2_bf16;
 
 // round-to-nearest TF32 (the contraction kernel feeds these values to kind::tf32 MMAs, which ignore the low bits)
 __device__ __forceinline__ float tf32r(float x) {
@@ -96,10 +77,6 @@ __device__ __forceinline__ float tf32r(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float4 tf32r4(float a, float b, float c, float d) {
-  return make_float4(tf32r(a), tf32r(b), tf32r(c), tf32r(d));
-}
-
 // Sum over the 32 lanes of a warp (= 32 sample points) of 16 per-lane values (= 16 channels), by recursive halving:
 // after the four exchange steps lane L holds channel 8 b4 + 4 b3 + 2 b2 + b1 (bits of L) summed over 16 lanes; one
 // more exchange completes the sum, and the even lanes add it to dst[channel * stride].  16 shuffles per call.
@@ -217,7 +194,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             ar_phase[t] ^= 1u;
             tc::fence_after_thread_sync();
             const uint32_t acc = tmem_base + t * 256;
-            issue_layer_mmas(acc, acc + 128, acc + 192, wbase, idesc);
+            issue_split_layer_mmas(acc, acc + 128, acc + 192, wbase, idesc);
             tc::mma_commit(&sm.acc_full[t]);
           }
           tc::mma_commit(&sm.w_empty[stage]);
@@ -239,8 +216,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
                                              (size_t)t * kCtaSlabs * kSlabFloats) + m;
     uint32_t af_phase = 0u;
-    // timing experiments only (results invalid): OiRenderBwdDesc.flags bit 3 / bit 4
+    // timing experiments only (results invalid; build with -DOI_BWD_TIMING_FLAGS=1): OiRenderBwdDesc.flags bit 3 =
+    // skip the operand-slab stores, bit 4 = skip the column-sum butterflies (profiles/r01_summary.md)
+#if OI_BWD_TIMING_FLAGS
     const bool skip_ops = (a.r.flags & 8) != 0, skip_cols = (a.r.flags & 16) != 0;
+#else
+    constexpr bool skip_ops = false, skip_cols = false;
+#endif
 #define OI_CTA(slab, quad) scr4[((size_t)(slab) * 32 + (quad)) * 128]
 #define OI_GS(slab, quad) gs4[((size_t)(slab) * 32 + (quad)) * 128]   /* ARG slabs: [quad][128 points] float4 */
 /* operand slabs: K-major SWIZZLE_128B tf32 image [32-point block][channel][32 points], 16-byte chunks XOR (ch & 7) */
@@ -402,9 +384,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = D - 1; l >= 1; --l) {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][l - 1]) + n0 * 2;
         const float gscale = (l - 1 == 0) ? kInvWScale : 1.0f;   // gamma'_0 is unscaled
-        float4 arn[4];   // one-chunk look-ahead of a_{l-1}, issued before the MMA wait
-#pragma unroll
-        for (int q = 0; q < 4; ++q) arn[q] = OI_GS(kSlabArg + l - 1, Q0 + q);
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -413,18 +392,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
-          float4 arc[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) arc[q] = arn[q];
-          if (c < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) arn[q] = OI_GS(kSlabArg + l - 1, Q0 + (c + 1) * 4 + q);
-          }
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = arc[q];
+            const float4 ar4 = OI_GS(kSlabArg + l - 1, quad);
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
             float gv[4], tv[4];
 #pragma unroll
@@ -552,12 +524,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
       {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][0]) + n0 * 2;
-        float4 arn[4], gn[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          arn[q] = OI_GS(kSlabArg + 0, Q0 + q);
-          gn[q] = OI_CTA(kCtaG + 0, Q0 + q);
-        }
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -566,28 +532,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
-          float4 arc[4], gc[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            arc[q] = arn[q];
-            gc[q] = gn[q];
-          }
-          if (c < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              arn[q] = OI_GS(kSlabArg + 0, Q0 + (c + 1) * 4 + q);
-              gn[q] = OI_CTA(kCtaG + 0, Q0 + (c + 1) * 4 + q);
-            }
-          }
           uint32_t hi[8], lo[8];
           float t0s[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
             float hb[4], cb[4], gb[4];
-            const float4 ar4 = arc[q];
+            const float4 ar4 = OI_GS(kSlabArg + 0, quad);
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            const float4 g14 = gc[q];   // g_1
+            const float4 g14 = OI_CTA(kCtaG + 0, quad);   // g_1
             const float g1[4] = {g14.x, g14.y, g14.z, g14.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -629,12 +582,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
         const float2* fb = fb_inst + l * kW + n0;
         const int gslab = (l < D - 1) ? kCtaG + l : kCtaHB;   // g_{l+1}, or h_bar_D at the top
-        float4 arn[4], gn[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          arn[q] = OI_GS(kSlabArg + l, Q0 + q);
-          gn[q] = OI_CTA(gslab, Q0 + q);
-        }
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -643,29 +590,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
-          float4 arc[4], gc[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            arc[q] = arn[q];
-            gc[q] = gn[q];
-          }
-          if (c < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              arn[q] = OI_GS(kSlabArg + l, Q0 + (c + 1) * 4 + q);
-              gn[q] = OI_CTA(gslab, Q0 + (c + 1) * 4 + q);
-            }
-          }
           uint32_t hi[8], lo[8];
           float dgs[16], dwss[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = arc[q];
+            const float4 ar4 = OI_GS(kSlabArg + l, quad);
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
             float o[4];
             if (l < D - 1) {
-              const float4 g4 = gc[q];   // g_{l+1}
+              const float4 g4 = OI_CTA(gslab, quad);   // g_{l+1}
               const float gn[4] = {g4.x, g4.y, g4.z, g4.w};
               float cb[4];
 #pragma unroll
@@ -679,7 +613,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               OI_OP4(kSlabGB + l + 1, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
             } else {
               // top: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
-              const float4 hb4 = gc[q];
+              const float4 hb4 = OI_CTA(gslab, quad);   // h_bar_D
               const float hb[4] = {hb4.x, hb4.y, hb4.z, hb4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -714,12 +648,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         const float* flf = reinterpret_cast<const float*>(sm.film[t][k]) + n0 * 2;
         const float2* fb = fb_inst + k * kW + n0;
         const float gsc = (k == 0) ? 1.0f : kWScale;
-        float4 arn[4], gn[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          arn[q] = OI_GS(kSlabArg + k, Q0 + q);
-          gn[q] = OI_CTA(kCtaG + k, Q0 + q);
-        }
         OI_WAIT_ACC();
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
@@ -728,27 +656,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
-          float4 arc[4], gc[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            arc[q] = arn[q];
-            gc[q] = gn[q];
-          }
-          if (c < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              arn[q] = OI_GS(kSlabArg + k, Q0 + (c + 1) * 4 + q);
-              gn[q] = OI_CTA(kCtaG + k, Q0 + (c + 1) * 4 + q);
-            }
-          }
           uint32_t hi[8], lo[8];
           float dgs[16], ubs[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = arc[q];
+            const float4 ar4 = OI_GS(kSlabArg + k, quad);
             const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            const float4 cb4 = gc[q];   // c_bar_k
+            const float4 cb4 = OI_CTA(kCtaG + k, quad);   // c_bar_k
             const float cb[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
             float o[4];
 #pragma unroll

@@ -29,7 +29,6 @@ constexpr int kSubPanelBytes = 16384;
 constexpr float kWScale = 256.0f;        // weights are packed as 2^8 * W (see pack_weights_kernel)
 constexpr float kInvWScale = 1.0f / 256.0f;
 constexpr uint32_t kIdesc = tc::make_idesc_f16(128, 128);
-constexpr uint32_t kIdescHalf = tc::make_idesc_f16(128, 64);
 
 struct __align__(1024) TcSmem {
   unsigned char w[kTcStages][kPanelBytes];  // weight panels (192 KB)
@@ -75,36 +74,11 @@ __device__ __forceinline__ void sincos_tc(float x, float* s, float* c) {
 #endif
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
+using tc::named_bar_sync;
 
-// 24 MMAs of one layer of one tile: acc = hi*Whi + lo*Whi + hi*Wlo over K = 128.
+// 24 MMAs of one layer of one tile: acc = hi*Whi + lo*Whi + hi*Wlo over K = 128 (fp16 split operands).
 __device__ __forceinline__ void issue_layer_mmas(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int kb = k >> 2, ks = k & 3;
-    const uint64_t bhi = tc::make_desc_k_sw128(wbase + kb * kSubPanelBytes + ks * 32);
-    const uint64_t blo = tc::make_desc_k_sw128(wbase + 2 * kSubPanelBytes + kb * kSubPanelBytes + ks * 32);
-    tc::mma_ts(acc, a_hi + k * 8, bhi, kIdesc, k > 0 ? 1u : 0u);
-    tc::mma_ts(acc, a_lo + k * 8, bhi, kIdesc, 1u);
-    tc::mma_ts(acc, a_hi + k * 8, blo, kIdesc, 1u);
-  }
-}
-
-// One column half (N = 64 output channels) of a layer: the epilogue can start on channels 0..63 while the
-// tensor core still works on channels 64..127.
-__device__ __forceinline__ void issue_layer_mmas_half(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase, int h) {
-  const uint32_t row_off = (uint32_t)h * 64u * 128u;   // 64 rows of 128 bytes inside each 16 KB sub-panel
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int kb = k >> 2, ks = k & 3;
-    const uint64_t bhi = tc::make_desc_k_sw128(wbase + kb * kSubPanelBytes + row_off + ks * 32);
-    const uint64_t blo = tc::make_desc_k_sw128(wbase + 2 * kSubPanelBytes + kb * kSubPanelBytes + row_off + ks * 32);
-    tc::mma_ts(acc + h * 64, a_hi + k * 8, bhi, kIdescHalf, k > 0 ? 1u : 0u);
-    tc::mma_ts(acc + h * 64, a_lo + k * 8, bhi, kIdescHalf, 1u);
-    tc::mma_ts(acc + h * 64, a_hi + k * 8, blo, kIdescHalf, 1u);
-  }
+  tc::issue_split_layer_mmas(acc, a_hi, a_lo, wbase, kIdesc);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKArgs a) {

@@ -1,5 +1,6 @@
 // tcgen05 / TMEM building blocks (sm_100a inline PTX) used by the tensor-core render core.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "oi_internal.cuh"
@@ -170,6 +171,36 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
   const __half2 l = __floats2half2_rn(d.x, d.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// fp32 pair -> bf16 {hi, lo} split: v = hi + lo + O(2^-17 |v|), full fp32 exponent range (adjoint operands)
+__device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// The 24 MMAs of one 128x128x128 layer of one tile with 2-term split operands: acc = hi*Whi + lo*Whi + hi*Wlo.
+// A operand {hi, lo} in TMEM (64 packed columns each), B = one 64 KB panel {hi: 2 k-blocks | lo: 2 k-blocks} of
+// 16 KB K-major SWIZZLE_128B images at shared address `wbase`; `idesc` selects fp16 or bf16 inputs.
+__device__ __forceinline__ void issue_split_layer_mmas(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase,
+                                                       uint32_t idesc) {
+  constexpr uint32_t kSub = 16384;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t kb = k >> 2, ks = k & 3;
+    const uint64_t bhi = make_desc_k_sw128(wbase + kb * kSub + ks * 32);
+    const uint64_t blo = make_desc_k_sw128(wbase + 2 * kSub + kb * kSub + ks * 32);
+    mma_ts(acc, a_hi + k * 8, bhi, idesc, k > 0 ? 1u : 0u);
+    mma_ts(acc, a_lo + k * 8, bhi, idesc, 1u);
+    mma_ts(acc, a_hi + k * 8, blo, idesc, 1u);
+  }
 }
 
 }  // namespace tc

@@ -55,7 +55,8 @@ for bs in (1, 4):
         ms = timeit(lambda: torch_graph.render_differentiable(r, ro, rd, near, far, w, 1.0), n=5, warm=2)
     print(f"torch eager (cuBLAS fp32 + elementwise), cfg2 bs={bs}: {ms:8.3f} ms  {ro.shape[0]/ms*1e3/1e6:7.3f} M rays/s", flush=True)
     rows.append((f"torch eager cfg2 bs={bs}", ro.shape[0], 64, ms, ro.shape[0] / ms * 1e3))
-# grad-mode step (forward + backward through torch_graph), cfg2 bs=1
+# grad-mode step (forward + backward through oi_render_backward), cfg2 bs=1; see tools_bench_backward.py for the
+# comparison with the torch formulation
 ro, rd, near, far = [t.cuda() for t in O.synthetic_rays(1, 64, seed=1)]
 z = torch.randn(1, 64, device="cuda")
 r = NeuSRenderer(None, sdf, dev, col, n_samples=64, n_importance=0, n_outside=0, up_sample_steps=1, perturb=0)
@@ -64,6 +65,6 @@ def gstep():
     out = r.render(ro, rd, near, far, cos_anneal_ratio=1.0, perturb_overwrite=0, z=z, w=w)
     (out["color_fine"].sum() + out["weight_sum"].sum() + 10 * out["gradient_error"]).backward()
 ms = timeit(gstep, n=5, warm=2)
-print(f"grad-mode render + backward (torch_graph), cfg2 bs=1: {ms:8.3f} ms", flush=True)
+print(f"grad-mode render + backward (oi_render_backward), cfg2 bs=1: {ms:8.3f} ms", flush=True)
 rows.append(("grad-mode fwd+bwd cfg2 bs=1", 4096, 64, ms, 4096 / ms * 1e3))
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "bench_extra.json"), "w"), indent=1)
