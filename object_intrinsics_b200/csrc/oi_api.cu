@@ -255,7 +255,7 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
 
 namespace {
 struct BwdWorkspace {
-  size_t film, film_b, d_film, adj, invs_partial, relax_count, ticket, scratch, slabs, aux, total;
+  size_t film, d_film, adj, invs_partial, relax_count, ticket, scratch, slabs, aux, total;
   int n_ctas, n_inst, tiles_per_inst, n_tiles, chunk_tiles;
   bool tc;
 };
@@ -302,7 +302,6 @@ void plan_bwd(const OiRenderBwdDesc* d, BwdWorkspace* w) {
     return o;
   };
   w->film = take((size_t)w->n_inst * kFilm * 4 * kW * 4);
-  w->film_b = take((size_t)w->n_inst * kFilm * 2 * kW * 4);
   w->d_film = take((size_t)w->n_inst * kFilm * 2 * kW * 4);
   w->adj = take((size_t)R * S * 8 * 4);
   w->invs_partial = take((size_t)R * 4);
@@ -375,7 +374,7 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
   if (!w.tc)
     return launch_render_bwd_ffma(*d, a, adj, invs_partial, d_film, reinterpret_cast<float*>(ws + w.scratch), w.n_ctas,
                                   st);
-  return launch_render_bwd_tc(*d, a, adj, invs_partial, reinterpret_cast<float*>(ws + w.film_b), d_film,
+  return launch_render_bwd_tc(*d, a, adj, invs_partial, d_film,
                               reinterpret_cast<float*>(ws + w.scratch), reinterpret_cast<float*>(ws + w.slabs),
                               reinterpret_cast<float*>(ws + w.aux), w.chunk_tiles, w.n_ctas, st);
 }

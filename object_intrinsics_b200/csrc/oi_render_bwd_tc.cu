@@ -44,7 +44,6 @@ constexpr int kCtaSlabs = 9;
 struct BwdTcArgs {
   RenderKArgs r;
   const float* adj;        // [N][8]
-  const float2* film_b;    // [n_inst][9][128] (beta, 1/gamma)
   float* scratch;
   size_t scratch_stride;   // floats per CTA
   float* slabs;            // [tiles of this launch][kSlabsPerTile][32][128] float4
@@ -262,7 +261,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       const int mc = (m & 31) >> 2;
       // aux operand (N = 16, rows 0..3 used): [32-point block][4 rows][32 points], same swizzle
       float* auxo = a.aux + (size_t)lt * 512 + (m >> 5) * 128 + (m & 3);
-      const float2* fb_inst = a.film_b + (size_t)inst * kFilm * kW;
       float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][dgamma | db][128]
       {
         const float2* src = reinterpret_cast<const float2*>(a.r.film_tc) + (size_t)inst * kFilm * kW;
@@ -447,7 +445,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       float nc0 = 0.f, nc1 = 0.f, nc2 = 0.f;   // W_cg^T u_bar_c, this thread's channels
       {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][OI_MAX_DEPTH]) + n0 * 2;
-        const float2* fb = fb_inst + OI_MAX_DEPTH * kW + n0;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t hi[8], lo[8];
@@ -472,8 +469,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               const float4 rw = sm.rgbw[n0 + j];
               const float hb = fmaf(rw.x, zb0, fmaf(rw.y, zb1, rw.z * zb2));
               const float ab = hb * cs;
-              const float2 bg = __ldg(fb + j);                 // (beta, 1/gamma)
-              dg[e] = ab * (ar[e] - bg.x) * bg.y;              // a_bar * u_c
+              dg[e] = ab * ar[e];                              // a_bar * a_c  (see finalize_bwd_tc_kernel)
               dgs[q * 4 + e] = dg[e];
               ub_[e] = ab * (gp * kWScale);                    // u_bar_c = a_bar * gamma
               nc0 = fmaf(hd.y * kInvWScale, ub_[e], nc0);
@@ -488,7 +484,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           tc::tmem_st8(a_lo + c * 8, lo);
           if (c == 3) OI_A_READY();   // the tensor core starts on W_cf^T u_bar_c while the column sums are reduced
           const int nc = n0 + c * 16;
-          colsum16(dgs, dfilm + (size_t)OI_MAX_DEPTH * 2 * kW + nc, 1, lane);          // d gamma_c
+          colsum16(dgs, dfilm + (size_t)OI_MAX_DEPTH * 2 * kW + nc, 1, lane);          // V_c = sum a_bar a
           {
             float tmp[16];
 #pragma unroll
@@ -580,7 +576,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // ---------------- backward of the reverse sweep, l = 1..D-1: t_bar_l = W_l g_bar_l ----------------
       for (int l = 1; l < D; ++l) {
         const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
-        const float2* fb = fb_inst + l * kW + n0;
         const int gslab = (l < D - 1) ? kCtaG + l : kCtaHB;   // g_{l+1}, or h_bar_D at the top
         OI_WAIT_ACC();
         uint32_t ub[2][16];
@@ -624,8 +619,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
                 dwss[q * 4 + e] = fmaf(sdf_bar, sn, tb * gam * cs);   // d w_s = sdf_bar h_D + t_bar_{D-1} c_{D-1}
                 const float cbar = tb * (sm.head[n0 + j].x * kInvWScale);
                 const float ab = hb[e] * cs - cbar * gam * sn;
-                const float2 bg = __ldg(fb + j);
-                dgs[q * 4 + e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cbar * cs);
+                dgs[q * 4 + e] = fmaf(ab, ar[e], gam * (cbar * cs));
                 o[e] = ab * gam;   // u_bar_{D-1}
               }
               OI_OP4(kSlabUB + l, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
@@ -638,7 +632,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           if (c == 3) OI_A_READY();
           if (l == D - 1) {
             colsum16(dwss, a.g.sigma_weight + n0 + c * 16, 1, lane);
-            colsum16(dgs, dfilm + (size_t)l * 2 * kW + n0 + c * 16, 1, lane);   // d gamma_{D-1}
+            colsum16(dgs, dfilm + (size_t)l * 2 * kW + n0 + c * 16, 1, lane);   // V_{D-1}
           }
         }
       }
@@ -646,7 +640,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = D - 1; l >= 1; --l) {
         const int k = l - 1;
         const float* flf = reinterpret_cast<const float*>(sm.film[t][k]) + n0 * 2;
-        const float2* fb = fb_inst + k * kW + n0;
         const float gsc = (k == 0) ? 1.0f : kWScale;
         OI_WAIT_ACC();
         uint32_t ub[2][16];
@@ -672,8 +665,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               const float gam = flf[(j >> 1) * 4 + (j & 1)] * gsc;
               const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
               const float ab = __uint_as_float(u[q * 4 + e]) * cs - cb[e] * gam * sn;
-              const float2 bg = __ldg(fb + j);
-              dgs[q * 4 + e] = fmaf(ab, (ar[e] - bg.x) * bg.y, cb[e] * cs);
+              dgs[q * 4 + e] = fmaf(ab, ar[e], gam * (cb[e] * cs));
               o[e] = ab * gam;   // u_bar_k
               ubs[q * 4 + e] = o[e];
             }
@@ -689,7 +681,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             if (c == 3) OI_A_READY();
           }
           const int nc = n0 + c * 16;
-          colsum16(dgs, dfilm + (size_t)k * 2 * kW + nc, 1, lane);   // d gamma_k
+          colsum16(dgs, dfilm + (size_t)k * 2 * kW + nc, 1, lane);   // V_k = sum a_bar a + gamma c_bar cos a
           if (k == 0) {
             colsum16(ubs, dfilm + kW + nc, 1, lane);                  // d b_0 = sum u_bar_0
             float* dst = a.g.pts_weight[0] + (size_t)nc * 3;          // dW_0 += u_bar_0 (x) x
@@ -721,17 +713,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
   if (warp == kProducerWarp) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// (beta, 1/gamma) per instance / FiLM layer / channel, from the (gamma, beta) table of film_kernel
-__global__ void film_b_kernel(const float* __restrict__ film, float2* __restrict__ film_b, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [inst][9][128]
-  if (i >= n) return;
-  const int ch = i % kW, il = i / kW;
-  const float g = film[(size_t)il * 2 * kW + ch], b = film[(size_t)il * 2 * kW + kW + ch];
-  film_b[i] = make_float2(b, 1.0f / g);
-}
-
-// TC variant of the finalize step: the (dgamma, db) table -> dbeta = db / gamma per instance, db summed over
-// instances, variance.
+// TC variant of the finalize step.  The sweep kernel reduces V = sum_m a_bar a + gamma c_bar cos a and the
+// contraction kernel db = sum_m u_bar = gamma sum_m a_bar per instance; with a = gamma u + beta:
+//   dL/dbeta = db / gamma,   dL/dgamma = sum_m a_bar u + c_bar cos a = (V - beta db / gamma) / gamma,
+// db is summed over instances into the bias gradient; plus the variance.
 __global__ void finalize_bwd_tc_kernel(int D, int n_inst, int R, const float* __restrict__ film,
                                        const float* __restrict__ d_film, const float* __restrict__ invs_partial,
                                        const float* __restrict__ blob, OiNetGrads g) {
@@ -742,10 +727,12 @@ __global__ void finalize_bwd_tc_kernel(int D, int n_inst, int R, const float* __
     float s = 0.f;
     for (int i = 0; i < n_inst; ++i) {
       const size_t o = ((size_t)i * kFilm + slot) * 2 * kW;
-      const float db = d_film[o + kW + n];
+      const float db = d_film[o + kW + n], V = d_film[o + n];
+      const float gam = film[o + n], bet = film[o + kW + n];
+      const float dbeta = db / gam;
       s += db;
-      g.film_gamma[((size_t)i * kFilm + slot) * kW + n] += d_film[o + n];
-      g.film_beta[((size_t)i * kFilm + slot) * kW + n] += db / film[o + n];
+      g.film_gamma[((size_t)i * kFilm + slot) * kW + n] += (V - bet * dbeta) / gam;
+      g.film_beta[((size_t)i * kFilm + slot) * kW + n] += dbeta;
     }
     float* dst = (l < D) ? g.pts_bias[l] : g.views_bias;
     dst[n] += s;
@@ -781,14 +768,9 @@ size_t render_bwd_tc_slab_floats_per_tile() { return (size_t)kSlabsPerTile * kSl
 
 // Runs the two tensor-core kernels over tiles [0, n_tiles) in chunks of at most `chunk_tiles`.
 int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
-                         float* film_b, float* d_film, float* scratch, float* slabs, float* aux, int chunk_tiles,
+                         float* d_film, float* scratch, float* slabs, float* aux, int chunk_tiles,
                          int n_ctas, cudaStream_t st) {
   const int n_inst = geo.n_inst, D = geo.D;
-  {
-    const int n = n_inst * kFilm * kW;
-    film_b_kernel<<<(n + 255) / 256, 256, 0, st>>>(geo.film, reinterpret_cast<float2*>(film_b), n);
-    OI_CHECK_CUDA(cudaGetLastError());
-  }
   OI_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(BwdTcSmem)));
   int sms = 148, dev = 0;
@@ -801,7 +783,6 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     BwdTcArgs a;
     a.r = geo;
     a.adj = adj;
-    a.film_b = reinterpret_cast<const float2*>(film_b);
     a.scratch = scratch;
     a.scratch_stride = render_bwd_tc_scratch_floats();
     a.slabs = slabs;
