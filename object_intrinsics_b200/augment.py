@@ -26,7 +26,7 @@ SYM6 = [0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.04
         0.787641141030194, 0.3379294217276218, -0.07263752278646252, -0.021060292512300564, 0.04472490177066578,
         0.0017677118642428036, -0.007800708325034148]   # augment.py:24 wavelets['sym6']
 
-_WS = {}
+_WS = {}    # one scratch buffer per device, reused by every call (calls on one stream, as in the reference's trainer)
 
 
 def _workspace(dev, nbytes):
