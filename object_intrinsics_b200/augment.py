@@ -26,6 +26,31 @@ SYM6 = [0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.04
         0.787641141030194, 0.3379294217276218, -0.07263752278646252, -0.021060292512300564, 0.04472490177066578,
         0.0017677118642428036, -0.007800708325034148]   # augment.py:24 wavelets['sym6']
 
+SYM2 = [-0.12940952255092145, 0.22414386804185735, 0.836516303737469, 0.48296291314469025]   # wavelets['sym2']
+
+
+def image_filter_bank(lowpass=SYM2, bands=4):
+    """The `Hz_fbank` buffer of the reference pipe (augment.py:169-179): row i is the zero-phase band-pass of
+    octave i built from the sym2 low-pass H(z).  With L = H(z)H(1/z)/2 and B = H(-z)H(-1/z)/2, every step
+    stretches the bank by 2 (zero stuffing), smooths it with L and drops B into the centre of the next row.
+    The image-space filtering that consumes it is disabled in the reference's configs (and raises here); the
+    buffer is registered only so that `state_dict()` keys / shapes match the reference's checkpoints."""
+    import numpy as np
+    h = np.asarray(lowpass, dtype=np.float64)
+    g = h * np.where(np.arange(h.size) % 2 == 0, 1.0, -1.0)
+    low2 = np.convolve(h, h[::-1]) * 0.5
+    high2 = np.convolve(g, g[::-1]) * 0.5
+    bank = np.zeros((bands, 1))
+    bank[0, 0] = 1.0
+    for i in range(1, bands):
+        stretched = np.zeros((bands, 2 * bank.shape[1] - 1))
+        stretched[:, ::2] = bank
+        bank = np.stack([np.convolve(row, low2) for row in stretched])
+        c0 = (bank.shape[1] - high2.size) // 2
+        bank[i, c0:c0 + high2.size] += high2
+    return torch.as_tensor(bank, dtype=torch.float32)
+
+
 _WS = {}    # one scratch buffer per device, reused by every call (calls on one stream, as in the reference's trainer)
 
 
@@ -170,6 +195,7 @@ class AugmentPipe(torch.nn.Module):
         f = torch.tensor(SYM6, dtype=torch.float32)
         self.register_buffer("Hz_geom", f / f.sum())          # upfirdn2d.setup_filter(wavelets['sym6']), augment.py:116
         self._taps = tuple(float(v) for v in (f / f.sum()))
+        self.register_buffer("Hz_fbank", image_filter_bank())  # augment.py:179 (unused: imgfilter is disabled)
 
     def sample_inverse_transform(self, batch, width, height, device):
         """G_inv [B,3,3] (pixel_out -> pixel_in), random draws in the reference's order (augment.py:196-264)."""

@@ -497,20 +497,23 @@ int oi_upfirdn2d(const OiUpfirdnDesc* d, void* stream) {
 
 int oi_bias_act(const OiBiasActDesc* d, void* stream) {
   OI_CHECK_ARG(d != nullptr, "desc is NULL");
-  OI_CHECK_ARG(d->x && d->y, "x and y must be non-NULL");
   OI_CHECK_ARG(d->size_x >= 0, "size_x must be non-negative");
   OI_CHECK_ARG(d->grad >= 0 && d->grad <= 2, "grad must be 0, 1 or 2");
+  OI_CHECK_ARG(d->act >= 1 && d->act <= 9, "act must be in [1, 9] (got %d)", d->act);
+  if (d->size_x == 0) return OI_OK;   // empty tensors are legal (their data_ptr() is NULL), as in the reference op
+  OI_CHECK_ARG(d->x && d->y, "x and y must be non-NULL");
   OI_CHECK_ARG(d->b == nullptr || (d->size_b > 0 && d->step_b > 0), "bias given but size_b/step_b invalid");
-  if (d->size_x == 0) return OI_OK;
   return launch_bias_act(*d, static_cast<cudaStream_t>(stream));
 }
 
 int oi_fused_bias_act(const OiFusedBiasActDesc* d, void* stream) {
   OI_CHECK_ARG(d != nullptr, "desc is NULL");
-  OI_CHECK_ARG(d->x && d->y, "x and y must be non-NULL");
   OI_CHECK_ARG(d->size_x >= 0, "size_x must be non-negative");
+  OI_CHECK_ARG(d->act >= 1 && d->grad >= 0 && d->grad <= 2, "act must be >= 1 and grad in 0..2 (got %d, %d)", d->act,
+               d->grad);
+  if (d->size_x == 0) return OI_OK;   // empty tensors are legal (their data_ptr() is NULL)
+  OI_CHECK_ARG(d->x && d->y, "x and y must be non-NULL");
   OI_CHECK_ARG(d->bias == nullptr || (d->size_b > 0 && d->step_b > 0), "bias given but size_b/step_b invalid");
-  if (d->size_x == 0) return OI_OK;
   return launch_fused_bias_act(*d, static_cast<cudaStream_t>(stream));
 }
 

@@ -92,6 +92,14 @@ class StyleMLP(nn.Sequential):
             return super().forward(z)
         import ctypes as C
         from . import _lib
+        # the one-kernel path is written for style_dim = 64 square layers of contiguous fp32 tensors on z's device
+        # (the reference's ShapeNetwork); anything else (e.g. StyleSDF's default 256) takes the per-layer path
+        ok = z.dim() == 2 and z.shape[-1] == _lib.OI_STYLE_DIM and all(
+            tuple(l.weight.shape) == (_lib.OI_STYLE_DIM, _lib.OI_STYLE_DIM) and l.weight.is_contiguous() and
+            l.bias.is_contiguous() and l.weight.dtype == torch.float32 and l.weight.device == z.device
+            for l in self)
+        if not ok:
+            return super().forward(z)
         p = _lib.OiNetParams()
         p.depth, p.width, p.style_dim = 1, _lib.OI_WIDTH, z.shape[-1]
         for i, layer in enumerate(self):

@@ -76,10 +76,14 @@ def render_maps(generator, bs, render_out, rays_info, prior_info, return_raw):
                                                   "color_fine")}
     d = _lib.OiRenderMapsDesc()
     d.n_rays, d.rays_per_instance, d.n_samples = R, R // bs, S
-    d.shininess = float(base.shininess)
-    amb, dif, spec = base.ambient_color.detach(), base.diffuse_color.detach(), base.specular_color.detach()
+    # ONE device->host read for the ten light scalars (ten float(tensor[i]) calls would be ten blocking syncs)
+    lp = torch.cat([base.ambient_color.detach().reshape(3).float(), base.diffuse_color.detach().reshape(3).float(),
+                    base.specular_color.detach().reshape(3).float(),
+                    torch.as_tensor(base.shininess, dtype=torch.float32, device=base.ambient_color.device).reshape(1)
+                    ]).tolist()
+    d.shininess = lp[9]
     for i in range(3):
-        d.ambient_color[i], d.diffuse_color[i], d.specular_color[i] = float(amb[i]), float(dif[i]), float(spec[i])
+        d.ambient_color[i], d.diffuse_color[i], d.specular_color[i] = lp[i], lp[3 + i], lp[6 + i]
     for k, t in ins.items():
         setattr(d, k, t.data_ptr())
     d.rays_o, d.light_dir, d.bg_color = rays_o.data_ptr(), light_dir.data_ptr(), bg_color.data_ptr()

@@ -114,10 +114,16 @@ class PackedWeights:
         self.blob: Optional[torch.Tensor] = None
         self.depth = 0
         self.repacks = 0
+        self.always = os.environ.get("OI_REPACK_ALWAYS", "0") == "1"   # repack on every call (7.5 us kernel)
 
-    def get(self, named_list):
-        key = tuple((t.data_ptr(), t._version) for _, t in named_list)
-        if key != self.key:
+    def invalidate(self):
+        """Forces a repack on the next call.  Needed after writes that bypass the autograd version counter:
+        `p.data.copy_()`, `p.data.mul_()`, ... (they do not bump `p._version`, which keys the cache)."""
+        self.key = None
+
+    def get(self, named_list, extra=()):
+        key = tuple((t.data_ptr(), t._version) for _, t in named_list) + tuple(extra)
+        if key != self.key or self.always:
             named = {k: t.detach() for k, t in named_list}
             p = fill_net_params(named)
             L = _lib.lib()
@@ -168,6 +174,7 @@ class _RenderFunction(torch.autograd.Function):
         ctx.depth = renderer._packed.depth
         ctx.n_film = gam.shape[1]
         ctx.direct_shapes = [t.shape for t in direct]
+        ctx.set_materialize_grads(False)   # unused outputs arrive as None -> NULL adjoint pointers in the C-ABI
         f32c = lambda t: t.detach().to(torch.float32).contiguous()
         ctx.save_for_backward(f32c(rays_o), f32c(rays_d), out["z_vals"], f32c(w), out["sdf"], out["gradients"],
                               out["raw_color"])
@@ -287,6 +294,16 @@ class NeuSRenderer:
         self.flags = int(os.environ.get("OI_RENDER_FLAGS", "1"))   # OiRenderDesc.flags: bit 0 = L2 discard of dead scratch
         self.last_launches = 0
         self.core_events = None   # optional (torch.cuda.Event, torch.cuda.Event) recorded around the core kernel
+        # the packed blob is keyed on (data_ptr, _version); load_state_dict goes through copy_ (bumps _version) but
+        # hooks are cheap insurance against loaders that write through `.data`
+        for mod in (sdf_network, color_network, deviation_network):
+            if hasattr(mod, "register_load_state_dict_post_hook"):
+                mod.register_load_state_dict_post_hook(lambda *_a, _p=self._packed: _p.invalidate())
+
+    def invalidate(self):
+        """Drop the packed-weight cache.  Call after modifying a parameter through `.data` (EMA copies, manual
+        clipping, custom initialisers): such writes do not change `param._version`, which keys the cache."""
+        self._packed.invalidate()
 
     # -------------------------------------------------------------------------------------------
     def _linspaces(self, device):
@@ -299,9 +316,14 @@ class NeuSRenderer:
             self._lin[key] = (lin_c, lin_f)
         return self._lin[key]
 
+    def _mode_key(self):
+        # a train()/eval() toggle also forces a repack (EMA swaps and test-time copies usually sit on that boundary)
+        return tuple(bool(getattr(m, "training", False)) for m in (self.sdf_network, self.color_network,
+                                                                   self.deviation_network))
+
     def packed_weights(self):
         return self._packed.get(collect_params(self.sdf_network, self.color_network, self.deviation_network,
-                                               with_style=False))
+                                               with_style=False), self._mode_key())
 
     # -------------------------------------------------------------------------------------------
     def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0,
@@ -379,7 +401,7 @@ class NeuSRenderer:
         S = n + m
         if z_vals is not None and tuple(z_vals.shape) != (R, S):
             raise ValueError(f"z_vals must have shape {(R, S)}")
-        blob = self._packed.get(params)
+        blob = self._packed.get(params, self._mode_key())
         lin_c, lin_f = self._linspaces(dev)
 
         out = {}

@@ -49,6 +49,9 @@ def main():
         blob[f"{name}/x"], blob[f"{name}/y"] = x.numpy(), y.numpy()
         blob[f"{name}/meta"] = np.array(json.dumps({"kwargs": kw, "seed": seed}))
         print(name, tuple(y.shape), float(y.abs().mean()))
+    ref_sd = A.AugmentPipe(scale=1, xint=1).state_dict()       # buffers of the reference pipe (augment.py:123,167,179)
+    for k, v in ref_sd.items():
+        blob[f"state_dict/{k}"] = v.numpy()
     np.savez_compressed(os.path.join(GOLDEN, "augment_golden.npz"), **blob)
 
 

@@ -158,3 +158,24 @@ def test_gloo_world_size_2_sharding_and_aggregation():
     assert res[0][2] == 1234 and res[1][2] == 1235
     for _, _, _, thr, total, tmax in res:                        # every rank sees the same aggregate
         assert total == 5 * 4096.0 and tmax == 0.8 and abs(thr - total / 0.8) < 1e-9
+
+
+def test_augment_pipe_state_dict_matches_reference_checkpoints():
+    """The reference loads discriminator checkpoints with strict=True (src/utils/checkpoint.py:109-130); the pipe is
+    the submodule `aug`, so its buffers must be exactly the reference's: p, Hz_geom, Hz_fbank (augment.py:123,167,179).
+    Fixture: state_dict of the unmodified reference AugmentPipe (oracle/gen_golden_augment.py)."""
+    import numpy as np
+    from helpers import GOLDEN
+    from object_intrinsics_b200.augment import AugmentPipe
+    with np.load(os.path.join(GOLDEN, "augment_golden.npz")) as f:
+        ref_sd = {k.split("/", 1)[1]: torch.from_numpy(f[k]) for k in f.files if k.startswith("state_dict/")}
+    pipe = AugmentPipe(scale=1, xint=1)
+    sd = pipe.state_dict()
+    assert set(sd) == {"p", "Hz_geom", "Hz_fbank"} == set(ref_sd)
+    for k in sd:
+        assert sd[k].shape == ref_sd[k].shape and sd[k].dtype == ref_sd[k].dtype, k
+        assert float((sd[k] - ref_sd[k]).abs().max()) <= 1e-7, k
+    ref_sd["p"] = torch.tensor(0.37)                   # an ADA-adjusted probability survives the round trip
+    pipe.load_state_dict(ref_sd, strict=True)
+    assert float(pipe.p) == pytest.approx(0.37)
+    AugmentPipe().load_state_dict(pipe.state_dict(), strict=True)
