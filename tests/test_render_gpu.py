@@ -110,10 +110,17 @@ def test_headline_config_full_size_properties_and_oracle(impl):
     assert linf(out["pts"].norm(dim=-1), out["pts_norm"]) < 2e-6
     assert ((out["pts_norm"] < 1.0).float() - out["inside_sphere"]).abs().sum() <= 2
     assert 0.1 < float(out["weight_sum"].mean()) < 0.95      # the r=0.5 sphere covers ~20% of the +-5 deg patch
-    ref = O.render(P, ro, rd, near, far, w=w, n_samples=64, n_importance=0, cos_anneal_ratio=1.0)
+    # the fp64 rule of the fixtures at FULL size: fp64 and fp32 oracle generated on the fly (a few seconds of CPU)
+    ref32 = O.render(P, ro, rd, near, far, w=w, n_samples=64, n_importance=0, cos_anneal_ratio=1.0)
+    P64 = load_params(meta["params"], torch.float64)
+    ref64 = O.render(P64, ro.double(), rd.double(), near.double(), far.double(), w=w.double(), n_samples=64,
+                     n_importance=0, cos_anneal_ratio=1.0)
     for k in OUT_KEYS:
-        tol = 3e-4 if k == "gradients" else 1e-4
-        assert linf(out[k], ref[k]) <= tol, (k, linf(out[k], ref[k]))
+        if k == "inside_sphere":   # an indicator: a point within rounding of the unit sphere may flip
+            assert int((out[k].double() - ref64[k]).abs().sum()) <= 2
+            continue
+        err, tol = linf(out[k], ref64[k]), _tol(k, ref32, ref64)
+        assert err <= tol, f"headline/{k}: Linf {err:.3e} > tol {tol:.3e}"
 
 
 @pytest.mark.parametrize("impl", IMPLS)
