@@ -2,12 +2,25 @@
 """Headline benchmark: rendered rays/s of the fused SDF renderer (BASELINE.json `metric`).
 
     python bench.py --gpus 1 --steps 20 --warmup 5            # our arm, N=1
-    torchrun --nproc-per-node N ... bench.py --gpus N ...     # our arm, N ranks (one per GPU, no data-path collective)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # our arm, N ranks (one per GPU)
     python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (oracle port) on host cores
 
 A step = one `NeuSRenderer.render` forward over one batch of synthetic rays of BASELINE config 2:
 64x64-ray patch x 64 samples/ray, D=8, W=128 FiLM-SIREN SDF + colour MLP (sphere_init SDF weights from the
 committed fixture), `bs` object instances per GPU (R = bs * 4096 rays per step).  Prints ONE JSON line.
+
+Legs of the repo arm (all in the one line):
+  value / ms_per_step   K forward steps, inputs resident in HBM, CUDA events, max over ranks        [headline bs]
+  bs1                   the same at 1 instance per GPU (the 64x64-patch unit of the metric)
+  e2e                   host (pinned) rays in, rendered patch + mask out, copies inside the timed region
+  roofline              core kernel timed live by CUDA events recorded inside the C-ABI call
+  grad_step             rank 0: grad-mode render + loss + oi_render_backward of 1 instance
+  grad_step_ddp         ALL ranks: the same step through DistributedDataParallel (scripts/train.py:157-158): one
+                        grad render + backward per rank, gradient all-reduce over NCCL/NVLink inside backward();
+                        rank 0 checks that .grad equals the mean of the per-rank gradients
+  train_step            rank 0: a training-shaped composition (gan_pose_trainer.py:77-101), see train_step_leg()
+  cpu_baseline          rank 0, N=1: the oracle port on the host cores (bounded sample)
+The repo arm imports nothing from oracle/ except inside cpu_baseline_leg() / run_reference_arm().
 """
 import argparse
 import json
@@ -20,7 +33,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import bench_inputs as BI  # noqa: E402
 
 PATCH, N_SAMPLES, N_IMPORTANCE, DEPTH, WIDTH = 64, 64, 0, 8, 128
 FLOP_PER_POINT = 494848          # fwd 115200 + reverse 115072 + colour 17152 MAC, x2
@@ -75,17 +89,26 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(bs, seed):
-    from helpers import load_params
-    from oracle import neus_oracle as O  # input generator only (synthetic_rays); not on the timed path
-    P = load_params("params_D8.npz")
-    ro, rd, near, far = O.synthetic_rays(bs, PATCH, seed=seed)
-    z = torch.randn(bs, 64, generator=torch.Generator().manual_seed(seed))
-    return P, ro, rd, near, far, z
+    P = BI.load_flat_params("params_D8.npz")
+    ro, rd, near, far = BI.synthetic_rays(bs, PATCH, seed=seed)
+    return P, ro, rd, near, far, BI.latent(bs, seed)
 
 
+def workload_config(bs, n_gpus):
+    return {"workload": f"cfg2: 64x64-ray patch x 64 samples/ray (n_importance=0), FiLM-SIREN D=8 W=128 SDF+colour "
+                        f"MLP + analytic normal + NeuS compositing, {bs} instance(s)/GPU = {bs * PATCH * PATCH} rays/step/GPU",
+            "patch": PATCH, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "D": DEPTH, "W": WIDTH,
+            "instances_per_gpu": bs, "parallelism": f"dp{n_gpus} (independent instances per rank, no forward collective)",
+            "l2": "flushed between timed steps by a 256 MiB write"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
     """The reference's own CPU implementation of the path = the oracle port (the reference is Python/torch and
-    cannot travel to the GPU box; the port is pinned bit-exactly to it by tests/test_oracle.py)."""
+    cannot travel to the GPU box; the port is pinned bit-exactly to it by tests/test_oracle.py).  Same `config` as
+    the repo arm; each step renders a BOUNDED SAMPLE of that workload: one of its `bs` instances (4096 rays x 64)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -111,28 +134,20 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "rendered_rays_per_sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1, args.gpus),
+        "config": workload_config(args.bs, args.gpus),
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{R} rays (1 instance, 64x64 patch) x 64 samples per step, torch-CPU fp32, "
-                                   f"{torch.get_num_threads()} threads"},
+                         "sample": f"per step ONE instance of the workload's {args.bs} ({R} rays = one 64x64 patch, x 64 "
+                                   f"samples), torch-CPU fp32 oracle port, {torch.get_num_threads()} threads"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(bs, n_gpus):
-    return {"workload": f"cfg2: 64x64-ray patch x 64 samples/ray (n_importance=0), FiLM-SIREN D=8 W=128 SDF+colour "
-                        f"MLP + analytic normal + NeuS compositing, {bs} instance(s)/GPU = {bs * PATCH * PATCH} rays/step/GPU",
-            "patch": PATCH, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "D": DEPTH, "W": WIDTH,
-            "instances_per_gpu": bs, "parallelism": f"dp{n_gpus} (independent instances per rank, no forward collective)",
-            "l2": "flushed between timed steps by a 256 MiB write"}
-
-
-def cpu_baseline_leg(P, n_runs=2):
+def cpu_baseline_leg(n_runs=2):
     from oracle import neus_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    _, ro, rd, near, far, z = make_inputs(1, 1234)
+    P, ro, rd, near, far, z = make_inputs(1, 1234)
     w = O.style_mlp(P, z)
     ts = []
     with torch.no_grad():
@@ -147,6 +162,101 @@ def cpu_baseline_leg(P, n_runs=2):
                       f"torch-CPU fp32 oracle port, {torch.get_num_threads()} threads"}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# helpers of the repo arm
+# ------------------------------------------------------------------------------------------------------------------
+def lib_stamp():
+    p = os.path.join(ROOT, "object_intrinsics_b200", "lib", "liboi_b200.stamp")
+    return open(p).read().strip() if os.path.exists(p) else None
+
+
+def recorded_traffic(kernel_name, rays):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture -- only if that capture was
+    taken on THIS build (profiles/traffic.json carries the source stamp of the library it profiled)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)[kernel_name]
+    except Exception:  # noqa: BLE001
+        return None, "no capture recorded for this kernel"
+    if tr.get("stamp") != lib_stamp():
+        return None, f"capture {tr.get('capture')} was taken on another build (stamp mismatch): not reported"
+    return tr["dram_bytes_per_launch"] * (rays / tr["rays_per_launch"]), tr.get("capture")
+
+
+def timed_forward(renderer, sdf, tensors, steps, flush, barrier):
+    """K resident forward steps; returns (sum of per-step ms, list of core-kernel ms)."""
+    d_ro, d_rd, d_near, d_far, d_z = tensors
+
+    def step():
+        with torch.no_grad():
+            w = sdf.style(d_z)
+            return renderer.render(d_ro, d_rd, d_near, d_far, cos_anneal_ratio=1.0, perturb_overwrite=0, z=d_z, w=w)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    cores = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for pair in cores:
+        for e in pair:
+            e.record()   # torch creates the cudaEvent_t lazily; the C-ABI needs the handle
+    barrier()
+    # K steps are enqueued back to back (no host sync inside the timed region); each step is bracketed by its own
+    # event pair, the L2 flush between steps sits outside the brackets
+    for i in range(steps):
+        flush.fill_(i & 0xFF)          # evict L2 between timed iterations (not timed)
+        renderer.core_events = cores[i]
+        starts[i].record()
+        step()
+        stops[i].record()
+    barrier()
+    renderer.core_events = None
+    return sum(s.elapsed_time(e) for s, e in zip(starts, stops)), [a.elapsed_time(b) for a, b in cores]
+
+
+def ddp_leg(args, dev, rank, world, local_rank, P, dist, flush):
+    """Row e2: per rank ONE grad-mode render of its own instance (4096 rays x 64) + backward through DDP."""
+    from object_intrinsics_b200 import fields
+    from object_intrinsics_b200.parallel import (RenderModule, aggregate_throughput, check_ddp_gradients,
+                                                  training_loss)
+
+    def build():
+        sdf, col, devn = fields.build_networks(D=DEPTH, device=dev)
+        fields.load_flat_params(sdf, col, devn, P)
+        return RenderModule(sdf, col, devn, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, impl=args.kernel)
+    local, wrapped = build(), build()
+    ddp = torch.nn.parallel.DistributedDataParallel(wrapped, device_ids=[local_rank])
+    _, ro, rd, near, far, z = make_inputs(1, 1234 + rank)
+    inputs = tuple(t.to(dev) for t in (ro, rd, near, far, z))
+    err, n_grad = check_ddp_gradients(ddp, local, inputs)
+    del local
+    steps = max(5, min(args.steps, 20))
+
+    def step():
+        for p in ddp.parameters():
+            p.grad = None
+        training_loss(ddp(*inputs)).backward()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    R = ro.shape[0]
+    value, _, total_s = aggregate_throughput(R * steps, ms * 1e-3)
+    return {"ms_per_step": total_s * 1e3 / steps, "value": value, "unit": "rays/s (grad-mode render + backward + "
+            "gradient all-reduce, whole job)", "rays_per_step_per_gpu": R, "steps": steps, "world_size": world,
+            "allreduce_bytes_per_step": n_grad * 4, "grad_vs_rank_mean_rel_err": err,
+            "nccl_env": {k: os.environ.get(k) for k in ("NCCL_P2P_LEVEL", "NCCL_IB_DISABLE")},
+            "what": "RenderModule (sdf/color/deviation networks + renderer) wrapped in DistributedDataParallel("
+                    "device_ids=[local_rank]) as scripts/train.py:157-158; every rank renders its own instance; "
+                    "time = max over ranks, CUDA events"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +267,7 @@ def main():
     ap.add_argument("--bs", type=int, default=4, help="object instances per GPU per step (4 = the reference's "
                     "largest single training chunk, generator.py:14,289)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip grad_step / grad_step_ddp / train_step / bs1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -170,11 +281,14 @@ def main():
                          "for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    import torch.distributed as dist
+    from object_intrinsics_b200.parallel import aggregate_throughput, nccl_nvlink_env
+    nccl_nvlink_env()                 # NVLink/NVSwitch only (NCCL_P2P_LEVEL=NVL, NCCL_IB_DISABLE=1)
+    if world == 1:                    # plain `python bench.py`: a one-rank group so that the DDP leg runs at N=1 too
+        os.environ.setdefault("MASTER_PORT", str(29400 + os.getpid() % 500))
+        os.environ.setdefault("RANK", "0")
+        os.environ.setdefault("WORLD_SIZE", "1")
+    dist.init_process_group("nccl", device_id=dev)
 
     from object_intrinsics_b200 import fields
     from object_intrinsics_b200.renderer import NeuSRenderer
@@ -188,13 +302,9 @@ def main():
     R = ro.shape[0]
     N = R * N_SAMPLES
     host = [t.pin_memory() for t in (ro, rd, near, far, z)]
-    d_ro, d_rd, d_near, d_far, d_z = [t.to(dev) for t in host]
+    resident = [t.to(dev) for t in host]
+    d_ro, d_rd, d_near, d_far, d_z = resident
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step_resident():
-        with torch.no_grad():
-            w = sdf.style(d_z)
-            return renderer.render(d_ro, d_rd, d_near, d_far, cos_anneal_ratio=1.0, perturb_overwrite=0, z=d_z, w=w)
 
     # end-to-end leg: host (pinned) buffers in, rendered patch + mask out, through the public API.  Two result
     # buffers so that the host consumes step i-1 while the device works on step i (a streaming consumer).
@@ -217,12 +327,13 @@ def main():
         e2e_checksum[0] += float(h_mask[i & 1][0, 0]) + float(h_color[i & 1][0, 0])   # the host reads the result
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step_resident()
+        with torch.no_grad():
+            renderer.render(d_ro, d_rd, d_near, d_far, cos_anneal_ratio=1.0, perturb_overwrite=0, z=d_z,
+                            w=sdf.style(d_z))
     step_e2e(0)
     consume_e2e(0)
     barrier()
@@ -230,25 +341,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     # ---- timed region: K steps, device-timed, inputs resident in HBM
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    cores = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for pair in cores:
-        for e in pair:
-            e.record()   # torch creates the cudaEvent_t lazily; the C-ABI needs the handle
-    barrier()
-    # K steps are enqueued back to back (no host sync inside the timed region); each step is bracketed by its own
-    # event pair, the L2 flush between steps sits outside the brackets
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)          # evict L2 between timed iterations (not timed)
-        renderer.core_events = cores[i]
-        starts[i].record()
-        step_resident()
-        stops[i].record()
-    barrier()
-    renderer.core_events = None
-    core_ms = [a_.elapsed_time(b_) for a_, b_ in cores]
-    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    total_ms, core_ms = timed_forward(renderer, sdf, resident, args.steps, flush, barrier)
     # ---- end-to-end: host buffers in, rendered patch + mask out, copies inside the timed region
     barrier()
     t0 = time.perf_counter()
@@ -262,18 +355,84 @@ def main():
     clocks = sampler.stop()
 
     # whole-job numbers: units summed over ranks / max elapsed time over ranks (no data-path collective)
-    from object_intrinsics_b200.parallel import aggregate_throughput
     value, _, total_s = aggregate_throughput(R * args.steps, total_ms * 1e-3)
     e2e_value, _, _ = aggregate_throughput(R * args.steps, e2e_s)
     total_ms = total_s * 1e3
+
+    # ---- the same forward at ONE instance per GPU (the 64x64-patch unit the metric is named after)
+    bs1 = None
+    if not args.no_side_legs:
+        r1 = R // bs
+        one = [d_ro[:r1], d_rd[:r1], d_near[:r1], d_far[:r1], d_z[:1]]
+        ms1, core1 = timed_forward(renderer, sdf, one, args.steps, flush, barrier)
+        v1, _, t1 = aggregate_throughput(r1 * args.steps, ms1 * 1e-3)
+        bs1 = {"value": v1, "unit": "rays/s", "ms_per_step": t1 * 1e3 / args.steps,
+               "core_kernel_ms": sum(core1) / len(core1), "rays_per_step_per_gpu": r1}
+
+    # ---- row e2: DDP grad step on every rank
+    ddp_info = None
+    if not args.no_side_legs:
+        ddp_info = ddp_leg(args, dev, rank, world, local_rank, P, dist, flush)
+    barrier()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        dist.destroy_process_group()
         return
 
-    # ---- side measurement (rank 0, outside every timed region): the grad-mode render of the generator update,
-    # forward + loss + hand-written backward (oi_render_backward), one instance of the workload
-    r1 = R // bs
+    line_extra = {}
+    if not args.no_side_legs:
+        line_extra["grad_step"] = grad_step_leg(renderer, sdf, col, devn, resident, R // bs, flush)
+        try:
+            line_extra["train_step"] = train_step_leg(dev, P, args.kernel, flush)
+        except Exception as e:  # noqa: BLE001  (a side measurement must not take the headline down with it)
+            line_extra["train_step"] = {"error": f"{type(e).__name__}: {e}"}
+
+    peaks = load_peaks()
+    core_avg_ms = sum(core_ms) / len(core_ms)
+    used_tc = args.kernel in ("auto", "tcgen05")   # auto resolves to the tcgen05 core for depth >= 2
+    flops = N * FLOP_PER_POINT
+    achieved_tflops = flops / (core_avg_ms * 1e-3) / 1e12
+    if used_tc:
+        peak, bound, peak_note = peaks["bf16_tflops"], "tensor", f"cuBLAS bf16 burst, {peaks['source']}"
+    else:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak = sms * FP32_FMA_LANES_PER_SM * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        bound, peak_note = "fp32_fma", f"nominal {sms} SMs x 128 lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz"
+    kernel_name = "render_tc_kernel" if used_tc else "render_ffma_kernel"
+    traffic, traffic_note = recorded_traffic(kernel_name, R)
+    alg_bytes = R * (BYTES_PER_RAY_IN + BYTES_PER_RAY_OUT) + N * BYTES_PER_POINT
+    hbm_gbs = alg_bytes / (core_avg_ms * 1e-3) / 1e9
+    line = {
+        "metric": "rendered_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if not used_tc else "f32 (fp16x2-split tcgen05 products, fp32 accumulate)",
+        "data": "synthetic", "config": workload_config(bs, world),
+        "e2e": {"value": e2e_value, "unit": "rays/s",
+                "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": R * 16},
+        "gpu_launches": args.steps * (renderer.last_launches + 1),
+        "roofline": {"bound": bound, "kernel": kernel_name,
+                     "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
+                     "peak_source": peak_note, "traffic": traffic, "traffic_source": traffic_note,
+                     "split_ceiling_frac": (achieved_tflops / (peak / 3.0)) if used_tc else None,
+                     "core_kernel_ms": core_avg_ms, "algorithmic_flop_per_launch": flops,
+                     "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": hbm_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes,
+                             "note": "path is compute-bound (8100 FLOP/B); reported because BASELINE north_star asks"}},
+        "clocks": clocks,
+        "bs1": bs1,
+        "grad_step_ddp": ddp_info,
+        "lib_stamp": lib_stamp(),
+    }
+    line.update(line_extra)
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def grad_step_leg(renderer, sdf, col, devn, resident, r1, flush):
+    """Rank 0, outside every timed region: the grad-mode render of the generator update, forward + loss +
+    hand-written backward (oi_render_backward), one instance of the workload."""
+    d_ro, d_rd, d_near, d_far, d_z = resident
     bwd_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     for e in bwd_ev:
         e.record()
@@ -292,7 +451,7 @@ def main():
     for _ in range(3):
         grad_step()
     torch.cuda.synchronize()
-    gs = []
+    gs, ks = [], []
     for i in range(5):
         flush.fill_(i)
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -301,56 +460,20 @@ def main():
         b_.record()
         b_.synchronize()
         gs.append(a_.elapsed_time(b_))
+        ks.append(bwd_ev[0].elapsed_time(bwd_ev[1]))
     renderer.bwd_events = None
     gs.sort()
-    grad_info = {"ms": gs[len(gs) // 2], "rays": r1, "bwd_kernels_ms": bwd_ev[0].elapsed_time(bwd_ev[1]),
-                 "what": "grad-mode render of 1 instance: forward + loss + oi_render_backward (sweep kernel on tcgen05 "
-                         "+ TMA-fed TF32 point-contraction), gradients on every nn.Parameter"}
+    ks.sort()
+    return {"ms": gs[len(gs) // 2], "rays": r1, "bwd_kernels_ms": ks[len(ks) // 2],
+            "what": "grad-mode render of 1 instance: forward + loss + oi_render_backward (sweep kernel on tcgen05 "
+                    "+ TMA-fed TF32 point-contraction), gradients on every nn.Parameter"}
 
-    peaks = load_peaks()
-    core_avg_ms = sum(core_ms) / len(core_ms)
-    used_tc = args.kernel in ("auto", "tcgen05")   # auto resolves to the tcgen05 core for depth >= 2
-    flops = N * FLOP_PER_POINT
-    achieved_tflops = flops / (core_avg_ms * 1e-3) / 1e12
-    if used_tc:
-        peak, bound, peak_note = peaks["bf16_tflops"], "tensor", f"cuBLAS bf16 burst, {peaks['source']}"
-    else:
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        peak = sms * FP32_FMA_LANES_PER_SM * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-        bound, peak_note = "fp32_fma", f"nominal {sms} SMs x 128 lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz"
-    kernel_name = "render_tc_kernel" if used_tc else "render_ffma_kernel"
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tr = json.load(f)[kernel_name]
-        traffic = tr["dram_bytes_per_launch"] * (R / tr["rays_per_launch"])   # ncu capture, scaled to this launch
-    except Exception:  # noqa: BLE001
-        pass
-    alg_bytes = R * (BYTES_PER_RAY_IN + BYTES_PER_RAY_OUT) + N * BYTES_PER_POINT
-    hbm_gbs = alg_bytes / (core_avg_ms * 1e-3) / 1e9
-    line = {
-        "metric": "rendered_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if not used_tc else "f32 (fp16x2-split tcgen05 products, fp32 accumulate)",
-        "data": "synthetic", "config": workload_config(bs, world),
-        "e2e": {"value": e2e_value, "unit": "rays/s",
-                "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": R * 16},
-        "gpu_launches": args.steps * (renderer.last_launches + 1),
-        "roofline": {"bound": bound, "kernel": kernel_name,
-                     "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
-                     "peak_source": peak_note, "traffic": traffic,
-                     "core_kernel_ms": core_avg_ms, "algorithmic_flop_per_launch": flops,
-                     "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": hbm_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": "path is compute-bound (8100 FLOP/B); reported because BASELINE north_star asks"}},
-        "clocks": clocks,
-        "grad_step": grad_info,
-    }
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg(P)
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+
+def train_step_leg(dev, P, kernel, flush):
+    """Rank 0: a training-shaped composition of the path's kernels (no trainer code), mirroring
+    src/trainers/gan_pose_trainer.py:77-101 -- implemented in tools_train_step.py so that it can be profiled alone."""
+    import tools_train_step as T
+    return T.measure(dev, P, kernel, flush)
 
 
 if __name__ == "__main__":

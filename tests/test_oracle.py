@@ -88,3 +88,14 @@ def test_degenerate_inputs():
     n2, f2 = O.near_far_from_sphere(ro2, rd)
     out2 = O.render(P, ro2, rd, n2, f2, z=z, n_samples=8, n_importance=4, cos_anneal_ratio=1.0)
     assert torch.isfinite(out2["weights"]).all() and out2["inside_sphere"].sum() == 0
+
+
+def test_bench_input_generator_equals_the_oracles():
+    """bench.py's repo arm builds its rays with bench_inputs.py (no oracle import on that arm); same rays, bit for bit."""
+    import bench_inputs as BI
+    for bs, patch, seed in ((1, 64, 1234), (4, 16, 1237), (3, 5, 5)):
+        for a, b in zip(BI.synthetic_rays(bs, patch, seed=seed), O.synthetic_rays(bs, patch, seed=seed)):
+            assert torch.equal(a, b)
+    ref = load_params("params_D8.npz")
+    mine = BI.load_flat_params("params_D8.npz")
+    assert set(ref) == set(mine) and all(torch.equal(ref[k], mine[k]) for k in ref)
