@@ -15,7 +15,9 @@ OI_STYLE_DIM = 64
 OI_IMPL_AUTO, OI_IMPL_FFMA, OI_IMPL_TCGEN05 = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liboi_b200.so")
+# OI_LIB_PATH selects an experiment build (object_intrinsics_b200/build.py --variant ...) for A/B timing; the product
+# path is the in-tree default
+LIB_PATH = os.environ.get("OI_LIB_PATH") or os.path.join(_HERE, "lib", "liboi_b200.so")
 
 f32p = C.c_void_p  # device pointers travel as integers
 

@@ -32,7 +32,7 @@ def _nvcc():
 
 def _stamp():
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "oi_b200.h")]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [os.path.join(ROOT, "include", "oi_b200.h")]
     for f in files:
         with open(f, "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
@@ -40,17 +40,22 @@ def _stamp():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    os.makedirs(LIB_DIR, exist_ok=True)
-    stamp_file = os.path.join(LIB_DIR, "liboi_b200.stamp")
-    stamp = _stamp()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
-        return LIB_PATH
+def build(force=False, verbose=False, variant=None, defines=()):
+    """Default: object_intrinsics_b200/lib/liboi_b200.so.  `variant` (developer tooling for A/B timing on the GPU
+    box): the same sources with extra -D `defines`, written to lib/variants/<variant>/liboi_b200.so and selected at
+    run time with OI_LIB_PATH (see _lib.py)."""
+    lib_dir = LIB_DIR if variant is None else os.path.join(LIB_DIR, "variants", variant)
+    lib_path = os.path.join(lib_dir, "liboi_b200.so")
+    os.makedirs(lib_dir, exist_ok=True)
+    stamp_file = os.path.join(lib_dir, "liboi_b200.stamp")
+    stamp = _stamp() + "".join(" -D" + d for d in defines)
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return lib_path
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(lib_dir, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
@@ -59,16 +64,20 @@ def build(force=False, verbose=False):
         log.append(f"==== {src}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.run(cmd, check=True)
-    with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
+    with open(os.path.join(lib_dir, "build.log"), "w") as f:
         f.write("\n".join(log))
     with open(stamp_file, "w") as f:
         f.write(stamp)
     if verbose:
         print("\n".join(log))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    # python -m object_intrinsics_b200.build [--force] [--variant NAME -DFOO=1 -DBAR=2 ...]
+    args = sys.argv[1:]
+    var = args[args.index("--variant") + 1] if "--variant" in args else None
+    print(build(force="--force" in args, verbose=var is None, variant=var,
+                defines=[a[2:] for a in args if a.startswith("-D")]))

@@ -255,7 +255,7 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
 
 namespace {
 struct BwdWorkspace {
-  size_t film, d_film, adj, invs_partial, relax_count, ticket, scratch, slabs, aux, total;
+  size_t film, d_film, adj, invs_partial, relax_count, ticket, scratch, slabs, aux, dw_inst, total;
   int n_ctas, n_inst, tiles_per_inst, n_tiles, chunk_tiles;
   bool tc;
 };
@@ -311,9 +311,10 @@ void plan_bwd(const OiRenderBwdDesc* d, BwdWorkspace* w) {
     w->scratch = take((size_t)w->n_ctas * render_bwd_tc_scratch_floats() * 4);
     w->slabs = take((size_t)w->chunk_tiles * kSlabsPerTile * kSlabFloats * 4);
     w->aux = take((size_t)w->chunk_tiles * 512 * 4);
+    w->dw_inst = take(render_bwd_tc_dw_floats(w->n_inst, d->depth) * 4);
   } else {
     w->scratch = take((size_t)w->n_ctas * render_bwd_scratch_floats() * 4);
-    w->slabs = w->aux = 0;
+    w->slabs = w->aux = w->dw_inst = 0;
   }
   w->total = off;
 }
@@ -376,7 +377,8 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
                                   st);
   return launch_render_bwd_tc(*d, a, adj, invs_partial, d_film,
                               reinterpret_cast<float*>(ws + w.scratch), reinterpret_cast<float*>(ws + w.slabs),
-                              reinterpret_cast<float*>(ws + w.aux), w.chunk_tiles, w.n_ctas, st);
+                              reinterpret_cast<float*>(ws + w.aux), reinterpret_cast<float*>(ws + w.dw_inst),
+                              w.chunk_tiles, w.n_ctas, st);
 }
 
 int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,

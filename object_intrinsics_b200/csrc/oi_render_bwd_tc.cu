@@ -8,23 +8,41 @@
 //   recompute  forward l=1..D-1, colour features, reverse l=D-1..1      (fp16 2-term split, panels of the forward)
 //   adjoint    colour^T, backward-of-reverse l=1..D-1 (operand W_l), backward-of-forward l=D-1..1 (operand W_l^T)
 //              (bf16 2-term split: adjoints have no bounded range; unscaled bf16 panels)
-// Contractions over POINTS (weight gradients, per-channel sums) are not done here: every per-point quantity they
-// need is left as an fp32 slab [32 channel-quads][128 points] float4 per tile (oi_wgrad.cuh) and contracted by
-// wgrad_tc_kernel.  Warp roles: 0-7 / 8-15 epilogue of slot 0 / 1, 16 TMA producer, 17 MMA issuer.
+// Contractions over POINTS (weight gradients, bias sums) are not done here: every per-point operand they need is left
+// as a slab per tile (oi_wgrad.cuh) and contracted by wgrad_tc_kernel.
+//
+// Round-2 structure of the epilogues:
+//   * every stage walks its 64 channels in eight OCTS of 8 columns: tcgen05.ld.x8 (double-buffered), the two
+//     scratch float4 pairs it re-reads (pre-activations a_l, g_{l+1} / c_bar_l) prefetched TWO octs ahead -- the
+//     first two octs before the wait on the accumulator barrier, so that the L2 / DRAM latency of the re-reads sits
+//     under the MMA -- and no per-stage arrays that outlive an oct (no spills);
+//   * dL/dgamma needs NO per-point column sums: with a = gamma u + beta, u = W h + b,
+//         sum_m a_bar u + c_bar cos a = (1/gamma) [ sum_k W[j][k] dW[j][k] + b[j] db[j] ]
+//     (dW = both parts of the layer's weight gradient, per instance; db = sum_m u_bar), because
+//     sum_m a_bar_j h_k = dW^fwd_jk / gamma_j and sum_m c_bar_j cos a_j = sum_m t_bar_j t_j / gamma_j =
+//     sum_k W_jk dW^rev_jk / gamma_j.  finalize_bwd_tc_kernel evaluates it from the per-instance weight gradients;
+//     tests/test_backward_math.py checks the identity in fp64.  That removes 10 of the 21 warp butterflies per
+//     16-channel chunk and every "a_bar * a" product from the sweep;
+//   * 640 threads = 5 warpgroups: the producer / issuer warpgroup drops to 32 registers (setmaxnreg), the four
+//     epilogue warpgroups grow to 112.
+// Warp roles: 0-7 / 8-15 epilogue of slot 0 / 1, 16 TMA producer, 17 MMA issuer, 18-19 idle.
 #include "oi_internal.cuh"
 #include "oi_render_common.cuh"
 #include "oi_tc.cuh"
 #include "oi_wgrad.cuh"
 
-#ifndef OI_BWD_TIMING_FLAGS
-#define OI_BWD_TIMING_FLAGS 0
+#ifndef OI_BWD_PF2
+#define OI_BWD_PF2 1   // octs of look-ahead of the scratch re-reads in stages that re-read one slab
+#endif
+#ifndef OI_BWD_PF4
+#define OI_BWD_PF4 1   // ... in stages that re-read two slabs
 #endif
 
 namespace oi {
 
 namespace {
 
-constexpr int kTcThreads = 576;
+constexpr int kTcThreads = 640;
 constexpr int kEpiThreadsPerSlot = 256;
 constexpr int kProducerWarp = 16, kMmaWarp = 17;
 constexpr int kTcStages = 3;
@@ -49,8 +67,9 @@ struct BwdTcArgs {
   float* slabs;            // [tiles of this launch][kSlabsPerTile][32][128] float4
   float* aux;              // [tiles of this launch][16][128]
   int tile_begin, tile_end;
-  OiNetGrads g;            // per-channel sums over points are reduced here (warp butterflies + atomics)
-  float* d_film;           // [n_inst][9][2][128] (dgamma, db)
+  OiNetGrads g;            // per-channel sums over points of the narrow heads (warp butterflies + atomics)
+  float* d_film;           // [n_inst][9][2][128] (unused | db)
+  float* dw0;              // [n_inst][128][3] per-instance dW_0 (both parts)
 };
 
 struct __align__(1024) BwdTcSmem {
@@ -66,56 +85,105 @@ struct __align__(1024) BwdTcSmem {
 };
 static_assert(sizeof(BwdTcSmem) <= 227 * 1024, "BwdTcSmem exceeds the 227 KB per-CTA limit");
 
-using tc::issue_split_layer_mmas;
 using tc::named_bar_sync;
-using tc::split2_bf16;
 
-// round-to-nearest TF32 (the contraction kernel feeds these values to kind::tf32 MMAs, which ignore the low bits)
-__device__ __forceinline__ float tf32r(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// The 24 MMAs of one layer of one tile (acc = hi*Whi + lo*Whi + hi*Wlo over K = 128), written for the 32-register
+// issuer thread: two 64-bit descriptors advanced by immediates instead of 16 hoisted ones.
+__device__ __forceinline__ void issue_layer_lean(uint32_t acc, uint32_t wbase, uint32_t idesc) {
+  uint64_t dhi = tc::make_desc_k_sw128(wbase);
+  const uint32_t a_hi = acc + 128, a_lo = acc + 192;
+#pragma unroll 1
+  for (int kb = 0; kb < 2; ++kb) {
+    const uint64_t dlo = dhi + (2 * 16384 >> 4);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t k8 = (uint32_t)(kb * 4 + ks) * 8;
+      tc::mma_ts(acc, a_hi + k8, dhi + ks * 2, idesc, (kb | ks) ? 1u : 0u);
+      tc::mma_ts(acc, a_lo + k8, dhi + ks * 2, idesc, 1u);
+      tc::mma_ts(acc, a_hi + k8, dlo + ks * 2, idesc, 1u);
+    }
+    dhi += 16384 >> 4;
+  }
 }
-// Sum over the 32 lanes of a warp (= 32 sample points) of 16 per-lane values (= 16 channels), by recursive halving:
-// after the four exchange steps lane L holds channel 8 b4 + 4 b3 + 2 b2 + b1 (bits of L) summed over 16 lanes; one
-// more exchange completes the sum, and the even lanes add it to dst[channel * stride].  16 shuffles per call.
-__device__ __forceinline__ void colsum16_impl(const float (&v)[16], float* dst, int stride, int lane) {
-  float a8[8], a4[4], a2[2];
+
+// ---- TMEM accessors at oct granularity (8 accumulator columns / 4 packed operand columns) ----
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+
+// fp32 pair -> bf16 {hi, lo}: hi = truncation to the upper 16 bits (one PRMT packs two of them), lo = rn(v - hi);
+// v = hi + lo + O(2^-16 |v|), full fp32 exponent range.  5 instructions per pair.
+__device__ __forceinline__ void split2_bf16t(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const uint32_t b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
+  hi = __byte_perm(b0, b1, 0x7632);
+  const float2 d = tc::sub2(make_float2(v0, v1),
+                            make_float2(__uint_as_float(b0 & 0xFFFF0000u), __uint_as_float(b1 & 0xFFFF0000u)));
+  const __nv_bfloat162 l = __floats2bfloat162_rn(d.x, d.y);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// value stored into a TF32 operand slab: round-to-nearest (ties away) is the +2^12 of the bit pattern; the tensor core
+// drops the 13 low mantissa bits itself
+__device__ __forceinline__ float tf32_bias(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+// Sum over the 32 lanes of a warp (= 32 sample points) of 8 per-lane values (= 8 channels) by recursive halving;
+// lane L ends up with channel 4 b4 + 2 b3 + b2 (bits of L) and lanes with (L & 3) == 0 add it to dst[ch * stride].
+__device__ __forceinline__ void colsum8(const float (&v)[8], float* dst, int stride, int lane) {
+  float a4[4], a2[2];
   {
     const bool up = (lane & 16) != 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
-      a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    for (int i = 0; i < 4; ++i) {
+      const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
   }
   {
     const bool up = (lane & 8) != 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float keep = up ? a8[i + 4] : a8[i], send = up ? a8[i] : a8[i + 4];
-      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool up = (lane & 4) != 0;
-#pragma unroll
     for (int i = 0; i < 2; ++i) {
       const float keep = up ? a4[i + 2] : a4[i], send = up ? a4[i] : a4[i + 2];
-      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
   }
-  const bool up = (lane & 2) != 0;
-  float a1 = (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 2);
+  const bool up = (lane & 4) != 0;
+  float a1 = (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 4);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
   a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-  const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-  if ((lane & 1) == 0) atomicAdd(dst + (size_t)ch * stride, a1);
+  const int ch = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  if ((lane & 3) == 0) atomicAdd(dst + (size_t)ch * stride, a1);
 }
 
-#define colsum16(v, dst, stride, lane)                  \
-  do {                                                  \
-    if (!skip_cols) colsum16_impl(v, dst, stride, lane); \
-  } while (0)
+// One stage of a tile slot.  For o = 0..7: u = accumulator columns [8o, 8o+8) of this thread (if WAIT), buf = the
+// stage's scratch float4s of oct o.  `load(o, buf)` issues the global loads of oct o, PF octs ahead of their use;
+// the first PF octs are issued BEFORE the wait on the accumulator barrier (their latency sits under the MMA).
+template <int NL, bool WAIT, int PF, class Load, class Body, class WaitAcc>
+__device__ __forceinline__ void run_stage(uint32_t acc, Load load, Body body, WaitAcc wait_acc) {
+  float4 buf[PF + 1][NL > 0 ? NL : 1];
+#pragma unroll
+  for (int o = 0; o < PF; ++o) load(o, buf[o]);
+  uint32_t ub[2][8];
+  if (WAIT) {
+    wait_acc();
+    tmem_ld8_async(acc, ub[0]);
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    if (o + PF < 8) load(o + PF, buf[(o + PF) % (PF + 1)]);
+    if (WAIT) {
+      tc::wait_ld();
+      if (o < 7) tmem_ld8_async(acc + (o + 1) * 8, ub[(o + 1) & 1]);
+    }
+    body(o, ub[o & 1], buf[o % (PF + 1)]);
+  }
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -158,49 +226,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_base;
 
-  if (warp == kProducerWarp) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
-        for (int p = 0; p < NP; ++p, ++it) {
-          const int stage = it % kTcStages;
-          if (it >= kTcStages) mbar_wait_sleep(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1);
-          mbar_expect_tx(&sm.w_full[stage], kPanelBytes);
-          // adjoint panels: [colour^T | forward orientation l=1..D-1 | reverse orientation l=D-1..1]
-          const unsigned char* src = (p < NR) ? panels_f16 + (size_t)p * kPanelBytes
-                                              : panels_bf16 + (size_t)(p - NR) * kPanelBytes;
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == kProducerWarp) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int it = 0;
+        for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+          for (int p = 0; p < NP; ++p, ++it) {
+            const int stage = it % kTcStages;
+            if (it >= kTcStages) mbar_wait_sleep(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1);
+            mbar_expect_tx(&sm.w_full[stage], kPanelBytes);
+            // adjoint panels: [colour^T | forward orientation l=1..D-1 | reverse orientation l=D-1..1]
+            const unsigned char* src = (p < NR) ? panels_f16 + (size_t)p * kPanelBytes
+                                                : panels_bf16 + (size_t)(p - NR) * kPanelBytes;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            tma_bulk_g2s(sm.w[stage] + q * kSubPanelBytes, src + q * kSubPanelBytes, kSubPanelBytes, &sm.w_full[stage]);
+            for (int q = 0; q < 4; ++q)
+              tma_bulk_g2s(sm.w[stage] + q * kSubPanelBytes, src + q * kSubPanelBytes, kSubPanelBytes,
+                           &sm.w_full[stage]);
+          }
         }
       }
-    }
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int it = 0;
-      uint32_t ar_phase[2] = {0u, 0u};
-      for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
-        const int n_active = (2 * pi + 1 < n_tiles) ? 2 : 1;
-        for (int p = 0; p < NP; ++p, ++it) {
-          const int stage = it % kTcStages;
-          mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
-          const uint32_t wbase = smem_u32(sm.w[stage]);
-          const uint32_t idesc = (p < NR) ? kIdescF16 : kIdescBf16;
-          for (int t = 0; t < n_active; ++t) {
-            mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
-            ar_phase[t] ^= 1u;
-            tc::fence_after_thread_sync();
-            const uint32_t acc = tmem_base + t * 256;
-            issue_split_layer_mmas(acc, acc + 128, acc + 192, wbase, idesc);
-            tc::mma_commit(&sm.acc_full[t]);
+    } else if (warp == kMmaWarp) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        int it = 0;
+        uint32_t ar_phase[2] = {0u, 0u};
+        for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+          const int n_active = (2 * pi + 1 < n_tiles) ? 2 : 1;
+          for (int p = 0; p < NP; ++p, ++it) {
+            const int stage = it % kTcStages;
+            mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
+            const uint32_t wbase = smem_u32(sm.w[stage]);
+            const uint32_t idesc = (p < NR) ? kIdescF16 : kIdescBf16;
+            for (int t = 0; t < n_active; ++t) {
+              mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
+              ar_phase[t] ^= 1u;
+              tc::fence_after_thread_sync();
+              issue_layer_lean(tmem_base + t * 256, wbase, idesc);
+              tc::mma_commit(&sm.acc_full[t]);
+            }
+            tc::mma_commit(&sm.w_empty[stage]);
           }
-          tc::mma_commit(&sm.w_empty[stage]);
         }
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ===================== epilogue warps =====================
     const int t = warp >> 3;
     const int h = (warp >> 2) & 1;
@@ -215,39 +287,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
                                              (size_t)t * kCtaSlabs * kSlabFloats) + m;
     uint32_t af_phase = 0u;
-    // timing experiments only (results invalid; build with -DOI_BWD_TIMING_FLAGS=1): OiRenderBwdDesc.flags bit 3 =
-    // skip the operand-slab stores, bit 4 = skip the column-sum butterflies (profiles/r01_summary.md)
-#if OI_BWD_TIMING_FLAGS
-    const bool skip_ops = (a.r.flags & 8) != 0, skip_cols = (a.r.flags & 16) != 0;
-#else
-    constexpr bool skip_ops = false, skip_cols = false;
-#endif
-#define OI_CTA(slab, quad) scr4[((size_t)(slab) * 32 + (quad)) * 128]
-#define OI_GS(slab, quad) gs4[((size_t)(slab) * 32 + (quad)) * 128]   /* ARG slabs: [quad][128 points] float4 */
-/* operand slabs: K-major SWIZZLE_128B tf32 image [32-point block][channel][32 points], 16-byte chunks XOR (ch & 7) */
-#define OI_OP(slab, j, v)                                                                                  \
-  do {                                                                                                    \
-    if (!skip_ops) gso[(size_t)(slab) * kSlabFloats + (n0 + (j)) * 32 + ((mc ^ ((j) & 7)) << 2)] = tf32r(v); \
-  } while (0)
-#define OI_OP4(slab, j0, a0, a1, a2, a3) \
-  do {                                   \
-    OI_OP(slab, (j0) + 0, a0);           \
-    OI_OP(slab, (j0) + 1, a1);           \
-    OI_OP(slab, (j0) + 2, a2);           \
-    OI_OP(slab, (j0) + 3, a3);           \
-  } while (0)
-#define OI_A_READY()               \
-  do {                             \
-    tc::wait_st();                 \
-    tc::fence_before_thread_sync(); \
-    mbar_arrive(&sm.a_ready[t]);   \
-  } while (0)
-#define OI_WAIT_ACC()                                \
-  do {                                               \
-    mbar_wait_sleep(&sm.acc_full[t], af_phase);      \
-    af_phase ^= 1u;                                  \
-    tc::fence_after_thread_sync();                   \
-  } while (0)
+    // operand slabs: K-major SWIZZLE_128B tf32 image [32-point block][channel][32 points]; the 16-byte chunk of this
+    // thread's point is XOR-permuted by (channel & 7) = the position e inside an oct
+    const int mc = (m & 31) >> 2;
+    const int mc4 = mc << 2;   // element e of an oct lands at e * 32 + ((mc ^ e) << 2) = e * 32 + (mc4 ^ (e << 2))
+
+    auto wait_acc = [&]() {
+      mbar_wait_sleep(&sm.acc_full[t], af_phase);
+      af_phase ^= 1u;
+      tc::fence_after_thread_sync();
+    };
+    auto a_ready = [&]() {
+      tc::wait_st();
+      tc::fence_before_thread_sync();
+      mbar_arrive(&sm.a_ready[t]);
+    };
+    auto no_load = [](int, float4 (&)[1]) {};
 
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
       const int lt = 2 * pi + t;   // tile index inside this launch
@@ -256,12 +311,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       const int inst = tile / a.r.tiles_per_inst;
       const int tin = tile - inst * a.r.tiles_per_inst;
       float* slab_tile = a.slabs + (size_t)lt * kSlabsPerTile * kSlabFloats;
-      float4* gs4 = reinterpret_cast<float4*>(slab_tile) + m;
-      float* gso = slab_tile + (m >> 5) * 4096 + (m & 3);
-      const int mc = (m & 31) >> 2;
+      float4* gs4 = reinterpret_cast<float4*>(slab_tile) + m;                  // ARG slabs [quad][128 points] float4
+      float* gso = slab_tile + (m >> 5) * 4096 + (m & 3) + n0 * 32;           // operand slabs, this thread's channels
       // aux operand (N = 16, rows 0..3 used): [32-point block][4 rows][32 points], same swizzle
       float* auxo = a.aux + (size_t)lt * 512 + (m >> 5) * 128 + (m & 3);
-      float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][dgamma | db][128]
+      float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][unused | db][128]
+      float* dw0 = a.dw0 + (size_t)inst * kW * 3;
       {
         const float2* src = reinterpret_cast<const float2*>(a.r.film_tc) + (size_t)inst * kFilm * kW;
         float2* dst = &sm.film[t][0][0];
@@ -284,147 +339,141 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
 
+#define OI_ARG(l, quad) gs4[((size_t)(kSlabArg + (l)) * 32 + (quad)) * 128]
+#define OI_CTA(slab, quad) scr4[((size_t)(slab) * 32 + (quad)) * 128]
+#define OI_FILM4(l) (reinterpret_cast<const float4*>(sm.film[t][(l)]) + n0 / 2)   /* (g0, g1, d0, d1) per pair */
+      // the 8 values of an oct -> operand slab `slab` (rounded to TF32)
+      auto op8 = [&](int slab, int o, const float (&v)[8]) {
+        float* p = gso + (size_t)slab * kSlabFloats + o * 256;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e * 32 + (mc4 ^ (e << 2))] = tf32_bias(v[e]);
+      };
+      // the 8 values of an oct -> next A operand (TMEM), fp16 or bf16 two-term split
+      auto a8_f16 = [&](int o, const float (&v)[8]) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+        tmem_st4(a_hi + o * 4, hi);
+        tmem_st4(a_lo + o * 4, lo);
+      };
+      auto a8_bf16 = [&](int o, const float (&v)[8]) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2_bf16t(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+        tmem_st4(a_hi + o * 4, hi);
+        tmem_st4(a_lo + o * 4, lo);
+      };
+
       // =========================== recompute ===========================
       // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
       {
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][0]) + n0 * 2;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hi[8], lo[8];
+        const float4* fl = OI_FILM4(0);
+        run_stage<0, false, 1>(acc, no_load, [&](int o, const uint32_t (&)[8], const float4 (&)[1]) {
+          float ar[8], s[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float s[4], ar[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              const float4 w0 = sm.w0[n0 + j];
-              const float u = fmaf(w0.z, pz, fmaf(w0.y, py, w0.x * px));
-              ar[e] = fmaf(flf[(j >> 1) * 4 + (j & 1)], u, flf[(j >> 1) * 4 + 2 + (j & 1)]);
-              s[e] = __sinf(ar[e]);
-            }
-            OI_GS(kSlabArg + 0, Q0 + c * 4 + q) = make_float4(ar[0], ar[1], ar[2], ar[3]);
-            OI_OP4(kSlabH + 1, c * 16 + q * 4, s[0], s[1], s[2], s[3]);
-            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
-            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+          for (int i = 0; i < 4; ++i) {
+            const float4 wa = sm.w0[n0 + o * 8 + 2 * i], wb = sm.w0[n0 + o * 8 + 2 * i + 1];
+            const float4 f = fl[o * 4 + i];
+            const float2 u = make_float2(fmaf(wa.z, pz, fmaf(wa.y, py, wa.x * px)),
+                                         fmaf(wb.z, pz, fmaf(wb.y, py, wb.x * px)));
+            const float2 arg = tc::fma2(make_float2(f.x, f.y), u, make_float2(f.z, f.w));
+            ar[2 * i] = arg.x;
+            ar[2 * i + 1] = arg.y;
+            s[2 * i] = __sinf(arg.x);
+            s[2 * i + 1] = __sinf(arg.y);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
-        }
-        OI_A_READY();
+          OI_ARG(0, Q0 + 2 * o) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+          OI_ARG(0, Q0 + 2 * o + 1) = make_float4(ar[4], ar[5], ar[6], ar[7]);
+          op8(kSlabH + 1, o, s);
+          a8_f16(o, s);
+        }, wait_acc);
+        a_ready();
       }
       // ---------------- forward layers 1..D-1 ----------------
       for (int l = 1; l < D; ++l) {
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
-        OI_WAIT_ACC();
-        uint32_t ub[2][16];
-        tc::tmem_ld16_async(acc, ub[0]);
+        const float4* fl = OI_FILM4(l);
+        run_stage<0, true, 1>(acc, no_load, [&](int o, const uint32_t (&u)[8], const float4 (&)[1]) {
+          float ar[8], s[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tc::wait_ld();
-          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
-          const uint32_t(&u)[16] = ub[c & 1];
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float s[4], ar[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              ar[e] = fmaf(flf[(j >> 1) * 4 + (j & 1)], __uint_as_float(u[q * 4 + e]), flf[(j >> 1) * 4 + 2 + (j & 1)]);
-              s[e] = __sinf(ar[e]);
-            }
-            OI_GS(kSlabArg + l, Q0 + c * 4 + q) = make_float4(ar[0], ar[1], ar[2], ar[3]);
-            OI_OP4(kSlabH + l + 1, c * 16 + q * 4, s[0], s[1], s[2], s[3]);
-            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
-            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const float2 arg = tc::fma2(make_float2(f.x, f.y),
+                                        make_float2(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1])),
+                                        make_float2(f.z, f.w));
+            ar[2 * i] = arg.x;
+            ar[2 * i + 1] = arg.y;
+            s[2 * i] = __sinf(arg.x);
+            s[2 * i + 1] = __sinf(arg.y);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
-        }
-        OI_A_READY();
+          OI_ARG(l, Q0 + 2 * o) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+          OI_ARG(l, Q0 + 2 * o + 1) = make_float4(ar[4], ar[5], ar[6], ar[7]);
+          op8(kSlabH + l + 1, o, s);
+          a8_f16(o, s);
+        }, wait_acc);
+        a_ready();
       }
       // ---------------- colour features -> slot UC; t_{D-1} = w_sigma gamma cos(a_{D-1}) ----------------
       {
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][D - 1]) + n0 * 2;
-        OI_WAIT_ACC();
-        uint32_t ub[2][16];
-        tc::tmem_ld16_async(acc, ub[0]);
+        const float4* fl = OI_FILM4(D - 1);
+        run_stage<2, true, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
+          b[0] = OI_ARG(D - 1, Q0 + 2 * o);
+          b[1] = OI_ARG(D - 1, Q0 + 2 * o + 1);
+        }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[2]) {
+          OI_CTA(kCtaUC, Q0 + 2 * o) = make_float4(__uint_as_float(u[0]), __uint_as_float(u[1]), __uint_as_float(u[2]),
+                                                   __uint_as_float(u[3]));
+          OI_CTA(kCtaUC, Q0 + 2 * o + 1) = make_float4(__uint_as_float(u[4]), __uint_as_float(u[5]),
+                                                       __uint_as_float(u[6]), __uint_as_float(u[7]));
+          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          float tv[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tc::wait_ld();
-          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
-          const uint32_t(&u)[16] = ub[c & 1];
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int quad = Q0 + c * 4 + q;
-            OI_CTA(kCtaUC, quad) = make_float4(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1]),
-                                               __uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3]));
-            const float4 ar4 = OI_GS(kSlabArg + D - 1, quad);
-            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            float tv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              tv[e] = sm.head[n0 + j].x * flf[(j >> 1) * 4 + (j & 1)] * __cosf(ar[e]);  // 2^8 w_s * gamma/2^8 * cos
-            }
-            OI_OP4(kSlabT + D - 1, c * 16 + q * 4, tv[0], tv[1], tv[2], tv[3]);
-            tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
-            tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const int n = n0 + o * 8 + 2 * i;
+            // 2^8 w_s * gamma / 2^8 * cos
+            tv[2 * i] = sm.head[n].x * f.x * __cosf(ar[2 * i]);
+            tv[2 * i + 1] = sm.head[n + 1].x * f.y * __cosf(ar[2 * i + 1]);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
-        }
-        OI_A_READY();
+          op8(kSlabT + D - 1, o, tv);
+          a8_f16(o, tv);
+        }, wait_acc);
+        a_ready();
       }
       // ---------------- reverse sweep l = D-1 .. 1: g_l (slot G[l]), t_{l-1} (slab T[l-1]) ----------------
       float gx = 0.f, gy = 0.f, gz = 0.f;
       for (int l = D - 1; l >= 1; --l) {
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][l - 1]) + n0 * 2;
+        const float4* fl = OI_FILM4(l - 1);
         const float gscale = (l - 1 == 0) ? kInvWScale : 1.0f;   // gamma'_0 is unscaled
-        OI_WAIT_ACC();
-        uint32_t ub[2][16];
-        tc::tmem_ld16_async(acc, ub[0]);
+        run_stage<2, true, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
+          b[0] = OI_ARG(l - 1, Q0 + 2 * o);
+          b[1] = OI_ARG(l - 1, Q0 + 2 * o + 1);
+        }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[2]) {
+          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          float gv[8], tv[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tc::wait_ld();
-          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
-          const uint32_t(&u)[16] = ub[c & 1];
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = OI_GS(kSlabArg + l - 1, quad);
-            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            float gv[4], tv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              const float accv = __uint_as_float(u[q * 4 + e]);           // 2^8 g_l
-              gv[e] = accv * kInvWScale;
-              tv[e] = accv * (flf[(j >> 1) * 4 + (j & 1)] * gscale) * __cosf(ar[e]);  // g_l gamma cos = t_{l-1}
-            }
-            OI_CTA(kCtaG + l - 1, quad) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-            if (l > 1) {
-              OI_OP4(kSlabT + l - 1, c * 16 + q * 4, tv[0], tv[1], tv[2], tv[3]);
-              tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
-              tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float4 w = sm.w0[n0 + c * 16 + q * 4 + e];
-                gx = fmaf(w.x, tv[e], gx);
-                gy = fmaf(w.y, tv[e], gy);
-                gz = fmaf(w.z, tv[e], gz);
-              }
-            }
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const float a0 = __uint_as_float(u[2 * i]), a1 = __uint_as_float(u[2 * i + 1]);   // 2^8 g_l
+            gv[2 * i] = a0 * kInvWScale;
+            gv[2 * i + 1] = a1 * kInvWScale;
+            tv[2 * i] = a0 * (f.x * gscale) * __cosf(ar[2 * i]);           // g_l gamma cos = t_{l-1}
+            tv[2 * i + 1] = a1 * (f.y * gscale) * __cosf(ar[2 * i + 1]);
           }
+          OI_CTA(kCtaG + l - 1, Q0 + 2 * o) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+          OI_CTA(kCtaG + l - 1, Q0 + 2 * o + 1) = make_float4(gv[4], gv[5], gv[6], gv[7]);
           if (l > 1) {
-            tc::tmem_st8(a_hi + c * 8, hi);
-            tc::tmem_st8(a_lo + c * 8, lo);
+            op8(kSlabT + l - 1, o, tv);
+            a8_f16(o, tv);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 w = sm.w0[n0 + o * 8 + e];
+              gx = fmaf(w.x, tv[e], gx);
+              gy = fmaf(w.y, tv[e], gy);
+              gz = fmaf(w.z, tv[e], gz);
+            }
           }
-        }
-        if (l > 1) OI_A_READY();
+        }, wait_acc);
+        if (l > 1) a_ready();
       }
       // ---------------- combine the two column halves: normal ----------------
       float* xch = &sm.xch[t][m][0];
@@ -444,60 +493,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // ---------------- colour layer: recompute + backward; A <- u_bar_c (bf16) ----------------
       float nc0 = 0.f, nc1 = 0.f, nc2 = 0.f;   // W_cg^T u_bar_c, this thread's channels
       {
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][OI_MAX_DEPTH]) + n0 * 2;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hi[8], lo[8];
-          float dgs[16], sns[16];
+        const float4* fl = OI_FILM4(OI_MAX_DEPTH);
+        run_stage<2, false, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
+          b[0] = OI_CTA(kCtaUC, Q0 + 2 * o);
+          b[1] = OI_CTA(kCtaUC, Q0 + 2 * o + 1);
+        }, [&](int o, const uint32_t (&)[8], const float4 (&b)[2]) {
+          const float uc[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          float ub_[8], sn[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int quad = Q0 + c * 4 + q;
-            const float4 uc4 = OI_CTA(kCtaUC, quad);
-            const float uc[4] = {uc4.x, uc4.y, uc4.z, uc4.w};
-            float ar[4], ub_[4], dg[4];
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const float gp[2] = {f.x, f.y}, dl[2] = {f.z, f.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              const float4 hd = sm.head[n0 + j];
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = 2 * i + e2;
+              const float4 hd = sm.head[n0 + o * 8 + e];
               float pre = fmaf(hd.y, gx, uc[e]);
               pre = fmaf(hd.z, gy, pre);
               pre = fmaf(hd.w, gz, pre);
-              const float gp = flf[(j >> 1) * 4 + (j & 1)];
-              ar[e] = fmaf(gp, pre, flf[(j >> 1) * 4 + 2 + (j & 1)]);
-              const float cs = __cosf(ar[e]);
-              sns[q * 4 + e] = __sinf(ar[e]);
-              const float4 rw = sm.rgbw[n0 + j];
+              const float arg = fmaf(gp[e2], pre, dl[e2]);
+              const float cs = __cosf(arg);
+              sn[e] = __sinf(arg);
+              const float4 rw = sm.rgbw[n0 + o * 8 + e];
               const float hb = fmaf(rw.x, zb0, fmaf(rw.y, zb1, rw.z * zb2));
-              const float ab = hb * cs;
-              dg[e] = ab * ar[e];                              // a_bar * a_c  (see finalize_bwd_tc_kernel)
-              dgs[q * 4 + e] = dg[e];
-              ub_[e] = ab * (gp * kWScale);                    // u_bar_c = a_bar * gamma
+              ub_[e] = hb * cs * (gp[e2] * kWScale);               // u_bar_c = a_bar * gamma
               nc0 = fmaf(hd.y * kInvWScale, ub_[e], nc0);
               nc1 = fmaf(hd.z * kInvWScale, ub_[e], nc1);
               nc2 = fmaf(hd.w * kInvWScale, ub_[e], nc2);
             }
-            OI_OP4(kSlabUBC, c * 16 + q * 4, ub_[0], ub_[1], ub_[2], ub_[3]);
-            split2_bf16(ub_[0], ub_[1], hi[2 * q], lo[2 * q]);
-            split2_bf16(ub_[2], ub_[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
-          if (c == 3) OI_A_READY();   // the tensor core starts on W_cf^T u_bar_c while the column sums are reduced
-          const int nc = n0 + c * 16;
-          colsum16(dgs, dfilm + (size_t)OI_MAX_DEPTH * 2 * kW + nc, 1, lane);          // V_c = sum a_bar a
+          op8(kSlabUBC, o, ub_);
+          a8_bf16(o, ub_);
+          if (o == 7) a_ready();   // the tensor core starts on W_cf^T u_bar_c while the column sums are reduced
           {
-            float tmp[16];
+            float tmp[8];
+            const int nc = n0 + o * 8;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = zb0 * sns[i];
-            colsum16(tmp, a.g.rgb_weight + 0 * kW + nc, 1, lane);                       // dW_rgb = z_bar (x) h_c
+            for (int i = 0; i < 8; ++i) tmp[i] = zb0 * sn[i];
+            colsum8(tmp, a.g.rgb_weight + 0 * kW + nc, 1, lane);                       // dW_rgb = z_bar (x) h_c
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = zb1 * sns[i];
-            colsum16(tmp, a.g.rgb_weight + 1 * kW + nc, 1, lane);
+            for (int i = 0; i < 8; ++i) tmp[i] = zb1 * sn[i];
+            colsum8(tmp, a.g.rgb_weight + 1 * kW + nc, 1, lane);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = zb2 * sns[i];
-            colsum16(tmp, a.g.rgb_weight + 2 * kW + nc, 1, lane);
+            for (int i = 0; i < 8; ++i) tmp[i] = zb2 * sn[i];
+            colsum8(tmp, a.g.rgb_weight + 2 * kW + nc, 1, lane);
           }
-        }
+        }, wait_acc);
       }
       // normal_bar = direct + W_cg^T u_bar_c (both halves)
       xch[h * 4 + 1] = nc0;
@@ -511,201 +552,179 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         nb2 += nc2 + xch[o + 3];
       }
       if (h == 0) {
-        auxo[0 * 32 + ((mc ^ 0) << 2)] = tf32r(gx);
-        auxo[1 * 32 + ((mc ^ 1) << 2)] = tf32r(gy);
-        auxo[2 * 32 + ((mc ^ 2) << 2)] = tf32r(gz);
+        auxo[0 * 32 + ((mc ^ 0) << 2)] = tf32_bias(gx);
+        auxo[1 * 32 + ((mc ^ 1) << 2)] = tf32_bias(gy);
+        auxo[2 * 32 + ((mc ^ 2) << 2)] = tf32_bias(gz);
         auxo[3 * 32 + ((mc ^ 3) << 2)] = 1.0f;
       }
       // ---------------- h_bar_D = W_cf^T u_bar_c + sdf_bar w_s -> slot HB;
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
       {
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][0]) + n0 * 2;
-        OI_WAIT_ACC();
-        uint32_t ub[2][16];
-        tc::tmem_ld16_async(acc, ub[0]);
+        const float4* fl = OI_FILM4(0);
+        run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
+          b[0] = OI_ARG(0, Q0 + 2 * o);
+          b[1] = OI_ARG(0, Q0 + 2 * o + 1);
+          b[2] = OI_CTA(kCtaG + 0, Q0 + 2 * o);       // g_1
+          b[3] = OI_CTA(kCtaG + 0, Q0 + 2 * o + 1);
+        }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
+          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          const float g1[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+          float hb[8], cb[8], gb[8], t0[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tc::wait_ld();
-          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
-          const uint32_t(&u)[16] = ub[c & 1];
-          uint32_t hi[8], lo[8];
-          float t0s[16];
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const float gp[2] = {f.x, f.y};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int quad = Q0 + c * 4 + q;
-            float hb[4], cb[4], gb[4];
-            const float4 ar4 = OI_GS(kSlabArg + 0, quad);
-            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            const float4 g14 = OI_CTA(kCtaG + 0, quad);   // g_1
-            const float g1[4] = {g14.x, g14.y, g14.z, g14.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              hb[e] = fmaf(sdf_bar, sm.head[n0 + j].x * kInvWScale, __uint_as_float(u[q * 4 + e]));
-              const float4 w = sm.w0[n0 + j];
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = 2 * i + e2;
+              hb[e] = fmaf(sdf_bar, sm.head[n0 + o * 8 + e].x * kInvWScale, __uint_as_float(u[e]));
+              const float4 w = sm.w0[n0 + o * 8 + e];
               const float tb = fmaf(w.x, nb0, fmaf(w.y, nb1, w.z * nb2));   // t_bar_0 = W_0 normal_bar
-              const float c0 = flf[(j >> 1) * 4 + (j & 1)] * __cosf(ar[e]);  // gamma_0 cos a_0
+              const float c0 = gp[e2] * __cosf(ar[e]);                      // gamma_0 cos a_0
               cb[e] = tb * g1[e];
               gb[e] = tb * c0;
-              t0s[q * 4 + e] = g1[e] * c0;   // t_0
+              t0[e] = g1[e] * c0;   // t_0
             }
-            OI_CTA(kCtaHB, quad) = make_float4(hb[0], hb[1], hb[2], hb[3]);
-            OI_CTA(kCtaG + 0, quad) = make_float4(cb[0], cb[1], cb[2], cb[3]);   // c_bar_0
-            OI_OP4(kSlabGB + 1, c * 16 + q * 4, gb[0], gb[1], gb[2], gb[3]);
-            split2_bf16(gb[0], gb[1], hi[2 * q], lo[2 * q]);
-            split2_bf16(gb[2], gb[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
-          if (c == 3) OI_A_READY();
-          {  // dW_0 += t_0 (x) normal_bar
-            float* dst = a.g.pts_weight[0] + (size_t)(n0 + c * 16) * 3;
-            float tmp[16];
+          OI_CTA(kCtaHB, Q0 + 2 * o) = make_float4(hb[0], hb[1], hb[2], hb[3]);
+          OI_CTA(kCtaHB, Q0 + 2 * o + 1) = make_float4(hb[4], hb[5], hb[6], hb[7]);
+          OI_CTA(kCtaG + 0, Q0 + 2 * o) = make_float4(cb[0], cb[1], cb[2], cb[3]);   // c_bar_0
+          OI_CTA(kCtaG + 0, Q0 + 2 * o + 1) = make_float4(cb[4], cb[5], cb[6], cb[7]);
+          op8(kSlabGB + 1, o, gb);
+          a8_bf16(o, gb);
+          if (o == 7) a_ready();
+          {  // dW_0 += t_0 (x) normal_bar (per instance)
+            float* dst = dw0 + (size_t)(n0 + o * 8) * 3;
+            float tmp[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = nb0 * t0s[i];
-            colsum16(tmp, dst + 0, 3, lane);
+            for (int i = 0; i < 8; ++i) tmp[i] = nb0 * t0[i];
+            colsum8(tmp, dst + 0, 3, lane);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = nb1 * t0s[i];
-            colsum16(tmp, dst + 1, 3, lane);
+            for (int i = 0; i < 8; ++i) tmp[i] = nb1 * t0[i];
+            colsum8(tmp, dst + 1, 3, lane);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = nb2 * t0s[i];
-            colsum16(tmp, dst + 2, 3, lane);
+            for (int i = 0; i < 8; ++i) tmp[i] = nb2 * t0[i];
+            colsum8(tmp, dst + 2, 3, lane);
           }
-        }
+        }, wait_acc);
       }
-      // ---------------- backward of the reverse sweep, l = 1..D-1: t_bar_l = W_l g_bar_l ----------------
-      for (int l = 1; l < D; ++l) {
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][l]) + n0 * 2;
-        const int gslab = (l < D - 1) ? kCtaG + l : kCtaHB;   // g_{l+1}, or h_bar_D at the top
-        OI_WAIT_ACC();
-        uint32_t ub[2][16];
-        tc::tmem_ld16_async(acc, ub[0]);
+      // ---------------- backward of the reverse sweep, l = 1..D-2: t_bar_l = W_l g_bar_l ----------------
+      for (int l = 1; l < D - 1; ++l) {
+        const float4* fl = OI_FILM4(l);
+        run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
+          b[0] = OI_ARG(l, Q0 + 2 * o);
+          b[1] = OI_ARG(l, Q0 + 2 * o + 1);
+          b[2] = OI_CTA(kCtaG + l, Q0 + 2 * o);       // g_{l+1}
+          b[3] = OI_CTA(kCtaG + l, Q0 + 2 * o + 1);
+        }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
+          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          const float gn[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+          float cb[8], gb[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tc::wait_ld();
-          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
-          const uint32_t(&u)[16] = ub[c & 1];
-          uint32_t hi[8], lo[8];
-          float dgs[16], dwss[16];
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const float2 gam = tc::mul2(make_float2(f.x, f.y), make_float2(kWScale, kWScale));
+            const float tb0 = __uint_as_float(u[2 * i]), tb1 = __uint_as_float(u[2 * i + 1]);
+            cb[2 * i] = tb0 * gn[2 * i];                                  // c_bar_l
+            cb[2 * i + 1] = tb1 * gn[2 * i + 1];
+            gb[2 * i] = tb0 * gam.x * __cosf(ar[2 * i]);                 // g_bar_{l+1}
+            gb[2 * i + 1] = tb1 * gam.y * __cosf(ar[2 * i + 1]);
+          }
+          OI_CTA(kCtaG + l, Q0 + 2 * o) = make_float4(cb[0], cb[1], cb[2], cb[3]);
+          OI_CTA(kCtaG + l, Q0 + 2 * o + 1) = make_float4(cb[4], cb[5], cb[6], cb[7]);
+          op8(kSlabGB + l + 1, o, gb);
+          a8_bf16(o, gb);
+        }, wait_acc);
+        a_ready();
+      }
+      // ---------------- top, l = D-1: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
+      {
+        const int l = D - 1;
+        const float4* fl = OI_FILM4(l);
+        run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
+          b[0] = OI_ARG(l, Q0 + 2 * o);
+          b[1] = OI_ARG(l, Q0 + 2 * o + 1);
+          b[2] = OI_CTA(kCtaHB, Q0 + 2 * o);          // h_bar_D
+          b[3] = OI_CTA(kCtaHB, Q0 + 2 * o + 1);
+        }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
+          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          const float hb[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+          float ubv[8], dws[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = OI_GS(kSlabArg + l, quad);
-            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            float o[4];
-            if (l < D - 1) {
-              const float4 g4 = OI_CTA(gslab, quad);   // g_{l+1}
-              const float gn[4] = {g4.x, g4.y, g4.z, g4.w};
-              float cb[4];
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const float gp[2] = {f.x * kWScale, f.y * kWScale};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = c * 16 + q * 4 + e;
-                const float tb = __uint_as_float(u[q * 4 + e]);
-                cb[e] = tb * gn[e];                                                     // c_bar_l
-                o[e] = tb * (flf[(j >> 1) * 4 + (j & 1)] * kWScale) * __cosf(ar[e]);    // g_bar_{l+1}
-              }
-              OI_CTA(kCtaG + l, quad) = make_float4(cb[0], cb[1], cb[2], cb[3]);
-              OI_OP4(kSlabGB + l + 1, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
-            } else {
-              // top: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
-              const float4 hb4 = OI_CTA(gslab, quad);   // h_bar_D
-              const float hb[4] = {hb4.x, hb4.y, hb4.z, hb4.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = c * 16 + q * 4 + e;
-                const float tb = __uint_as_float(u[q * 4 + e]);
-                const float gam = flf[(j >> 1) * 4 + (j & 1)] * kWScale;
-                const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
-                dwss[q * 4 + e] = fmaf(sdf_bar, sn, tb * gam * cs);   // d w_s = sdf_bar h_D + t_bar_{D-1} c_{D-1}
-                const float cbar = tb * (sm.head[n0 + j].x * kInvWScale);
-                const float ab = hb[e] * cs - cbar * gam * sn;
-                dgs[q * 4 + e] = fmaf(ab, ar[e], gam * (cbar * cs));
-                o[e] = ab * gam;   // u_bar_{D-1}
-              }
-              OI_OP4(kSlabUB + l, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = 2 * i + e2;
+              const float tb = __uint_as_float(u[e]);
+              const float gam = gp[e2];
+              const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
+              dws[e] = fmaf(sdf_bar, sn, tb * gam * cs);   // d w_s = sdf_bar h_D + t_bar_{D-1} c_{D-1}
+              const float cbar = tb * (sm.head[n0 + o * 8 + e].x * kInvWScale);
+              const float ab = hb[e] * cs - cbar * gam * sn;
+              ubv[e] = ab * gam;   // u_bar_{D-1}
             }
-            split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
-            split2_bf16(o[2], o[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
-          if (c == 3) OI_A_READY();
-          if (l == D - 1) {
-            colsum16(dwss, a.g.sigma_weight + n0 + c * 16, 1, lane);
-            colsum16(dgs, dfilm + (size_t)l * 2 * kW + n0 + c * 16, 1, lane);   // V_{D-1}
-          }
-        }
+          op8(kSlabUB + l, o, ubv);
+          a8_bf16(o, ubv);
+          if (o == 7) a_ready();
+          colsum8(dws, a.g.sigma_weight + n0 + o * 8, 1, lane);
+        }, wait_acc);
       }
       // ---------------- backward of the forward sweep: h_bar_l = W_l^T u_bar_l, then layer k = l-1 ----------------
       for (int l = D - 1; l >= 1; --l) {
         const int k = l - 1;
-        const float* flf = reinterpret_cast<const float*>(sm.film[t][k]) + n0 * 2;
+        const float4* fl = OI_FILM4(k);
         const float gsc = (k == 0) ? 1.0f : kWScale;
-        OI_WAIT_ACC();
-        uint32_t ub[2][16];
-        tc::tmem_ld16_async(acc, ub[0]);
+        run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
+          b[0] = OI_ARG(k, Q0 + 2 * o);
+          b[1] = OI_ARG(k, Q0 + 2 * o + 1);
+          b[2] = OI_CTA(kCtaG + k, Q0 + 2 * o);       // c_bar_k
+          b[3] = OI_CTA(kCtaG + k, Q0 + 2 * o + 1);
+        }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
+          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          const float cb[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+          float ubv[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tc::wait_ld();
-          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
-          const uint32_t(&u)[16] = ub[c & 1];
-          uint32_t hi[8], lo[8];
-          float dgs[16], ubs[16];
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = fl[o * 4 + i];
+            const float gp[2] = {f.x * gsc, f.y * gsc};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int quad = Q0 + c * 4 + q;
-            const float4 ar4 = OI_GS(kSlabArg + k, quad);
-            const float ar[4] = {ar4.x, ar4.y, ar4.z, ar4.w};
-            const float4 cb4 = OI_CTA(kCtaG + k, quad);   // c_bar_k
-            const float cb[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              const float gam = flf[(j >> 1) * 4 + (j & 1)] * gsc;
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = 2 * i + e2;
+              const float gam = gp[e2];
               const float sn = __sinf(ar[e]), cs = __cosf(ar[e]);
-              const float ab = __uint_as_float(u[q * 4 + e]) * cs - cb[e] * gam * sn;
-              dgs[q * 4 + e] = fmaf(ab, ar[e], gam * (cb[e] * cs));
-              o[e] = ab * gam;   // u_bar_k
-              ubs[q * 4 + e] = o[e];
-            }
-            if (k >= 1) {
-              OI_OP4(kSlabUB + k, c * 16 + q * 4, o[0], o[1], o[2], o[3]);
-              split2_bf16(o[0], o[1], hi[2 * q], lo[2 * q]);
-              split2_bf16(o[2], o[3], hi[2 * q + 1], lo[2 * q + 1]);
+              const float ab = __uint_as_float(u[e]) * cs - cb[e] * gam * sn;
+              ubv[e] = ab * gam;   // u_bar_k
             }
           }
           if (k >= 1) {
-            tc::tmem_st8(a_hi + c * 8, hi);
-            tc::tmem_st8(a_lo + c * 8, lo);
-            if (c == 3) OI_A_READY();
+            op8(kSlabUB + k, o, ubv);
+            a8_bf16(o, ubv);
+          } else {
+            const int nc = n0 + o * 8;
+            colsum8(ubv, dfilm + kW + nc, 1, lane);                  // d b_0 = sum u_bar_0
+            float* dst = dw0 + (size_t)nc * 3;                       // dW_0 += u_bar_0 (x) x (per instance)
+            float tmp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tmp[i] = px * ubv[i];
+            colsum8(tmp, dst + 0, 3, lane);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tmp[i] = py * ubv[i];
+            colsum8(tmp, dst + 1, 3, lane);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tmp[i] = pz * ubv[i];
+            colsum8(tmp, dst + 2, 3, lane);
           }
-          const int nc = n0 + c * 16;
-          colsum16(dgs, dfilm + (size_t)k * 2 * kW + nc, 1, lane);   // V_k = sum a_bar a + gamma c_bar cos a
-          if (k == 0) {
-            colsum16(ubs, dfilm + kW + nc, 1, lane);                  // d b_0 = sum u_bar_0
-            float* dst = a.g.pts_weight[0] + (size_t)nc * 3;          // dW_0 += u_bar_0 (x) x
-            float tmp[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = px * ubs[i];
-            colsum16(tmp, dst + 0, 3, lane);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = py * ubs[i];
-            colsum16(tmp, dst + 1, 3, lane);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) tmp[i] = pz * ubs[i];
-            colsum16(tmp, dst + 2, 3, lane);
-          }
-        }
+        }, wait_acc);
+        if (k >= 1) a_ready();
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);   // film table / exchange buffer of this slot may be reused now
     }
+#undef OI_ARG
 #undef OI_CTA
-#undef OI_GS
-#undef OI_OP
-#undef OI_OP4
-#undef OI_A_READY
-#undef OI_WAIT_ACC
+#undef OI_FILM4
   }
 
   tc::fence_before_thread_sync();
@@ -713,26 +732,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
   if (warp == kProducerWarp) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// TC variant of the finalize step.  The sweep kernel reduces V = sum_m a_bar a + gamma c_bar cos a and the
-// contraction kernel db = sum_m u_bar = gamma sum_m a_bar per instance; with a = gamma u + beta:
-//   dL/dbeta = db / gamma,   dL/dgamma = sum_m a_bar u + c_bar cos a = (V - beta db / gamma) / gamma,
-// db is summed over instances into the bias gradient; plus the variance.
+// Finalize of the tensor-core backward.  Inputs: the per-instance weight gradients dW_l (both parts) left by the
+// contraction kernel (l >= 1, colour) and by the sweep kernel's butterflies (l = 0), and db = sum_m u_bar per
+// instance.  With a = gamma u + beta, u = W h + b (see the header of this file):
+//   dL/dbeta = db / gamma,    dL/dgamma = ( sum_k W[j][k] dW[j][k] + b[j] db[j] ) / gamma,
+// db and dW are summed over the instances into the bias / weight gradients; plus the variance.
+// Block l = 0..D-1: pts_linears[l]; block D: views_linears; block D+1: variance.  Thread = output channel j.
 __global__ void finalize_bwd_tc_kernel(int D, int n_inst, int R, const float* __restrict__ film,
                                        const float* __restrict__ d_film, const float* __restrict__ invs_partial,
-                                       const float* __restrict__ blob, OiNetGrads g) {
+                                       const float* __restrict__ blob, const float* __restrict__ dwi,
+                                       const float* __restrict__ dwc, const float* __restrict__ dw0, OiNetGrads g) {
   const int n = threadIdx.x;
   const int l = blockIdx.x;
+  const BlobLayout L = blob_layout(D);
+  const float* cst = blob + L.const_off;
+  const float* stream = blob + L.stream_off;
   if (l <= D) {
     const int slot = (l < D) ? l : OI_MAX_DEPTH;
+    const float bias = cst[BlobLayout::kBias + slot * kW + n];
     float s = 0.f;
     for (int i = 0; i < n_inst; ++i) {
+      float dot = 0.f;
+      if (l == 0) {
+        const float* row = dw0 + ((size_t)i * kW + n) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float v = row[k];
+          dot = fmaf(cst[BlobLayout::kW0t + k * kW + n], v, dot);
+          g.pts_weight[0][n * 3 + k] += v;
+        }
+      } else if (l < D) {
+        const float4* row = reinterpret_cast<const float4*>(dwi + (((size_t)i * (D - 1) + (l - 1)) * kW + n) * kW);
+        const float4* wr = reinterpret_cast<const float4*>(stream + (size_t)(1 + 8 * (2 * D - 1 - l)) * kChunkFloats +
+                                                           (size_t)n * kW);   // W_l as stored: row = output channel
+        float4* out = reinterpret_cast<float4*>(g.pts_weight[l] + (size_t)n * kW);
+        for (int k = 0; k < kW / 4; ++k) {
+          const float4 v = row[k], w = wr[k];
+          dot = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, dot))));
+          float4 o = out[k];
+          o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+          out[k] = o;
+        }
+      } else {
+        const float* row = dwc + ((size_t)i * kW + n) * (kW + 3);
+        const float* wr = stream + (size_t)(1 + 8 * (2 * D - 1)) * kChunkFloats + (size_t)n * kW;   // W_c[:, :128] as stored
+        float* out = g.views_weight + (size_t)n * (kW + 3);
+        for (int k = 0; k < kW; ++k) {
+          const float v = row[k];
+          dot = fmaf(wr[k], v, dot);
+          out[k] += v;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float v = row[kW + k];
+          dot = fmaf(cst[BlobLayout::kWcg + k * kW + n], v, dot);
+          out[kW + k] += v;
+        }
+      }
       const size_t o = ((size_t)i * kFilm + slot) * 2 * kW;
-      const float db = d_film[o + kW + n], V = d_film[o + n];
-      const float gam = film[o + n], bet = film[o + kW + n];
-      const float dbeta = db / gam;
+      const float db = d_film[o + kW + n];
+      const float gam = film[o + n];
       s += db;
-      g.film_gamma[((size_t)i * kFilm + slot) * kW + n] += (V - bet * dbeta) / gam;
-      g.film_beta[((size_t)i * kFilm + slot) * kW + n] += dbeta;
+      g.film_gamma[((size_t)i * kFilm + slot) * kW + n] += fmaf(bias, db, dot) / gam;
+      g.film_beta[((size_t)i * kFilm + slot) * kW + n] += db / gam;
     }
     float* dst = (l < D) ? g.pts_bias[l] : g.views_bias;
     dst[n] += s;
@@ -744,8 +806,7 @@ __global__ void finalize_bwd_tc_kernel(int D, int n_inst, int R, const float* __
     if ((n & 31) == 0) red[n >> 5] = s;
     __syncthreads();
     if (n == 0) {
-      const BlobLayout L = blob_layout(D);
-      const float inv_s = blob[L.const_off + BlobLayout::kScalars + 4];
+      const float inv_s = cst[BlobLayout::kScalars + 4];
       const double tot = red[0] + red[1] + red[2] + red[3];
       const bool inside = inv_s > 1e-6f && inv_s < 1e6f;
       if (inside) g.variance[0] += (float)(tot * 10.0 * (double)inv_s);
@@ -765,10 +826,14 @@ int render_bwd_tc_ctas(int n_tiles) {
 }
 size_t render_bwd_tc_scratch_floats() { return (size_t)2 * kCtaSlabs * kSlabFloats; }
 size_t render_bwd_tc_slab_floats_per_tile() { return (size_t)kSlabsPerTile * kSlabFloats + 512; }
+// per-instance weight gradients: [n_inst][D-1][128][128] | [n_inst][128][131] | [n_inst][128][3]
+size_t render_bwd_tc_dw_floats(int n_inst, int depth) {
+  return (size_t)n_inst * ((size_t)(depth - 1) * kW * kW + (size_t)kW * (kW + 3) + (size_t)kW * 3) + 16;
+}
 
 // Runs the two tensor-core kernels over tiles [0, n_tiles) in chunks of at most `chunk_tiles`.
 int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
-                         float* d_film, float* scratch, float* slabs, float* aux, int chunk_tiles,
+                         float* d_film, float* scratch, float* slabs, float* aux, float* dw_inst, int chunk_tiles,
                          int n_ctas, cudaStream_t st) {
   const int n_inst = geo.n_inst, D = geo.D;
   OI_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -776,6 +841,10 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float* dwi = dw_inst;
+  float* dwc = dwi + (((size_t)n_inst * (D - 1) * kW * kW + 3) & ~(size_t)3);
+  float* dw0 = dwc + (((size_t)n_inst * kW * (kW + 3) + 3) & ~(size_t)3);
+  OI_CHECK_CUDA(cudaMemsetAsync(dw_inst, 0, render_bwd_tc_dw_floats(n_inst, D) * sizeof(float), st));
 
   if (d.evt_core_start) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d.evt_core_start), st));
   for (int t0 = 0; t0 < geo.n_tiles; t0 += chunk_tiles) {
@@ -791,11 +860,12 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     a.tile_end = t1;
     a.g = d.grads;
     a.d_film = d_film;
+    a.dw0 = dw0;
     const int ctas = render_bwd_tc_ctas(t1 - t0) < n_ctas ? render_bwd_tc_ctas(t1 - t0) : n_ctas;
     bwd_tc_kernel<<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
     OI_CHECK_CUDA(cudaGetLastError());
 
-    // ---- contraction over the points of this chunk
+    // ---- contraction over the points of this chunk (per-instance outputs: the finalize kernel needs them)
     WgArgs w;
     memset(&w, 0, sizeof(w));
     w.n_tiles = t1 - t0;
@@ -817,7 +887,8 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
       g.aux_out[3] = dbia(l);                           // d b_l = sum u_bar_l  (aux column 3 = 1)
       g.aux_inst_stride[3] = inst_stride;
       g.aux_ch_stride[3] = 1;
-      g.out = d.grads.pts_weight[l];
+      g.out = dwi + (size_t)(l - 1) * kW * kW;
+      g.out_inst_stride = (D - 1) * kW * kW;
       g.out_ld = kW;
       g.weight = 4;
     }
@@ -827,14 +898,15 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
       g.pairs[0] = WgPair{kSlabUBC, kSlabH + D};
       g.use_aux = 1;
       for (int j = 0; j < 3; ++j) {
-        g.aux_out[j] = d.grads.views_weight + kW + j;
-        g.aux_inst_stride[j] = 0;
+        g.aux_out[j] = dwc + kW + j;
+        g.aux_inst_stride[j] = kW * (kW + 3);
         g.aux_ch_stride[j] = kW + 3;
       }
       g.aux_out[3] = dbia(OI_MAX_DEPTH);
       g.aux_inst_stride[3] = inst_stride;
       g.aux_ch_stride[3] = 1;
-      g.out = d.grads.views_weight;
+      g.out = dwc;
+      g.out_inst_stride = kW * (kW + 3);
       g.out_ld = kW + 3;
       g.weight = 2;
     }
@@ -845,7 +917,8 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
   }
   if (d.evt_core_stop) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d.evt_core_stop), st));
 
-  finalize_bwd_tc_kernel<<<D + 2, kW, 0, st>>>(D, n_inst, d.n_rays, geo.film, d_film, invs_partial, geo.blob, d.grads);
+  finalize_bwd_tc_kernel<<<D + 2, kW, 0, st>>>(D, n_inst, d.n_rays, geo.film, d_film, invs_partial, geo.blob, dwi, dwc,
+                                               dw0, d.grads);
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

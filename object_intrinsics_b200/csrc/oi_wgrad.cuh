@@ -28,8 +28,9 @@ struct WgPair {
 struct WgGroup {
   int n_pairs;      // operand pairs accumulated into the same matrix (1 or 2)
   WgPair pairs[2];
-  float* out;       // [128][out_ld], accumulated with reductions
+  float* out;       // [128][out_ld] per instance (instance i at out + i * out_inst_stride), accumulated with reductions
   int out_ld;
+  int out_inst_stride;   // floats; 0 = one matrix shared by all instances
   // narrow products of the X operand of pair 0 with the aux columns: aux_out[c][inst * inst_stride + i * ch_stride]
   // += sum_m X[m][i] aux[m][c]; NULL entries are skipped, aux_out == all NULL disables the extra MMA
   float* aux_out[4];

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       if (inst == cur_inst) continue;
       mbar_wait_sleep(&sm.acc_done, seg & 1, 1000u);
       tc::fence_after_thread_sync();
-      float* row = G.out + (size_t)i * G.out_ld;
+      float* row = G.out + (size_t)cur_inst * G.out_inst_stride + (size_t)i * G.out_ld;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float u[32];

@@ -77,3 +77,27 @@ def test_manual_backward_two_instances():
     for k, ga in zip(keys + ["w"], g_auto):
         scale = float(ga.abs().max()) + 1e-30
         assert float((g_man[k].reshape(ga.shape) - ga).abs().max()) / scale < 1e-9, k
+
+
+def test_dgamma_identity_used_by_the_tensor_core_backward():
+    """csrc/oi_render_bwd_tc.cu takes dL/dgamma from the (per-instance) weight gradients instead of per-point column
+    sums:  dgamma_l[j] = ( sum_k W_l[j][k] dW_l[j][k] + b_l[j] db_l[j] ) / gamma_l[j]   (same for the colour layer).
+    Checked here in fp64 against the reverse sweep's own dgamma (which test_manual_backward_matches_autograd pins to
+    torch.autograd)."""
+    torch.manual_seed(3)
+    meta, P, r, a, w, z_vals = _setup("cfgd_n16_m4_D8", 24, 1.0)
+    D = meta["D"]
+    named = dict(torch_graph.collect_params(r.sdf_network, r.color_network, r.deviation_network, with_style=False))
+    Pd = {k: v.detach() for k, v in named.items()}
+    R, S = z_vals.shape
+    adj = {"color_fine": torch.randn(R, 3, dtype=torch.float64), "weight_sum": torch.randn(R, 1, dtype=torch.float64),
+           "gradients": torch.randn(R, S, 3, dtype=torch.float64), "weights": torch.randn(R, S, dtype=torch.float64),
+           "gradient_error": torch.tensor(3.0, dtype=torch.float64)}
+    g = B.manual_backward(Pd, D, a["rays_o"], a["rays_d"], z_vals, w.detach(), 1.0, meta["n_samples"], adj)
+    gam, _ = B.film_tables(Pd, D, w.detach())
+    layers = [(l, f"sdf_network.pts_linears.{l}") for l in range(D)] + [(8, "color_network.views_linears")]
+    for slot, pre in layers:
+        W, b = Pd[pre + ".weight"], Pd[pre + ".bias"]
+        ident = ((W * g[pre + ".weight"]).sum(-1) + b * g[pre + ".bias"]) / gam[0, slot]     # one instance
+        ref = g["film_gamma"][0, slot]
+        assert float((ident - ref).abs().max()) <= 1e-11 * float(ref.abs().max()), pre
