@@ -476,7 +476,7 @@ def train_step_leg(dev, P, kernel, flush):
     """Rank 0: a training-shaped composition of the path's kernels (no trainer code), mirroring
     src/trainers/gan_pose_trainer.py:77-101 -- implemented in tools_train_step.py so that it can be profiled alone."""
     import tools_train_step as T
-    return T.measure(dev, P, kernel, flush)
+    return {s: T.measure(dev, P, kernel, flush, s) for s in ("cfg5", "cfg3")}
 
 
 if __name__ == "__main__":
