@@ -210,6 +210,23 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, uint32_
       "r"(parity), "r"(hint_ns)
       : "memory");
 }
+// Polling with back-off: a failed probe parks the warp for `sleep_ns` (nanosleep) before the next one.  For the
+// single-lane service warps (TMA producer, MMA issuers): their probes otherwise take MIO-queue and issue slots from
+// the epilogue warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, uint32_t parity, uint32_t sleep_ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "nanosleep.u32 %2;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(sleep_ns)
+      : "memory");
+}
 // Drops a 128-byte line from L2 without writing it back (the data is dead: read-once scratch).
 __device__ __forceinline__ void l2_discard_128(const void* p) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");

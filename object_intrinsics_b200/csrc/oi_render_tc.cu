@@ -9,9 +9,15 @@
 //     consumed from TMEM (.ts form) -- activations never touch shared memory;
 //   * B panels (64 KB per layer: {hi,lo} x 2 k-blocks, K-major SWIZZLE_128B images) are streamed from L2 by
 //     TMA bulk copies through a 3-stage mbarrier ring and are shared by both tiles;
-//   * per TMEM lane, one thread does the FiLM epilogue: sincos, split, tcgen05.st of the next operand,
-//     gamma*cos to the reverse-sweep scratch; while tile 0 is in its epilogue the tensor core works on tile 1.
-// Warp roles: 0-3 epilogue of tile 0, 4-7 epilogue of tile 1, 8 TMA producer, 9 MMA issuer.
+//   * per TMEM lane, two threads (64 channels each) do the FiLM epilogue in four 16-channel chunks: sincos, split,
+//     tcgen05.st of the next operand, gamma*cos to the reverse-sweep scratch;
+//   * a tile slot owns two 128-column TMEM buffers used as a ping-pong: the epilogue of stage s reads the
+//     accumulator from buffer s&1 and writes the split operand of the next layer IN PLACE over the 16 columns it has
+//     just consumed (8 packed hi + 8 packed lo); the MMAs of stage s read that operand and accumulate into the other
+//     buffer.  The k-blocks of a chunk are issued as soon as the chunk is stored, so a slot's tensor work runs
+//     behind its own epilogue (only the last 6 of the 24 MMAs of a layer are exposed) and the other slot fills the
+//     rest.
+// Warp roles: 0-7 epilogue of tile slot 0, 8-15 of slot 1, 16 TMA producer, 17 / 18 MMA issuer of slot 0 / 1.
 #include "oi_internal.cuh"
 #include "oi_render_common.cuh"
 #include "oi_tc.cuh"
@@ -20,9 +26,10 @@ namespace oi {
 
 namespace {
 
-constexpr int kTcThreads = 576;            // 16 epilogue warps + TMA producer + MMA issuer
+constexpr int kTcThreads = 608;            // 16 epilogue warps + TMA producer + one MMA issuer per tile slot
 constexpr int kEpiThreadsPerSlot = 256;     // 8 warps per tile slot
-constexpr int kProducerWarp = 16, kMmaWarp = 17;
+constexpr int kEpiWarpsPerSlot = 8;
+constexpr int kProducerWarp = 16, kMmaWarp = 17;   // MMA issuer of slot t = warp kMmaWarp + t
 constexpr int kTcStages = 3;
 constexpr int kPanelBytes = 65536;
 constexpr int kSubPanelBytes = 16384;
@@ -38,7 +45,7 @@ struct __align__(1024) TcSmem {
   float4 rgbw[kW];                          // (W_rgb[0..2][n], 0)
   unsigned long long w_full[kTcStages], w_empty[kTcStages];
   float xch[2][128][8];                     // per slot / point: partial sums exchanged between the column halves
-  unsigned long long acc_full[2], a_ready[2];
+  unsigned long long acc_full[2], a_ready[2][4];   // a_ready[slot][chunk]: one arrival per epilogue warp
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB per-CTA limit");
@@ -66,7 +73,10 @@ __device__ __forceinline__ void sin_film(float x, float* s) {
 #endif
 }
 __device__ __forceinline__ void sincos_tc(float x, float* s, float* c) {
-#if OI_TC_SINCOS_REDUCE
+#if OI_TC_X_NOMUFU   // timing experiment (invalid render)
+  *s = x * 0.5f;
+  *c = x * 0.25f;
+#elif OI_TC_SINCOS_REDUCE
   sincos_film(x, s, c);
 #else
   *s = __sinf(x);
@@ -76,9 +86,40 @@ __device__ __forceinline__ void sincos_tc(float x, float* s, float* c) {
 
 using tc::named_bar_sync;
 
+#if OI_TC_X_NOSPLIT   // timing experiment (invalid render): no conversion instructions
+__device__ __forceinline__ void split2x(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v0);
+  lo = __float_as_uint(v1);
+}
+#else
+__device__ __forceinline__ void split2x(float v0, float v1, uint32_t& hi, uint32_t& lo) { tc::split2(v0, v1, hi, lo); }
+#endif
+
+// nanosleep back-off of the single-lane service warps between mbarrier probes (ns)
+#ifndef OI_TC_SLEEP_PRODUCER
+#define OI_TC_SLEEP_PRODUCER 400u
+#endif
+#ifndef OI_TC_SLEEP_MMA
+#define OI_TC_SLEEP_MMA 100u
+#endif
+
 // 24 MMAs of one layer of one tile: acc = hi*Whi + lo*Whi + hi*Wlo over K = 128 (fp16 split operands).
 __device__ __forceinline__ void issue_layer_mmas(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wbase) {
   tc::issue_split_layer_mmas(acc, a_hi, a_lo, wbase, kIdesc);
+}
+
+// The 6 MMAs that consume epilogue chunk c of both column halves: k-blocks c (channels 16c..16c+15) and 4 + c
+// (channels 64+16c..).  Operand of k-block k in the in-place layout: hi = abuf + 16k (8 packed columns), lo = +8.
+__device__ __forceinline__ void issue_chunk_mmas(uint32_t acc, uint32_t abuf, uint32_t wbase, int c) {
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+    const uint64_t bhi = tc::make_desc_k_sw128(wbase + kb * kSubPanelBytes + c * 32);
+    const uint64_t blo = tc::make_desc_k_sw128(wbase + 2 * kSubPanelBytes + kb * kSubPanelBytes + c * 32);
+    const uint32_t a_hi = abuf + 16 * (kb * 4 + c), a_lo = a_hi + 8;
+    tc::mma_ts(acc, a_hi, bhi, kIdesc, (c > 0 || kb > 0) ? 1u : 0u);
+    tc::mma_ts(acc, a_lo, bhi, kIdesc, 1u);
+    tc::mma_ts(acc, a_hi, blo, kIdesc, 1u);
+  }
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKArgs a) {
@@ -95,10 +136,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&sm.w_full[s], 1);
-      mbar_init(&sm.w_empty[s], 1);
+      mbar_init(&sm.w_empty[s], 2);     // released by both MMA issuers
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&sm.a_ready[t], kEpiThreadsPerSlot);
+      for (int c = 0; c < 4; ++c) mbar_init(&sm.a_ready[t][c], kEpiWarpsPerSlot);
       mbar_init(&sm.acc_full[t], 1);
     }
     mbar_fence_init();
@@ -126,7 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
         for (int p = 0; p < NP; ++p, ++it) {
           const int stage = it % kTcStages;
-          if (it >= kTcStages) mbar_wait_sleep(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1);
+          if (it >= kTcStages) mbar_wait_backoff(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1, OI_TC_SLEEP_PRODUCER);
           mbar_expect_tx(&sm.w_full[stage], kPanelBytes);
           const unsigned char* src = panels + (size_t)p * kPanelBytes;
 #pragma unroll
@@ -135,27 +176,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
+  } else if (warp >= kMmaWarp) {
+    // ===================== MMA issuer of tile slot t =====================
     if (lane == 0) {
+      const int t = warp - kMmaWarp;
+      const uint32_t buf = tmem_base + t * 256;
       int it = 0;
-      uint32_t ar_phase[2] = {0u, 0u};
+      uint32_t ar_phase = 0u;
       for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
-        const int n_active = (2 * pi + 1 < a.n_tiles) ? 2 : 1;
+#if OI_TC_X_ONESLOT   // timing experiment: slot 1 idle, half of the tiles are skipped
+        const bool active = 2 * pi + t < a.n_tiles && t == 0;
+#else
+        const bool active = 2 * pi + t < a.n_tiles;
+#endif
         for (int p = 0; p < NP; ++p, ++it) {
           const int stage = it % kTcStages;
-          mbar_wait_sleep(&sm.w_full[stage], (it / kTcStages) & 1);
-          const uint32_t wbase = smem_u32(sm.w[stage]);
-          for (int t = 0; t < n_active; ++t) {
-            mbar_wait_sleep(&sm.a_ready[t], ar_phase[t], 2000u);
-            ar_phase[t] ^= 1u;
-            tc::fence_after_thread_sync();
-            const uint32_t acc = tmem_base + t * 256;
-            // The whole layer is committed at once: the A operand is overwritten in place by the epilogue, so
-            // the epilogue must not start before every MMA that reads it has completed.
-            issue_layer_mmas(acc, acc + 128, acc + 192, wbase);
-            tc::mma_commit(&sm.acc_full[t]);
+          mbar_wait_backoff(&sm.w_full[stage], (it / kTcStages) & 1, OI_TC_SLEEP_MMA);
+          if (!active) {   // odd tile count: the idle slot only releases the panel
+            mbar_arrive(&sm.w_empty[stage]);
+            continue;
           }
+          const uint32_t wbase = smem_u32(sm.w[stage]);
+          const uint32_t abuf = buf + (p & 1) * 128, acc = buf + ((p + 1) & 1) * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait_backoff(&sm.a_ready[t][c], ar_phase, OI_TC_SLEEP_MMA);
+            tc::fence_after_thread_sync();
+            issue_chunk_mmas(acc, abuf, wbase, c);
+          }
+          ar_phase ^= 1u;
+          tc::mma_commit(&sm.acc_full[t]);
           tc::mma_commit(&sm.w_empty[stage]);
         }
       }
@@ -170,20 +220,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     const int sub = tid & (kEpiThreadsPerSlot - 1);
     const int n0 = h * 64;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t acc = tmem_base + t * 256 + lane_field + n0;          // my 64 accumulator columns
-    const uint32_t a_hi = tmem_base + t * 256 + lane_field + 128 + h * 32;  // my 32 packed A_hi columns
-    const uint32_t a_lo = a_hi + 64;
+    // my 64 columns of the slot's two ping-pong buffers: stage s reads its accumulator from buf[s & 1] and writes
+    // the next operand in place (chunk c: 8 packed hi columns at +16c, 8 packed lo columns at +16c+8)
+    const uint32_t buf0 = tmem_base + t * 256 + lane_field + n0;
     // scratch of this tile slot: (D+1) slots of [32 channel-quads][128 points] float4; mine: quads 16h..16h+15
     float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
                                              (size_t)t * (D + 1) * kW * 128) + (size_t)(h * 16) * 128 + m;
     const bool discard = (a.flags & 1) != 0 && (m & 7) == 0;
     uint32_t af_phase = 0u;
-#define OI_SLOT(slot, q) scr4[((size_t)(slot) * 32 + (q)) * 128]
-#define OI_A_READY()               \
+    int film_inst = -1;
+#ifdef OI_TC_PROFILE   // developer build: cycles per phase of one epilogue warp per slot (block 0), printed at exit
+    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#define OI_PROF(i)                 \
   do {                             \
-    tc::wait_st();                 \
-    tc::fence_before_thread_sync(); \
-    mbar_arrive(&sm.a_ready[t]);   \
+    const long long now = clock64(); \
+    prof[i] += now - prof_t;       \
+    prof_t = now;                  \
+  } while (0)
+#else
+#define OI_PROF(i)
+#endif
+#define OI_SLOT(slot, q) scr4[((size_t)(slot) * 32 + (q)) * 128]
+#if OI_TC_X_NOSCR   // timing experiment (invalid render): no scratch traffic
+#define OI_SLOT_ST(slot, q, v) ((void)(v))
+#define OI_SLOT_LD(slot, q) make_float4(0.5f, 0.25f, 0.125f, 0.0625f)
+#else
+#define OI_SLOT_ST(slot, q, v) (OI_SLOT(slot, q) = (v))
+#define OI_SLOT_LD(slot, q) OI_SLOT(slot, q)
+#endif
+#define OI_CHUNK_READY(c)                             \
+  do {                                                \
+    tc::wait_st();                                    \
+    tc::fence_before_thread_sync();                   \
+    __syncwarp();                                     \
+    if (lane == 0) mbar_arrive(&sm.a_ready[t][(c)]);  \
   } while (0)
 #define OI_WAIT_ACC()                                \
   do {                                               \
@@ -195,12 +266,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
       const int tile = 2 * pi + t;
       if (tile >= a.n_tiles) continue;
+#if OI_TC_X_ONESLOT
+      if (t == 1) continue;
+#endif
       const int inst = tile / a.tiles_per_inst;
       const int tin = tile - inst * a.tiles_per_inst;
-      {  // FiLM table of this tile's instance
+      if (inst != film_inst) {  // FiLM table of this tile's instance (consecutive tiles mostly share it)
         const float2* src = reinterpret_cast<const float2*>(a.film_tc) + (size_t)inst * kFilm * kW;
         float2* dst = &sm.film[t][0][0];
         for (int i = sub; i < kFilm * kW; i += kEpiThreadsPerSlot) dst[i] = src[i];
+        film_inst = inst;
       }
       float px, py, pz;
       {
@@ -210,6 +285,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         pz = pc.pz;
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
+      OI_PROF(0);
 
       float sdf_acc = 0.f;
       // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
@@ -236,20 +312,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               cv[e] = cvp.x;
               cv[e + 1] = cvp.y;
             }
-            if (!a.coarse) OI_SLOT(0, c * 4 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
-            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+            if (!a.coarse) OI_SLOT_ST(0, c * 4 + q, make_float4(cv[0], cv[1], cv[2], cv[3]));
+            split2x(s[0], s[1], hi[2 * q], lo[2 * q]);
+            split2x(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
+          tc::tmem_st8(buf0 + c * 16, hi);
+          tc::tmem_st8(buf0 + c * 16 + 8, lo);
+          OI_CHUNK_READY(c);
         }
-        OI_A_READY();
       }
+      OI_PROF(1);
       // ---------------- forward layers 1..D-1: accumulator chunk c+1 is in flight while chunk c is processed ----
       for (int l = 1; l < D; ++l) {
         const float4* fl = reinterpret_cast<const float4*>(sm.film[t][l]) + n0 / 2;
         const bool last = (l == D - 1);
+        const uint32_t acc = buf0 + (l & 1) * 128;
         OI_WAIT_ACC();
+        OI_PROF(2);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
@@ -279,16 +358,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
                 sdf_acc = fmaf(sm.head[n0 + j + 1].x, s[e + 1], sdf_acc);
               }
             }
-            if (!a.coarse) OI_SLOT(l, c * 4 + q) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
-            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+            if (!a.coarse) OI_SLOT_ST(l, c * 4 + q, make_float4(cv[0], cv[1], cv[2], cv[3]));
+            split2x(s[0], s[1], hi[2 * q], lo[2 * q]);
+            split2x(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
           if (!(last && a.coarse)) {
-            tc::tmem_st8(a_hi + c * 8, hi);
-            tc::tmem_st8(a_lo + c * 8, lo);
+            tc::tmem_st8(acc + c * 16, hi);
+            tc::tmem_st8(acc + c * 16 + 8, lo);
+            OI_CHUNK_READY(c);
           }
         }
-        if (!(last && a.coarse)) OI_A_READY();
+        OI_PROF(3);
       }
       float* xch = &sm.xch[t][m][0];
       if (a.coarse) {
@@ -308,8 +388,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       {
         float4 csn[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(D - 1, q);
+        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(D - 1, q);
+        const uint32_t acc = buf0 + (D & 1) * 128;
         OI_WAIT_ACC();
+        OI_PROF(4);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
@@ -322,28 +404,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           for (int q = 0; q < 4; ++q) csc[q] = csn[q];
           if (c < 3) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(D - 1, (c + 1) * 4 + q);
+            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(D - 1, (c + 1) * 4 + q);
           }
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            OI_SLOT(D, c * 4 + q) = make_float4(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1]),
-                                                 __uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3]));
+            OI_SLOT_ST(D, c * 4 + q, make_float4(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1]),
+                                                   __uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3])));
             const int n = n0 + c * 16 + q * 4;
-            tc::split2(sm.head[n].x * csc[q].x, sm.head[n + 1].x * csc[q].y, hi[2 * q], lo[2 * q]);
-            tc::split2(sm.head[n + 2].x * csc[q].z, sm.head[n + 3].x * csc[q].w, hi[2 * q + 1], lo[2 * q + 1]);
+            split2x(sm.head[n].x * csc[q].x, sm.head[n + 1].x * csc[q].y, hi[2 * q], lo[2 * q]);
+            split2x(sm.head[n + 2].x * csc[q].z, sm.head[n + 3].x * csc[q].w, hi[2 * q + 1], lo[2 * q + 1]);
           }
-          tc::tmem_st8(a_hi + c * 8, hi);
-          tc::tmem_st8(a_lo + c * 8, lo);
+          tc::tmem_st8(acc + c * 16, hi);
+          tc::tmem_st8(acc + c * 16 + 8, lo);
+          OI_CHUNK_READY(c);
         }
-        OI_A_READY();
       }
+      OI_PROF(5);
       // ---------------- reverse sweep l = D-1 .. 1 ----------------
       float gx = 0.f, gy = 0.f, gz = 0.f;
       for (int l = D - 1; l >= 1; --l) {
         float4 csn[4];   // one-chunk look-ahead of gamma*cos(arg_{l-1}), issued before the MMA wait
 #pragma unroll
-        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(l - 1, q);
+        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(l - 1, q);
         // pull the scratch lines of the NEXT reverse layer (and, near the end, the parked colour pre-activation)
         // from DRAM into L2 a whole phase ahead of their use; one lane per 128-byte line
         if ((m & 7) == 0) {
@@ -351,7 +434,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
 #pragma unroll 4
           for (int q = 0; q < 16; ++q) l2_prefetch(&OI_SLOT(pf_slot, q));
         }
+        const uint32_t acc = buf0 + (l & 1) * 128;   // stage 2D - l
         OI_WAIT_ACC();
+        OI_PROF(6);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
@@ -364,7 +449,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           for (int q = 0; q < 4; ++q) csc[q] = csn[q];
           if (c < 3) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT(l - 1, (c + 1) * 4 + q);
+            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(l - 1, (c + 1) * 4 + q);
           }
           if (l > 1) {
             uint32_t hi[8], lo[8];
@@ -374,11 +459,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
                                           make_float2(csc[q].x, csc[q].y));
               const float2 t23 = tc::mul2(make_float2(__uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3])),
                                           make_float2(csc[q].z, csc[q].w));
-              tc::split2(t01.x, t01.y, hi[2 * q], lo[2 * q]);
-              tc::split2(t23.x, t23.y, hi[2 * q + 1], lo[2 * q + 1]);
+              split2x(t01.x, t01.y, hi[2 * q], lo[2 * q]);
+              split2x(t23.x, t23.y, hi[2 * q + 1], lo[2 * q + 1]);
             }
-            tc::tmem_st8(a_hi + c * 8, hi);
-            tc::tmem_st8(a_lo + c * 8, lo);
+            tc::tmem_st8(acc + c * 16, hi);
+            tc::tmem_st8(acc + c * 16 + 8, lo);
+            OI_CHUNK_READY(c);
           } else {  // grad_x sdf = W_0^T t_0 (this thread's 64 channels)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -398,7 +484,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
             for (int q = 0; q < 4; ++q) l2_discard_128(&OI_SLOT(l - 1, c * 4 + q));
           }
         }
-        if (l > 1) OI_A_READY();
+        OI_PROF(7);
       }
       // ---------------- combine the two column halves: sdf and grad_x sdf ----------------
       xch[h * 4 + 0] = sdf_acc;
@@ -407,7 +493,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       xch[h * 4 + 3] = gz;
       float4 ucn[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT(D, q);
+      for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT_LD(D, q);
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
       {
         const int o = (h ^ 1) * 4;
@@ -428,7 +514,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           for (int q = 0; q < 4; ++q) ucc[q] = ucn[q];
           if (c < 3) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT(D, (c + 1) * 4 + q);
+            for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT_LD(D, (c + 1) * 4 + q);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -470,9 +556,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);  // film table / exchange buffer of this slot may be reused now
+      OI_PROF(8);
     }
+#ifdef OI_TC_PROFILE
+    if (blockIdx.x == 0 && lane == 0 && (warp & 7) == 0)
+      printf("tcprof slot %d: setup %lld l0 %lld | fwd wait %lld work %lld | park wait %lld work %lld | rev wait %lld "
+             "work %lld | colour+tail %lld\n", t, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7],
+             prof[8]);
+#endif
 #undef OI_SLOT
-#undef OI_A_READY
+#undef OI_SLOT_ST
+#undef OI_SLOT_LD
+#undef OI_CHUNK_READY
 #undef OI_WAIT_ACC
   }
 
