@@ -241,6 +241,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                : "memory");
 }
 
+// TMA 1-D bulk copy shared -> global (bulk async-group completion), and the group bookkeeping of the issuing thread.
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's most recent bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// at most N of this thread's most recent bulk groups are incomplete (writes not yet performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) that reads them next
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // sin and cos of a FiLM-SIREN pre-activation (|x| up to a few hundred rad).  Two-constant Cody-Waite
 // reduction by 2*pi (exact to ~1e-7 rad for |x| < 1e3) followed by the MUFU approximations, whose
 // absolute error on [-pi, pi] (2^-21.4) is below the fp32 rounding noise of the argument itself.

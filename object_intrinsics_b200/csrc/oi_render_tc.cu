@@ -30,7 +30,8 @@ constexpr int kTcThreads = 608;            // 16 epilogue warps + TMA producer +
 constexpr int kEpiThreadsPerSlot = 256;     // 8 warps per tile slot
 constexpr int kEpiWarpsPerSlot = 8;
 constexpr int kProducerWarp = 16, kMmaWarp = 17;   // MMA issuer of slot t = warp kMmaWarp + t
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 2;
+constexpr int kStageBytes = 2048;          // one warp's chunk of one layer: [4 channel quads][32 points] float4
 constexpr int kPanelBytes = 65536;
 constexpr int kSubPanelBytes = 16384;
 constexpr float kWScale = 256.0f;        // weights are packed as 2^8 * W (see pack_weights_kernel)
@@ -38,7 +39,8 @@ constexpr float kInvWScale = 1.0f / 256.0f;
 constexpr uint32_t kIdesc = tc::make_idesc_f16(128, 128);
 
 struct __align__(1024) TcSmem {
-  unsigned char w[kTcStages][kPanelBytes];  // weight panels (192 KB)
+  unsigned char w[kTcStages][kPanelBytes];  // weight panels (128 KB)
+  float4 stg[16][2][128];                   // per epilogue warp: two 2 KB staging buffers of the scratch traffic (64 KB)
   float2 film[2][kFilm][kW];                // per tile: (gamma', delta)
   float4 w0[kW];                            // (W_0[n][0..2], 0)
   float4 head[kW];                          // 2^8 * (w_sigma[n], wc_grad[0..2][n])
@@ -46,6 +48,7 @@ struct __align__(1024) TcSmem {
   unsigned long long w_full[kTcStages], w_empty[kTcStages];
   float xch[2][128][8];                     // per slot / point: partial sums exchanged between the column halves
   unsigned long long acc_full[2], a_ready[2][4];   // a_ready[slot][chunk]: one arrival per epilogue warp
+  unsigned long long ld_full[16][2];               // per epilogue warp / staging buffer: scratch re-read landed
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB per-CTA limit");
@@ -70,6 +73,14 @@ __device__ __forceinline__ void sin_film(float x, float* s) {
   *s = __sinf(r);
 #else
   *s = __sinf(x);
+#endif
+}
+__device__ __forceinline__ void cos_film(float x, float* c) {
+#if OI_TC_SINCOS_REDUCE
+  float s;
+  sincos_film(x, &s, c);
+#else
+  *c = __cosf(x);
 #endif
 }
 __device__ __forceinline__ void sincos_tc(float x, float* s, float* c) {
@@ -99,6 +110,15 @@ __device__ __forceinline__ void split2x(float v0, float v1, uint32_t& hi, uint32
 #ifndef OI_TC_SLEEP_PRODUCER
 #define OI_TC_SLEEP_PRODUCER 400u
 #endif
+#ifndef OI_TC_X_NOST     // timing experiments (invalid renders): no scratch stores / no proxy fence / no re-reads
+#define OI_TC_X_NOST 0
+#endif
+#ifndef OI_TC_X_NOFENCE
+#define OI_TC_X_NOFENCE 0
+#endif
+#ifndef OI_TC_X_NOLD
+#define OI_TC_X_NOLD 0
+#endif
 #ifndef OI_TC_SLEEP_MMA
 #define OI_TC_SLEEP_MMA 100u
 #endif
@@ -122,6 +142,14 @@ __device__ __forceinline__ void issue_chunk_mmas(uint32_t acc, uint32_t abuf, ui
   }
 }
 
+// Panel index (in the packed blob: fwd l=1..D-1 | colour-feature | reverse l=D-1..1) of MMA stage p of a tile.
+// Fine pass order: forward layers, reverse layers, colour-feature layer LAST (its operand h_D is re-loaded from the
+// scratch, its result is consumed straight from TMEM by the colour epilogue).
+__device__ __forceinline__ int stage_panel(int p, int D, int coarse) {
+  if (coarse || p < D - 1) return p;
+  return (p < 2 * D - 2) ? p + 1 : D - 1;
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -130,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   const BlobLayout L = blob_layout(D);
   const float* cst = a.blob + L.const_off;
   const unsigned char* panels = reinterpret_cast<const unsigned char*>(a.blob + L.tc_off);
-  const int NP = a.coarse ? (D - 1) : (2 * (D - 1) + 1);  // MMA panels per tile
+  const int NP = a.coarse ? (D - 1) : (2 * (D - 1) + 1);  // MMA stages per tile
   const int n_pairs = (a.n_tiles + 1) / 2;
 
   if (tid == 0) {
@@ -142,6 +170,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       for (int c = 0; c < 4; ++c) mbar_init(&sm.a_ready[t][c], kEpiWarpsPerSlot);
       mbar_init(&sm.acc_full[t], 1);
     }
+    for (int w = 0; w < 16; ++w)
+      for (int b = 0; b < 2; ++b) mbar_init(&sm.ld_full[w][b], 1);
     mbar_fence_init();
   }
   if (warp == kProducerWarp) {
@@ -161,7 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   const uint32_t tmem_base = sm.tmem_base;
 
   if (warp == kProducerWarp) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (weight panels) =====================
     if (lane == 0) {
       int it = 0;
       for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
@@ -169,7 +199,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           const int stage = it % kTcStages;
           if (it >= kTcStages) mbar_wait_backoff(&sm.w_empty[stage], ((it / kTcStages) - 1) & 1, OI_TC_SLEEP_PRODUCER);
           mbar_expect_tx(&sm.w_full[stage], kPanelBytes);
-          const unsigned char* src = panels + (size_t)p * kPanelBytes;
+          const unsigned char* src = panels + (size_t)stage_panel(p, D, a.coarse) * kPanelBytes;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             tma_bulk_g2s(sm.w[stage] + q * kSubPanelBytes, src + q * kSubPanelBytes, kSubPanelBytes, &sm.w_full[stage]);
@@ -184,11 +214,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       int it = 0;
       uint32_t ar_phase = 0u;
       for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
-#if OI_TC_X_ONESLOT   // timing experiment: slot 1 idle, half of the tiles are skipped
-        const bool active = 2 * pi + t < a.n_tiles && t == 0;
-#else
         const bool active = 2 * pi + t < a.n_tiles;
-#endif
         for (int p = 0; p < NP; ++p, ++it) {
           const int stage = it % kTcStages;
           mbar_wait_backoff(&sm.w_full[stage], (it / kTcStages) & 1, OI_TC_SLEEP_MMA);
@@ -223,11 +249,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     // my 64 columns of the slot's two ping-pong buffers: stage s reads its accumulator from buf[s & 1] and writes
     // the next operand in place (chunk c: 8 packed hi columns at +16c, 8 packed lo columns at +16c+8)
     const uint32_t buf0 = tmem_base + t * 256 + lane_field + n0;
-    // scratch of this tile slot: (D+1) slots of [32 channel-quads][128 points] float4; mine: quads 16h..16h+15
-    float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
-                                             (size_t)t * (D + 1) * kW * 128) + (size_t)(h * 16) * 128 + m;
-    const bool discard = (a.flags & 1) != 0 && (m & 7) == 0;
+    // Reverse-sweep scratch of this warp: per saved layer (slots 1..D-2: gamma' cos(arg_l); slot D-1: the split
+    // h_D operand of the colour layer) four 2 KB chunks [quad q][lane] float4, written and re-read by this warp
+    // only, through its two shared-memory staging buffers and TMA bulk copies (the LSU never sees this traffic).
+    unsigned char* gscr = reinterpret_cast<unsigned char*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride) +
+                          (size_t)t * (D + 1) * 65536 + (size_t)(warp & 7) * kStageBytes;
+    float4* stg = &sm.stg[warp][0][0];
+    unsigned long long* ld_bar = &sm.ld_full[warp][0];
+    const bool discard = (a.flags & 1) != 0 && lane < 16;
+    const int n_loads = 4 * (D - 1);
     uint32_t af_phase = 0u;
+    uint32_t st_n = 0u;   // bulk stores issued by this warp (buffer = st_n & 1)
+    uint32_t ld_n = 0u;   // bulk loads consumed by this warp (buffer = ld_n & 1, parity = (ld_n >> 1) & 1)
     int film_inst = -1;
 #ifdef OI_TC_PROFILE   // developer build: cycles per phase of one epilogue warp per slot (block 0), printed at exit
     long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -240,14 +273,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   } while (0)
 #else
 #define OI_PROF(i)
-#endif
-#define OI_SLOT(slot, q) scr4[((size_t)(slot) * 32 + (q)) * 128]
-#if OI_TC_X_NOSCR   // timing experiment (invalid render): no scratch traffic
-#define OI_SLOT_ST(slot, q, v) ((void)(v))
-#define OI_SLOT_LD(slot, q) make_float4(0.5f, 0.25f, 0.125f, 0.0625f)
-#else
-#define OI_SLOT_ST(slot, q, v) (OI_SLOT(slot, q) = (v))
-#define OI_SLOT_LD(slot, q) OI_SLOT(slot, q)
 #endif
 #define OI_CHUNK_READY(c)                             \
   do {                                                \
@@ -262,13 +287,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     af_phase ^= 1u;                                  \
     tc::fence_after_thread_sync();                   \
   } while (0)
+    // global address of chunk c of scratch slot `slot`
+    auto gchunk = [&](int slot, int c) { return gscr + (size_t)slot * 65536 + (size_t)c * (8 * kStageBytes); };
+    // k-th scratch re-read of a tile: slots D-2, D-3, .., 1 (reverse stages l = D-1 .. 2), then slot D-1 (h_D)
+    auto gload = [&](int k) {
+      const int kk = k >> 2;
+      return gchunk(kk < D - 2 ? D - 2 - kk : D - 1, k & 3);
+    };
+    // staging buffer of the next bulk store: the store issued two chunks ago must have finished reading it
+    auto store_begin = [&]() -> float4* {
+#if OI_TC_X_NOST == 0 || OI_TC_X_NOST == 3
+#ifdef OI_TC_PROFILE
+      const long long t0 = clock64();
+#endif
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+#ifdef OI_TC_PROFILE
+      prof[9] += clock64() - t0;
+#endif
+#endif
+      return stg + (st_n & 1u) * 128 + lane;
+    };
+    // after the chunk's shared-memory writes and a __syncwarp(): one 2 KB bulk store shared -> global
+    auto store_issue = [&](int slot, int c) {
+#if OI_TC_X_NOST == 0 || OI_TC_X_NOST == 3
+      if (lane == 0) {
+        tma_bulk_s2g(gchunk(slot, c), stg + (st_n & 1u) * 128, kStageBytes);
+        bulk_commit();
+      }
+#endif
+      ++st_n;
+    };
+    auto load_issue = [&](int k, uint32_t seq) {   // seq = ld_n the load will have when consumed
+      if (lane == 0 && !OI_TC_X_NOLD) {
+        unsigned long long* bar = ld_bar + (seq & 1u);
+        mbar_expect_tx(bar, kStageBytes);
+        tma_bulk_g2s(stg + (seq & 1u) * 128, gload(k), kStageBytes, bar);
+      }
+    };
+    auto load_wait = [&]() -> const float4* {
+#ifdef OI_TC_PROFILE
+      const long long t0 = clock64();
+#endif
+      if (!OI_TC_X_NOLD) mbar_wait(ld_bar + (ld_n & 1u), (ld_n >> 1) & 1u);
+#ifdef OI_TC_PROFILE
+      prof[4] += clock64() - t0;   // (the colour wait is reported together with the re-read waits)
+#endif
+      return stg + (ld_n & 1u) * 128 + lane;
+    };
+    // after the chunk has consumed re-read k (and a __syncwarp()): refill its buffer two re-reads ahead, drop the
+    // dead lines from L2
+    auto load_done = [&](int k) {
+      if (k + 2 < n_loads) {
+        if (k + 2 == 4 * (D - 2) && lane == 0) bulk_wait<0>();   // h_D must have landed before it is re-read
+        load_issue(k + 2, ld_n + 2);
+      }
+      if (discard) l2_discard_128(gload(k) + lane * 128);
+      ++ld_n;
+    };
 
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
       const int tile = 2 * pi + t;
       if (tile >= a.n_tiles) continue;
-#if OI_TC_X_ONESLOT
-      if (t == 1) continue;
-#endif
       const int inst = tile / a.tiles_per_inst;
       const int tin = tile - inst * a.tiles_per_inst;
       if (inst != film_inst) {  // FiLM table of this tile's instance (consecutive tiles mostly share it)
@@ -288,7 +368,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       OI_PROF(0);
 
       float sdf_acc = 0.f;
-      // ---------------- layer 0 (K = 3) on the FMA pipe ----------------
+      // ---------------- layer 0 (K = 3) on the FMA pipe; its gamma' cos is recomputed in the last reverse stage ----
       {
         const float4* fl = reinterpret_cast<const float4*>(sm.film[t][0]) + n0 / 2;   // (g0, g1, d0, d1) per pair
 #pragma unroll 1
@@ -296,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float s[4], cv[4];
+            float s[4];
 #pragma unroll
             for (int e = 0; e < 4; e += 2) {
               const int j = c * 16 + q * 4 + e;
@@ -305,16 +385,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               const float2 u = make_float2(fmaf(w0.z, pz, fmaf(w0.y, py, w0.x * px)),
                                            fmaf(w1.z, pz, fmaf(w1.y, py, w1.x * px)));
               const float2 arg = tc::fma2(make_float2(f.x, f.y), u, make_float2(f.z, f.w));
-              float c0, c1;
-              sincos_tc(arg.x, &s[e], &c0);
-              sincos_tc(arg.y, &s[e + 1], &c1);
-              const float2 cvp = tc::mul2(make_float2(f.x * kInvWScale, f.y * kInvWScale), make_float2(c0, c1));
-              cv[e] = cvp.x;
-              cv[e + 1] = cvp.y;
+              sin_film(arg.x, &s[e]);
+              sin_film(arg.y, &s[e + 1]);
             }
-            if (!a.coarse) OI_SLOT_ST(0, c * 4 + q, make_float4(cv[0], cv[1], cv[2], cv[3]));
-            split2x(s[0], s[1], hi[2 * q], lo[2 * q]);
-            split2x(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
+            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
           tc::tmem_st8(buf0 + c * 16, hi);
           tc::tmem_st8(buf0 + c * 16 + 8, lo);
@@ -322,10 +397,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
       OI_PROF(1);
-      // ---------------- forward layers 1..D-1: accumulator chunk c+1 is in flight while chunk c is processed ----
-      for (int l = 1; l < D; ++l) {
+      // ---------------- forward layers 1..D-2: accumulator chunk c+1 is in flight while chunk c is processed ----
+      const int l_last = D - 1;
+      for (int l = 1; l < l_last; ++l) {
         const float4* fl = reinterpret_cast<const float4*>(sm.film[t][l]) + n0 / 2;
-        const bool last = (l == D - 1);
         const uint32_t acc = buf0 + (l & 1) * 128;
         OI_WAIT_ACC();
         OI_PROF(2);
@@ -333,6 +408,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          float4* sb = a.coarse ? nullptr : store_begin();
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
@@ -353,19 +429,78 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               const float2 cvp = tc::mul2(make_float2(f.x, f.y), make_float2(c0, c1));
               cv[e] = cvp.x;
               cv[e + 1] = cvp.y;
-              if (last) {
-                sdf_acc = fmaf(sm.head[n0 + j].x, s[e], sdf_acc);
-                sdf_acc = fmaf(sm.head[n0 + j + 1].x, s[e + 1], sdf_acc);
-              }
             }
-            if (!a.coarse) OI_SLOT_ST(l, c * 4 + q, make_float4(cv[0], cv[1], cv[2], cv[3]));
-            split2x(s[0], s[1], hi[2 * q], lo[2 * q]);
-            split2x(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
+            if (!a.coarse && (OI_TC_X_NOST == 0 || OI_TC_X_NOST == 2)) sb[q * 32] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            if (OI_TC_X_NOST == 1 || OI_TC_X_NOST == 3) asm volatile("" ::"f"(cv[0]), "f"(cv[1]), "f"(cv[2]), "f"(cv[3]));   // keep the cosines alive
+            tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
+            tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
-          if (!(last && a.coarse)) {
+          if (!a.coarse && !OI_TC_X_NOST && !OI_TC_X_NOFENCE) fence_proxy_async_smem();
+          tc::tmem_st8(acc + c * 16, hi);
+          tc::tmem_st8(acc + c * 16 + 8, lo);
+          OI_CHUNK_READY(c);
+          if (!a.coarse) store_issue(l, c);
+        }
+        OI_PROF(3);
+      }
+      // ---------------- last forward layer D-1: sdf head; the operand written in place is the START of the reverse
+      //                  sweep, t_{D-1} = w_sigma * gamma cos(arg_{D-1}); h_D (split) goes to scratch slot D-1 -------
+      if (l_last >= 1) {
+        const int l = l_last;
+        const float4* fl = reinterpret_cast<const float4*>(sm.film[t][l]) + n0 / 2;
+        const uint32_t acc = buf0 + (l & 1) * 128;
+        OI_WAIT_ACC();
+        OI_PROF(2);
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4* sb = a.coarse ? nullptr : reinterpret_cast<uint4*>(store_begin());
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float s[4], tv[4];
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const int j = c * 16 + q * 4 + e;
+              const float4 f = fl[j >> 1];
+              const float2 arg = tc::fma2(make_float2(f.x, f.y),
+                                          make_float2(__uint_as_float(u[q * 4 + e]), __uint_as_float(u[q * 4 + e + 1])),
+                                          make_float2(f.z, f.w));
+              const float ws0 = sm.head[n0 + j].x, ws1 = sm.head[n0 + j + 1].x;
+              if (a.coarse) {
+                sin_film(arg.x, &s[e]);
+                sin_film(arg.y, &s[e + 1]);
+              } else {
+                float c0, c1;
+                sincos_tc(arg.x, &s[e], &c0);
+                sincos_tc(arg.y, &s[e + 1], &c1);
+                const float2 tp = tc::mul2(tc::mul2(make_float2(f.x, f.y), make_float2(ws0, ws1)), make_float2(c0, c1));
+                tv[e] = tp.x;
+                tv[e + 1] = tp.y;
+              }
+              sdf_acc = fmaf(ws0, s[e], sdf_acc);
+              sdf_acc = fmaf(ws1, s[e + 1], sdf_acc);
+            }
+            if (!a.coarse) {
+              tc::split2(tv[0], tv[1], hi[2 * q], lo[2 * q]);
+              tc::split2(tv[2], tv[3], hi[2 * q + 1], lo[2 * q + 1]);
+              uint4 hs;   // split h_D of this channel quad: (hi01, hi23, lo01, lo23)
+              tc::split2(s[0], s[1], hs.x, hs.z);
+              tc::split2(s[2], s[3], hs.y, hs.w);
+              if (OI_TC_X_NOST == 0 || OI_TC_X_NOST == 2) sb[q * 32] = hs;
+              if (OI_TC_X_NOST == 1 || OI_TC_X_NOST == 3) asm volatile("" ::"r"(hs.x), "r"(hs.y), "r"(hs.z), "r"(hs.w));
+            }
+          }
+          if (!a.coarse) {
+            if (!OI_TC_X_NOST && !OI_TC_X_NOFENCE) fence_proxy_async_smem();
             tc::tmem_st8(acc + c * 16, hi);
             tc::tmem_st8(acc + c * 16 + 8, lo);
             OI_CHUNK_READY(c);
+            store_issue(D - 1, c);
           }
         }
         OI_PROF(3);
@@ -383,106 +518,98 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         named_bar_sync(1 + t, kEpiThreadsPerSlot);
         continue;
       }
-      // ---------------- colour layer, feature part: park 2^8 * W_c[:, :128] h in scratch slot D;
-      //                  start the reverse sweep: t_{D-1} = w_sigma * gamma cos(arg_{D-1}) ----------------
-      {
-        float4 csn[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(D - 1, q);
-        const uint32_t acc = buf0 + (D & 1) * 128;
-        OI_WAIT_ACC();
-        OI_PROF(4);
-        uint32_t ub[2][16];
-        tc::tmem_ld16_async(acc, ub[0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tc::wait_ld();
-          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
-          const uint32_t(&u)[16] = ub[c & 1];
-          float4 csc[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) csc[q] = csn[q];
-          if (c < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(D - 1, (c + 1) * 4 + q);
-          }
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            OI_SLOT_ST(D, c * 4 + q, make_float4(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1]),
-                                                   __uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3])));
-            const int n = n0 + c * 16 + q * 4;
-            split2x(sm.head[n].x * csc[q].x, sm.head[n + 1].x * csc[q].y, hi[2 * q], lo[2 * q]);
-            split2x(sm.head[n + 2].x * csc[q].z, sm.head[n + 3].x * csc[q].w, hi[2 * q + 1], lo[2 * q + 1]);
-          }
-          tc::tmem_st8(acc + c * 16, hi);
-          tc::tmem_st8(acc + c * 16 + 8, lo);
-          OI_CHUNK_READY(c);
-        }
+      // ---------------- the staging buffers change direction: every store has left shared memory, the saved
+      //                  gamma' cos of layers <= D-2 have landed (the four h_D stores may still be in flight) ---------
+      if (lane == 0) {
+        bulk_wait_read<0>();
+        if (D > 2) bulk_wait<4>(); else bulk_wait<0>();
       }
+      __syncwarp();
+      load_issue(0, ld_n);
+      load_issue(1, ld_n + 1);
       OI_PROF(5);
-      // ---------------- reverse sweep l = D-1 .. 1 ----------------
-      float gx = 0.f, gy = 0.f, gz = 0.f;
-      for (int l = D - 1; l >= 1; --l) {
-        float4 csn[4];   // one-chunk look-ahead of gamma*cos(arg_{l-1}), issued before the MMA wait
-#pragma unroll
-        for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(l - 1, q);
-        // pull the scratch lines of the NEXT reverse layer (and, near the end, the parked colour pre-activation)
-        // from DRAM into L2 a whole phase ahead of their use; one lane per 128-byte line
-        if ((m & 7) == 0) {
-          const int pf_slot = (l >= 2) ? (l - 2) : D;
-#pragma unroll 4
-          for (int q = 0; q < 16; ++q) l2_prefetch(&OI_SLOT(pf_slot, q));
-        }
-        const uint32_t acc = buf0 + (l & 1) * 128;   // stage 2D - l
+      // ---------------- reverse sweep l = D-1 .. 2: t_{l-1} = g_l * gamma' cos(arg_{l-1}) ----------------
+      int k = 0;   // scratch re-reads consumed in this tile
+      for (int l = D - 1; l >= 2; --l) {
+        const uint32_t acc = buf0 + ((l + 1) & 1) * 128;   // stage 2D - 1 - l
         OI_WAIT_ACC();
         OI_PROF(6);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c, ++k) {
+          const float4* lb = load_wait();
+          float4 csc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) csc[q] = lb[q * 32];
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
-          float4 csc[4];
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) csc[q] = csn[q];
-          if (c < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) csn[q] = OI_SLOT_LD(l - 1, (c + 1) * 4 + q);
+          for (int q = 0; q < 4; ++q) {
+            const float2 t01 = tc::mul2(make_float2(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1])),
+                                        make_float2(csc[q].x, csc[q].y));
+            const float2 t23 = tc::mul2(make_float2(__uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3])),
+                                        make_float2(csc[q].z, csc[q].w));
+            tc::split2(t01.x, t01.y, hi[2 * q], lo[2 * q]);
+            tc::split2(t23.x, t23.y, hi[2 * q + 1], lo[2 * q + 1]);
           }
-          if (l > 1) {
-            uint32_t hi[8], lo[8];
+          tc::tmem_st8(acc + c * 16, hi);
+          tc::tmem_st8(acc + c * 16 + 8, lo);
+          OI_CHUNK_READY(c);
+          load_done(k);
+        }
+        OI_PROF(7);
+      }
+      // ---------------- last reverse stage l = 1: grad_x sdf = W_0^T (g_1 * gamma' cos(arg_0)), layer 0 recomputed;
+      //                  the operand written in place is h_D (from scratch) for the colour-feature MMA ----------------
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      {
+        const float4* fl = reinterpret_cast<const float4*>(sm.film[t][0]) + n0 / 2;
+        const uint32_t acc = buf0;   // stage 2D - 2
+        OI_WAIT_ACC();
+        OI_PROF(6);
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 t01 = tc::mul2(make_float2(__uint_as_float(u[q * 4]), __uint_as_float(u[q * 4 + 1])),
-                                          make_float2(csc[q].x, csc[q].y));
-              const float2 t23 = tc::mul2(make_float2(__uint_as_float(u[q * 4 + 2]), __uint_as_float(u[q * 4 + 3])),
-                                          make_float2(csc[q].z, csc[q].w));
-              split2x(t01.x, t01.y, hi[2 * q], lo[2 * q]);
-              split2x(t23.x, t23.y, hi[2 * q + 1], lo[2 * q + 1]);
+        for (int c = 0; c < 4; ++c, ++k) {
+          const uint4* lb = reinterpret_cast<const uint4*>(load_wait());
+          uint4 hs[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) hs[q] = lb[q * 32];
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const int j = c * 16 + q * 4 + e;
+              const float4 w0 = sm.w0[n0 + j], w1 = sm.w0[n0 + j + 1];
+              const float4 f = fl[j >> 1];
+              const float2 uu = make_float2(fmaf(w0.z, pz, fmaf(w0.y, py, w0.x * px)),
+                                            fmaf(w1.z, pz, fmaf(w1.y, py, w1.x * px)));
+              const float2 arg = tc::fma2(make_float2(f.x, f.y), uu, make_float2(f.z, f.w));
+              float c0, c1;
+              cos_film(arg.x, &c0);
+              cos_film(arg.y, &c1);
+              const float2 cv = tc::mul2(make_float2(f.x * kInvWScale, f.y * kInvWScale), make_float2(c0, c1));
+              const float2 tv = tc::mul2(make_float2(__uint_as_float(u[q * 4 + e]), __uint_as_float(u[q * 4 + e + 1])), cv);
+              gx = fmaf(w0.x, tv.x, gx);
+              gy = fmaf(w0.y, tv.x, gy);
+              gz = fmaf(w0.z, tv.x, gz);
+              gx = fmaf(w1.x, tv.y, gx);
+              gy = fmaf(w1.y, tv.y, gy);
+              gz = fmaf(w1.z, tv.y, gz);
             }
-            tc::tmem_st8(acc + c * 16, hi);
-            tc::tmem_st8(acc + c * 16 + 8, lo);
-            OI_CHUNK_READY(c);
-          } else {  // grad_x sdf = W_0^T t_0 (this thread's 64 channels)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float tv[4] = {__uint_as_float(u[q * 4]) * csc[q].x, __uint_as_float(u[q * 4 + 1]) * csc[q].y,
-                                   __uint_as_float(u[q * 4 + 2]) * csc[q].z, __uint_as_float(u[q * 4 + 3]) * csc[q].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float4 w = sm.w0[n0 + c * 16 + q * 4 + e];
-                gx = fmaf(w.x, tv[e], gx);
-                gy = fmaf(w.y, tv[e], gy);
-                gz = fmaf(w.z, tv[e], gz);
-              }
-            }
           }
-          if (discard) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) l2_discard_128(&OI_SLOT(l - 1, c * 4 + q));
-          }
+          const uint32_t hi[8] = {hs[0].x, hs[0].y, hs[1].x, hs[1].y, hs[2].x, hs[2].y, hs[3].x, hs[3].y};
+          const uint32_t lo[8] = {hs[0].z, hs[0].w, hs[1].z, hs[1].w, hs[2].z, hs[2].w, hs[3].z, hs[3].w};
+          tc::tmem_st8(acc + c * 16, hi);
+          tc::tmem_st8(acc + c * 16 + 8, lo);
+          OI_CHUNK_READY(c);
+          load_done(k);
         }
         OI_PROF(7);
       }
@@ -491,9 +618,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       xch[h * 4 + 1] = gx;
       xch[h * 4 + 2] = gy;
       xch[h * 4 + 3] = gz;
-      float4 ucn[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT_LD(D, q);
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
       {
         const int o = (h ^ 1) * 4;
@@ -503,43 +627,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         gz += xch[o + 3];
       }
       const float sdf = sdf_acc * kInvWScale + cst[BlobLayout::kScalars + 0];
-      // ---------------- colour layer epilogue + rgb head (this thread's 64 channels) ----------------
+      // ---------------- colour layer: feature part 2^8 W_c[:, :128] h_D straight from the accumulator, normal part
+      //                  in registers; rgb head (this thread's 64 channels) ----------------
       float rgb[3] = {0.f, 0.f, 0.f};
       {
         const float* flc = reinterpret_cast<const float*>(sm.film[t][OI_MAX_DEPTH]) + n0 * 2;   // pair layout
+        const uint32_t acc = buf0 + 128;   // stage 2D - 1
+        OI_WAIT_ACC();
+        OI_PROF(4);
+        uint32_t ub[2][16];
+        tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float4 ucc[4];
+          tc::wait_ld();
+          if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
+          const uint32_t(&u)[16] = ub[c & 1];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) ucc[q] = ucn[q];
-          if (c < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ucn[q] = OI_SLOT_LD(D, (c + 1) * 4 + q);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float uv[4] = {ucc[q].x, ucc[q].y, ucc[q].z, ucc[q].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 16 + q * 4 + e;
-              const float4 hd = sm.head[n0 + j];
-              const float2 f = make_float2(flc[(j >> 1) * 4 + (j & 1)], flc[(j >> 1) * 4 + 2 + (j & 1)]);
-              float pre = fmaf(hd.y, gx, uv[e]);
-              pre = fmaf(hd.z, gy, pre);
-              pre = fmaf(hd.w, gz, pre);
-              float s;
-              sin_film(fmaf(f.x, pre, f.y), &s);
-              const float4 rw = sm.rgbw[n0 + j];
-              rgb[0] = fmaf(rw.x, s, rgb[0]);
-              rgb[1] = fmaf(rw.y, s, rgb[1]);
-              rgb[2] = fmaf(rw.z, s, rgb[2]);
-            }
-          }
-          if (discard) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) l2_discard_128(&OI_SLOT(D, c * 4 + q));
+          for (int i = 0; i < 16; ++i) {
+            const int j = c * 16 + i;
+            const float4 hd = sm.head[n0 + j];
+            const float2 f = make_float2(flc[(j >> 1) * 4 + (j & 1)], flc[(j >> 1) * 4 + 2 + (j & 1)]);
+            float pre = fmaf(hd.y, gx, __uint_as_float(u[i]));
+            pre = fmaf(hd.z, gy, pre);
+            pre = fmaf(hd.w, gz, pre);
+            float s;
+            sin_film(fmaf(f.x, pre, f.y), &s);
+            const float4 rw = sm.rgbw[n0 + j];
+            rgb[0] = fmaf(rw.x, s, rgb[0]);
+            rgb[1] = fmaf(rw.y, s, rgb[1]);
+            rgb[2] = fmaf(rw.z, s, rgb[2]);
           }
         }
+        tc::fence_before_thread_sync();   // orders these TMEM reads before the next tile's operand stores / MMAs
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);   // everybody has read the first exchange
       if (h == 1) {
@@ -560,15 +679,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     }
 #ifdef OI_TC_PROFILE
     if (blockIdx.x == 0 && lane == 0 && (warp & 7) == 0)
-      printf("tcprof slot %d: setup %lld l0 %lld | fwd wait %lld work %lld | park wait %lld work %lld | rev wait %lld "
-             "work %lld | colour+tail %lld\n", t, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7],
-             prof[8]);
+      printf("tcprof slot %d: setup %lld l0 %lld | fwd wait %lld work %lld | colour wait %lld dir-switch %lld | rev wait "
+             "%lld work %lld | colour+tail %lld | store-buffer wait %lld (inside fwd work), re-read wait %lld (inside rev work)\n", t, prof[0], prof[1], prof[2], prof[3], 0ll, prof[5], prof[6],
+             prof[7], prof[8], prof[9], prof[4]);
 #endif
-#undef OI_SLOT
-#undef OI_SLOT_ST
-#undef OI_SLOT_LD
+    if (lane == 0) bulk_wait<0>();   // no bulk store may outlive the CTA's shared memory
 #undef OI_CHUNK_READY
 #undef OI_WAIT_ACC
+#undef OI_PROF
   }
 
   tc::fence_before_thread_sync();
