@@ -258,8 +258,9 @@ template <int N>
 __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
-// generic-proxy shared-memory writes -> visible to the async proxy (TMA) that reads them next
+// generic-proxy writes -> visible to the async proxy (TMA) that reads them next
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // sin and cos of a FiLM-SIREN pre-activation (|x| up to a few hundred rad).  Two-constant Cody-Waite
 // reduction by 2*pi (exact to ~1e-7 rad for |x| < 1e3) followed by the MUFU approximations, whose

@@ -26,7 +26,7 @@ namespace oi {
 
 namespace {
 
-constexpr int kTcThreads = 608;            // 16 epilogue warps + TMA producer + one MMA issuer per tile slot
+constexpr int kTcThreads = 640;            // 4 epilogue warpgroups + 1 service warpgroup (TMA producer, one MMA issuer per tile slot, 1 idle warp)
 constexpr int kEpiThreadsPerSlot = 256;     // 8 warps per tile slot
 constexpr int kEpiWarpsPerSlot = 8;
 constexpr int kProducerWarp = 16, kMmaWarp = 17;   // MMA issuer of slot t = warp kMmaWarp + t
@@ -84,10 +84,7 @@ __device__ __forceinline__ void cos_film(float x, float* c) {
 #endif
 }
 __device__ __forceinline__ void sincos_tc(float x, float* s, float* c) {
-#if OI_TC_X_NOMUFU   // timing experiment (invalid render)
-  *s = x * 0.5f;
-  *c = x * 0.25f;
-#elif OI_TC_SINCOS_REDUCE
+#if OI_TC_SINCOS_REDUCE
   sincos_film(x, s, c);
 #else
   *s = __sinf(x);
@@ -97,27 +94,13 @@ __device__ __forceinline__ void sincos_tc(float x, float* s, float* c) {
 
 using tc::named_bar_sync;
 
-#if OI_TC_X_NOSPLIT   // timing experiment (invalid render): no conversion instructions
-__device__ __forceinline__ void split2x(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v0);
-  lo = __float_as_uint(v1);
-}
-#else
-__device__ __forceinline__ void split2x(float v0, float v1, uint32_t& hi, uint32_t& lo) { tc::split2(v0, v1, hi, lo); }
-#endif
 
 // nanosleep back-off of the single-lane service warps between mbarrier probes (ns)
 #ifndef OI_TC_SLEEP_PRODUCER
 #define OI_TC_SLEEP_PRODUCER 400u
 #endif
-#ifndef OI_TC_X_NOST     // timing experiments (invalid renders): no scratch stores / no proxy fence / no re-reads
-#define OI_TC_X_NOST 0
-#endif
-#ifndef OI_TC_X_NOFENCE
-#define OI_TC_X_NOFENCE 0
-#endif
-#ifndef OI_TC_X_NOLD
-#define OI_TC_X_NOLD 0
+#ifndef OI_TC_SETMAXNREG
+#define OI_TC_SETMAXNREG 1
 #endif
 #ifndef OI_TC_SLEEP_MMA
 #define OI_TC_SLEEP_MMA 100u
@@ -190,6 +173,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_base;
 
+#if OI_TC_SETMAXNREG   // the service warpgroup hands its registers to the four epilogue warpgroups (20 x 96 = 16 x 112 + 4 x 32)
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+  }
+#endif
   if (warp == kProducerWarp) {
     // ===================== TMA producer (weight panels) =====================
     if (lane == 0) {
@@ -206,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
     }
-  } else if (warp >= kMmaWarp) {
+  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
     // ===================== MMA issuer of tile slot t =====================
     if (lane == 0) {
       const int t = warp - kMmaWarp;
@@ -236,7 +226,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
     }
-  } else {
+  } else if (warp < 16) {
     // ===================== epilogue warps =====================
     // 16 warps: slot t = warp / 8 (tile of the pair), column half h = (warp / 4) % 2, TMEM lane quarter = warp % 4.
     // Thread (m, h) owns channels [64h, 64h+64) of sample point m of its tile: four 16-column chunks per layer.
@@ -259,7 +249,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     const bool discard = (a.flags & 1) != 0 && lane < 16;
     const int n_loads = 4 * (D - 1);
     uint32_t af_phase = 0u;
-    uint32_t st_n = 0u;   // bulk stores issued by this warp (buffer = st_n & 1)
     uint32_t ld_n = 0u;   // bulk loads consumed by this warp (buffer = ld_n & 1, parity = (ld_n >> 1) & 1)
     int film_inst = -1;
 #ifdef OI_TC_PROFILE   // developer build: cycles per phase of one epilogue warp per slot (block 0), printed at exit
@@ -273,6 +262,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   } while (0)
 #else
 #define OI_PROF(i)
+#endif
+#ifdef OI_TC_PROFILE2   // cycles per step of a reverse-stage chunk
+    long long prof2[6] = {0, 0, 0, 0, 0, 0};
+    long long prof2_t = clock64();
+#define OI_PROF2(i)                  \
+  do {                               \
+    const long long now = clock64(); \
+    prof2[i] += now - prof2_t;       \
+    prof2_t = now;                   \
+  } while (0)
+#else
+#define OI_PROF2(i)
 #endif
 #define OI_CHUNK_READY(c)                             \
   do {                                                \
@@ -294,32 +295,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       const int kk = k >> 2;
       return gchunk(kk < D - 2 ? D - 2 - kk : D - 1, k & 3);
     };
-    // staging buffer of the next bulk store: the store issued two chunks ago must have finished reading it
-    auto store_begin = [&]() -> float4* {
-#if OI_TC_X_NOST == 0 || OI_TC_X_NOST == 3
-#ifdef OI_TC_PROFILE
-      const long long t0 = clock64();
-#endif
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-#ifdef OI_TC_PROFILE
-      prof[9] += clock64() - t0;
-#endif
-#endif
-      return stg + (st_n & 1u) * 128 + lane;
-    };
-    // after the chunk's shared-memory writes and a __syncwarp(): one 2 KB bulk store shared -> global
-    auto store_issue = [&](int slot, int c) {
-#if OI_TC_X_NOST == 0 || OI_TC_X_NOST == 3
-      if (lane == 0) {
-        tma_bulk_s2g(gchunk(slot, c), stg + (st_n & 1u) * 128, kStageBytes);
-        bulk_commit();
-      }
-#endif
-      ++st_n;
-    };
     auto load_issue = [&](int k, uint32_t seq) {   // seq = ld_n the load will have when consumed
-      if (lane == 0 && !OI_TC_X_NOLD) {
+      if (lane == 0) {
         unsigned long long* bar = ld_bar + (seq & 1u);
         mbar_expect_tx(bar, kStageBytes);
         tma_bulk_g2s(stg + (seq & 1u) * 128, gload(k), kStageBytes, bar);
@@ -329,7 +306,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
 #ifdef OI_TC_PROFILE
       const long long t0 = clock64();
 #endif
-      if (!OI_TC_X_NOLD) mbar_wait(ld_bar + (ld_n & 1u), (ld_n >> 1) & 1u);
+      mbar_wait(ld_bar + (ld_n & 1u), (ld_n >> 1) & 1u);
 #ifdef OI_TC_PROFILE
       prof[4] += clock64() - t0;   // (the colour wait is reported together with the re-read waits)
 #endif
@@ -339,7 +316,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
     // dead lines from L2
     auto load_done = [&](int k) {
       if (k + 2 < n_loads) {
-        if (k + 2 == 4 * (D - 2) && lane == 0) bulk_wait<0>();   // h_D must have landed before it is re-read
         load_issue(k + 2, ld_n + 2);
       }
       if (discard) l2_discard_128(gload(k) + lane * 128);
@@ -408,7 +384,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float4* sb = a.coarse ? nullptr : store_begin();
+          float4* sb = reinterpret_cast<float4*>(gchunk(l, c)) + lane;   // my 16 bytes of each of the chunk's 4 quads
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
@@ -430,16 +406,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               cv[e] = cvp.x;
               cv[e + 1] = cvp.y;
             }
-            if (!a.coarse && (OI_TC_X_NOST == 0 || OI_TC_X_NOST == 2)) sb[q * 32] = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            if (OI_TC_X_NOST == 1 || OI_TC_X_NOST == 3) asm volatile("" ::"f"(cv[0]), "f"(cv[1]), "f"(cv[2]), "f"(cv[3]));   // keep the cosines alive
+            if (!a.coarse) sb[q * 32] = make_float4(cv[0], cv[1], cv[2], cv[3]);
             tc::split2(s[0], s[1], hi[2 * q], lo[2 * q]);
             tc::split2(s[2], s[3], hi[2 * q + 1], lo[2 * q + 1]);
           }
-          if (!a.coarse && !OI_TC_X_NOST && !OI_TC_X_NOFENCE) fence_proxy_async_smem();
           tc::tmem_st8(acc + c * 16, hi);
           tc::tmem_st8(acc + c * 16 + 8, lo);
           OI_CHUNK_READY(c);
-          if (!a.coarse) store_issue(l, c);
         }
         OI_PROF(3);
       }
@@ -455,7 +428,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint4* sb = a.coarse ? nullptr : reinterpret_cast<uint4*>(store_begin());
+          uint4* sb = reinterpret_cast<uint4*>(gchunk(D - 1, c)) + lane;
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
@@ -491,16 +464,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               uint4 hs;   // split h_D of this channel quad: (hi01, hi23, lo01, lo23)
               tc::split2(s[0], s[1], hs.x, hs.z);
               tc::split2(s[2], s[3], hs.y, hs.w);
-              if (OI_TC_X_NOST == 0 || OI_TC_X_NOST == 2) sb[q * 32] = hs;
-              if (OI_TC_X_NOST == 1 || OI_TC_X_NOST == 3) asm volatile("" ::"r"(hs.x), "r"(hs.y), "r"(hs.z), "r"(hs.w));
+              sb[q * 32] = hs;
             }
           }
           if (!a.coarse) {
-            if (!OI_TC_X_NOST && !OI_TC_X_NOFENCE) fence_proxy_async_smem();
             tc::tmem_st8(acc + c * 16, hi);
             tc::tmem_st8(acc + c * 16 + 8, lo);
             OI_CHUNK_READY(c);
-            store_issue(D - 1, c);
           }
         }
         OI_PROF(3);
@@ -520,10 +490,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
       }
       // ---------------- the staging buffers change direction: every store has left shared memory, the saved
       //                  gamma' cos of layers <= D-2 have landed (the four h_D stores may still be in flight) ---------
-      if (lane == 0) {
-        bulk_wait_read<0>();
-        if (D > 2) bulk_wait<4>(); else bulk_wait<0>();
-      }
+      fence_proxy_async_global();
       __syncwarp();
       load_issue(0, ld_n);
       load_issue(1, ld_n + 1);
@@ -538,11 +505,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         tc::tmem_ld16_async(acc, ub[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c, ++k) {
+          OI_PROF2(0);
           const float4* lb = load_wait();
           float4 csc[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) csc[q] = lb[q * 32];
+          OI_PROF2(1);
           tc::wait_ld();
+          OI_PROF2(2);
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
           const uint32_t(&u)[16] = ub[c & 1];
           uint32_t hi[8], lo[8];
@@ -557,8 +527,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
           }
           tc::tmem_st8(acc + c * 16, hi);
           tc::tmem_st8(acc + c * 16 + 8, lo);
+          OI_PROF2(3);
           OI_CHUNK_READY(c);
+          OI_PROF2(4);
           load_done(k);
+          OI_PROF2(5);
         }
         OI_PROF(7);
       }
@@ -683,10 +656,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
              "%lld work %lld | colour+tail %lld | store-buffer wait %lld (inside fwd work), re-read wait %lld (inside rev work)\n", t, prof[0], prof[1], prof[2], prof[3], 0ll, prof[5], prof[6],
              prof[7], prof[8], prof[9], prof[4]);
 #endif
-    if (lane == 0) bulk_wait<0>();   // no bulk store may outlive the CTA's shared memory
+#ifdef OI_TC_PROFILE2
+    if (blockIdx.x == 0 && lane == 0 && (warp & 7) == 0)
+      printf("tcprof2 slot %d reverse chunks: other %lld | re-read wait+LDS %lld | wait_ld %lld | mul/split/STTM issue %lld | "
+             "wait_st+fence+syncwarp+arrive %lld | refill+discard %lld\n", t, prof2[0], prof2[1], prof2[2], prof2[3],
+             prof2[4], prof2[5]);
+#endif
 #undef OI_CHUNK_READY
 #undef OI_WAIT_ACC
 #undef OI_PROF
+#undef OI_PROF2
   }
 
   tc::fence_before_thread_sync();
