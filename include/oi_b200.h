@@ -343,8 +343,27 @@ typedef struct OiRenderMapsDesc {
   float *image, *image_no_bg, *mask, *shading_map, *color_map, *weight_sum_map;
   float *amb_shading_map, *diff_shading_map, *normal_map, *no_specular_map, *specular_map, *z_map;
   float* z_min_per_ray;     /* [R] min_s mid_z (reduced per instance by the caller) or NULL */
+  const float* light_params; /* device [10] = ambient[3], diffuse[3], specular[3], shininess, or NULL; when given it
+                              * replaces the four by-value fields above (the light's nn.Parameters are then never read
+                              * back to the host: lighting.py:13-52 keeps them on the device) */
 } OiRenderMapsDesc;
 int oi_render_maps(const OiRenderMapsDesc* desc, void* stream);
+
+/* Reverse mode of oi_render_maps: what autograd does for generator.py:80-174 + lighting.py:126-225 in the generator
+ * step (gan_pose_trainer.py:141).  `fwd` repeats the forward call's inputs (its output pointers are ignored);
+ * g_* are the adjoints of the maps ([bs,C,P,P], NULL = no gradient flows through that map).  Written (not
+ * accumulated): d_weights [R,S], d_gradients [R,S,3], d_raw_color [R,S,3], d_weight_sum [R,1], d_color_fine [R,3];
+ * d_light_params [10] (same order as light_params) and d_light_dir [bs,3] are zero-filled by the call and reduced
+ * over all sample points.  pts, rays_o, mid_z_vals and bg_color are constants of the training path. */
+typedef struct OiRenderMapsBwdDesc {
+  OiRenderMapsDesc fwd;
+  const float *g_image, *g_image_no_bg, *g_mask, *g_shading_map, *g_color_map, *g_weight_sum_map;
+  const float *g_amb_shading_map, *g_diff_shading_map, *g_normal_map, *g_no_specular_map, *g_specular_map, *g_z_map;
+  float *d_weights, *d_gradients, *d_raw_color, *d_weight_sum, *d_color_fine;
+  float* d_light_params;    /* [10] or NULL */
+  float* d_light_dir;       /* [bs,3] or NULL */
+} OiRenderMapsBwdDesc;
+int oi_render_maps_backward(const OiRenderMapsBwdDesc* desc, void* stream);
 
 /* Geometric path of the ADA AugmentPipe (src/third_party/ada/augment.py:270-301): reflect-pad by `margins`,
  * 2x up-sample with the separable low-pass `filter` (gain 4), bilinear affine resample (affine_grid + grid_sample,

@@ -137,7 +137,18 @@ class OiRenderMapsDesc(C.Structure):
         ("image", f32p), ("image_no_bg", f32p), ("mask", f32p), ("shading_map", f32p), ("color_map", f32p),
         ("weight_sum_map", f32p), ("amb_shading_map", f32p), ("diff_shading_map", f32p), ("normal_map", f32p),
         ("no_specular_map", f32p), ("specular_map", f32p), ("z_map", f32p), ("z_min_per_ray", f32p),
+        ("light_params", f32p),
     ]
+
+
+MAP_NAMES = ("image", "image_no_bg", "mask", "shading_map", "color_map", "weight_sum_map", "amb_shading_map",
+             "diff_shading_map", "normal_map", "no_specular_map", "specular_map", "z_map")
+
+
+class OiRenderMapsBwdDesc(C.Structure):
+    _fields_ = ([("fwd", OiRenderMapsDesc)] + [("g_" + n, f32p) for n in MAP_NAMES] +
+                [("d_weights", f32p), ("d_gradients", f32p), ("d_raw_color", f32p), ("d_weight_sum", f32p),
+                 ("d_color_fine", f32p), ("d_light_params", f32p), ("d_light_dir", f32p)])
 
 
 EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_render_workspace_bytes",
@@ -145,7 +156,7 @@ EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_ren
            "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps",
            "oi_render_backward_workspace_bytes", "oi_render_backward", "oi_selftest_wgrad",
            "oi_augment_geom_workspace_bytes", "oi_augment_geom_forward", "oi_augment_geom_backward",
-           "oi_augment_geom_setup"]
+           "oi_augment_geom_setup", "oi_render_maps_backward"]
 
 _lib = None
 
@@ -182,6 +193,7 @@ def lib():
     L.oi_fused_bias_act.argtypes = [C.POINTER(OiFusedBiasActDesc), C.c_void_p]
     L.oi_gen_rays.argtypes = [C.POINTER(OiGenRaysDesc), C.c_void_p]
     L.oi_render_maps.argtypes = [C.POINTER(OiRenderMapsDesc), C.c_void_p]
+    L.oi_render_maps_backward.argtypes = [C.POINTER(OiRenderMapsBwdDesc), C.c_void_p]
     L.oi_selftest_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     if L.oi_abi_version() != 1:
         raise RuntimeError(f"liboi_b200.so ABI version {L.oi_abi_version()} != 1")

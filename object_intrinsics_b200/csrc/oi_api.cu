@@ -482,6 +482,18 @@ int oi_render_maps(const OiRenderMapsDesc* d, void* stream) {
   return launch_render_maps(*d, static_cast<cudaStream_t>(stream));
 }
 
+int oi_render_maps_backward(const OiRenderMapsBwdDesc* bd, void* stream) {
+  OI_CHECK_ARG(bd != nullptr, "desc is NULL");
+  const OiRenderMapsDesc* d = &bd->fwd;
+  OI_CHECK_ARG(d->n_rays > 0 && d->rays_per_instance > 0 && d->n_rays % d->rays_per_instance == 0 && d->n_samples > 0,
+               "bad sizes");
+  OI_CHECK_ARG(d->weights && d->gradients && d->raw_color && d->pts && d->weight_sum && d->rays_o && d->light_dir &&
+                   d->bg_color,
+               "NULL input pointer");
+  OI_CHECK_ARG(!bd->g_z_map || d->mid_z_vals, "g_z_map needs mid_z_vals");
+  return launch_render_maps_bwd(*bd, static_cast<cudaStream_t>(stream));
+}
+
 int oi_upfirdn2d(const OiUpfirdnDesc* d, void* stream) {
   OI_CHECK_ARG(d != nullptr, "desc is NULL");
   OI_CHECK_ARG(d->x && d->f && d->y, "x, f, y must be non-NULL");

@@ -130,6 +130,7 @@ int launch_upfirdn2d(const OiUpfirdnDesc& d, cudaStream_t s);
 int launch_bias_act(const OiBiasActDesc& d, cudaStream_t s);
 int launch_fused_bias_act(const OiFusedBiasActDesc& d, cudaStream_t s);
 int launch_gen_rays(const OiGenRaysDesc& d, cudaStream_t st);
+int launch_render_maps_bwd(const OiRenderMapsBwdDesc& d, cudaStream_t st);
 int launch_augment_geom(const OiAugmentGeomDesc& d, bool backward, cudaStream_t st);
 int launch_augment_setup(const float* G_inv, int B, int H, int W, int hz_pad, float* theta, int* margins,
                          cudaStream_t st);

@@ -26,7 +26,7 @@ namespace oi {
 
 namespace {
 
-constexpr int kTcThreads = 640;            // 4 epilogue warpgroups + 1 service warpgroup (TMA producer, one MMA issuer per tile slot, 1 idle warp)
+constexpr int kTcThreads = 608;            // 16 epilogue warps + TMA producer + one MMA issuer per tile slot
 constexpr int kEpiThreadsPerSlot = 256;     // 8 warps per tile slot
 constexpr int kEpiWarpsPerSlot = 8;
 constexpr int kProducerWarp = 16, kMmaWarp = 17;   // MMA issuer of slot t = warp kMmaWarp + t
@@ -99,9 +99,6 @@ using tc::named_bar_sync;
 #ifndef OI_TC_SLEEP_PRODUCER
 #define OI_TC_SLEEP_PRODUCER 400u
 #endif
-#ifndef OI_TC_SETMAXNREG
-#define OI_TC_SETMAXNREG 1
-#endif
 #ifndef OI_TC_SLEEP_MMA
 #define OI_TC_SLEEP_MMA 100u
 #endif
@@ -173,13 +170,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_base;
 
-#if OI_TC_SETMAXNREG   // the service warpgroup hands its registers to the four epilogue warpgroups (20 x 96 = 16 x 112 + 4 x 32)
-  if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-  }
-#endif
   if (warp == kProducerWarp) {
     // ===================== TMA producer (weight panels) =====================
     if (lane == 0) {
@@ -196,7 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
     }
-  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+  } else if (warp >= kMmaWarp) {
     // ===================== MMA issuer of tile slot t =====================
     if (lane == 0) {
       const int t = warp - kMmaWarp;
@@ -226,7 +216,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         }
       }
     }
-  } else if (warp < 16) {
+  } else {
     // ===================== epilogue warps =====================
     // 16 warps: slot t = warp / 8 (tile of the pair), column half h = (warp / 4) % 2, TMEM lane quarter = warp % 4.
     // Thread (m, h) owns channels [64h, 64h+64) of sample point m of its tile: four 16-column chunks per layer.
