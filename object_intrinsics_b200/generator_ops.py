@@ -7,8 +7,8 @@ argument and keep the reference methods' signatures and return dicts, so that th
     Generator.gen_rays_at = G.gen_rays_at          # src/models/generator.py:255-279 (+ build_rays :317-333)
     Generator.render_maps = G.render_maps          # src/models/generator.py:80-174 (+ lighting.py:126-225)
 
-They are forward-only kernels: under autograd (the generator step) the reference's own torch code must be used
--- `render_maps` raises if any input requires grad while grad mode is on.
+`gen_rays_at` is forward-only (poses are sampled, rays are constants of the training path); `render_maps` is
+differentiable (oi_render_maps_backward) with respect to the render outputs and the light's parameters.
 """
 from __future__ import annotations
 
@@ -51,72 +51,101 @@ def gen_rays_at(generator, data, prior_info: Dict, with_near_far: bool = False) 
     return out
 
 
-_RAW_KEYS = ("amb_shading_map", "diff_shading_map", "normal_map", "no_specular_map", "specular_map")
+_MAPS_BASE = ("weight_sum_map", "color_map", "shading_map", "image_no_bg", "image", "mask")
+_MAPS_RAW = ("amb_shading_map", "diff_shading_map", "normal_map", "no_specular_map", "specular_map", "z_map")
+_MAP_CHANNELS = {"weight_sum_map": 1, "mask": 1, "z_map": 1}
+
+
+def _fill_maps_desc(d, n_rays, rays_per_instance, n_samples, tensors):
+    d.n_rays, d.rays_per_instance, d.n_samples = n_rays, rays_per_instance, n_samples
+    for k, t in tensors.items():
+        setattr(d, k, None if t is None else t.data_ptr())
+
+
+class _RenderMapsFunction(torch.autograd.Function):
+    """oi_render_maps / oi_render_maps_backward behind autograd.  Differentiable inputs: weights, gradients,
+    raw_color, weight_sum, color_fine, light_params [10], light_dir [bs,3]; the rest are constants of the training
+    path (sample positions, camera position, background colour)."""
+
+    @staticmethod
+    def forward(ctx, weights, gradients, raw_color, weight_sum, color_fine, light_params, light_dir, pts, mid_z,
+                rays_o, bg_color, bs, P, return_raw):
+        dev = weights.device
+        R, S = weights.shape
+        ins = {"weights": _f32c(weights, dev), "gradients": _f32c(gradients, dev), "raw_color": _f32c(raw_color, dev),
+               "weight_sum": _f32c(weight_sum, dev), "color_fine": _f32c(color_fine, dev),
+               "light_params": _f32c(light_params, dev), "light_dir": _f32c(light_dir, dev), "pts": _f32c(pts, dev),
+               "mid_z_vals": None if mid_z is None else _f32c(mid_z, dev), "rays_o": _f32c(rays_o, dev),
+               "bg_color": _f32c(bg_color, dev)}
+        names = _MAPS_BASE + (_MAPS_RAW if return_raw else ())
+        outs = {n: torch.empty(bs, _MAP_CHANNELS.get(n, 3), P, P, device=dev) for n in names}
+        zmin = torch.empty(R, device=dev) if return_raw else None
+        d = _lib.OiRenderMapsDesc()
+        _fill_maps_desc(d, R, R // bs, S, {**ins, **outs, "z_min_per_ray": zmin})
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().oi_render_maps(C.byref(d), _lib.current_stream_ptr(dev)), "oi_render_maps")
+        ctx.save_for_backward(*[t for t in ins.values() if t is not None])
+        ctx.keys = [k for k, t in ins.items() if t is not None]
+        ctx.names, ctx.bs, ctx.P = names, bs, P
+        ctx.set_materialize_grads(False)
+        ret = tuple(outs[n] for n in names)
+        if return_raw:
+            ctx.mark_non_differentiable(zmin)
+            ret = ret + (zmin,)
+        return ret
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        ins = dict(zip(ctx.keys, ctx.saved_tensors))
+        dev = ins["weights"].device
+        R, S = ins["weights"].shape
+        bd = _lib.OiRenderMapsBwdDesc()
+        _fill_maps_desc(bd.fwd, R, R // ctx.bs, S, ins)
+        keep = []
+        for n, g in zip(ctx.names, gouts):
+            if g is not None:
+                g = _f32c(g, dev)
+                keep.append(g)
+                setattr(bd, "g_" + n, g.data_ptr())
+        grads = {"d_weights": torch.empty(R, S, device=dev), "d_gradients": torch.empty(R, S, 3, device=dev),
+                 "d_raw_color": torch.empty(R, S, 3, device=dev), "d_weight_sum": torch.empty(R, 1, device=dev),
+                 "d_color_fine": torch.empty(R, 3, device=dev), "d_light_params": torch.empty(10, device=dev),
+                 "d_light_dir": torch.empty(ctx.bs, 3, device=dev)}
+        for k, t in grads.items():
+            setattr(bd, k, t.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().oi_render_maps_backward(C.byref(bd), _lib.current_stream_ptr(dev)),
+                       "oi_render_maps_backward")
+        return (grads["d_weights"], grads["d_gradients"], grads["d_raw_color"], grads["d_weight_sum"],
+                grads["d_color_fine"], grads["d_light_params"], grads["d_light_dir"], None, None, None, None, None,
+                None, None)
 
 
 def render_maps(generator, bs, render_out, rays_info, prior_info, return_raw):
-    """Phong shading of every sample + per-ray compositing of all maps in one kernel."""
+    """Phong shading of every sample + per-ray compositing of all maps in one kernel; differentiable with respect to
+    the render outputs and the light (module parameters stay on the device: no host read-back)."""
     light = prior_info["light"]            # BatchDirectionalLightWithSpecularFixInit (lighting.py:79-119)
     weights = render_out["weights"]
     if not weights.is_cuda:
         raise RuntimeError("render_maps: CUDA tensors only (object_intrinsics_b200 has no CPU path)")
-    if torch.is_grad_enabled() and any(render_out[k].requires_grad for k in ("weights", "gradients", "raw_color")):
-        raise RuntimeError("generator_ops.render_maps is forward-only; use the reference render_maps under autograd")
     dev = weights.device
     P = int(generator.resolution)
-    R, S = weights.shape
     base = light.light
-    w2b = light.w2b
-    direction = (base.param_direction / torch.linalg.norm(base.param_direction)).detach()
-    light_dir = _f32c(torch.einsum("bij,j->bi", w2b[:, :3, :3].detach(), direction), dev)   # lighting.py:115-119
+    direction = base.param_direction / torch.linalg.norm(base.param_direction)
+    light_dir = torch.einsum("bij,j->bi", light.w2b[:, :3, :3].to(dev), direction.to(dev))   # lighting.py:115-119
+    light_params = torch.cat([torch.as_tensor(v, dtype=torch.float32, device=dev).reshape(-1).expand(n)
+                              for v, n in ((base.ambient_color, 3), (base.diffuse_color, 3),
+                                           (base.specular_color, 3), (base.shininess, 1))])
     bg = generator.bg_color(bs)            # [bs,3,h,w] expand of a per-instance colour (utils/prior.py:12-29)
-    bg_color = _f32c(bg[:, :, 0, 0], dev)
-    rays_o = _f32c(rays_info["rays_o"].reshape(-1, 3), dev)
-    ins = {k: _f32c(render_out[k], dev) for k in ("weights", "gradients", "raw_color", "pts", "weight_sum",
-                                                  "color_fine")}
-    d = _lib.OiRenderMapsDesc()
-    d.n_rays, d.rays_per_instance, d.n_samples = R, R // bs, S
-    # ONE device->host read for the ten light scalars (ten float(tensor[i]) calls would be ten blocking syncs)
-    lp = torch.cat([base.ambient_color.detach().reshape(3).float(), base.diffuse_color.detach().reshape(3).float(),
-                    base.specular_color.detach().reshape(3).float(),
-                    torch.as_tensor(base.shininess, dtype=torch.float32, device=base.ambient_color.device).reshape(1)
-                    ]).tolist()
-    d.shininess = lp[9]
-    for i in range(3):
-        d.ambient_color[i], d.diffuse_color[i], d.specular_color[i] = lp[i], lp[3 + i], lp[6 + i]
-    for k, t in ins.items():
-        setattr(d, k, t.data_ptr())
-    d.rays_o, d.light_dir, d.bg_color = rays_o.data_ptr(), light_dir.data_ptr(), bg_color.data_ptr()
-    ret = {}
-
-    def new(name, c):
-        ret[name] = torch.empty(bs, c, P, P, device=dev)
-        setattr(d, name, ret[name].data_ptr())
-
-    new("weight_sum_map", 1)
-    new("color_map", 3)
+    outs = _RenderMapsFunction.apply(
+        weights, render_out["gradients"], render_out["raw_color"], render_out["weight_sum"], render_out["color_fine"],
+        light_params, light_dir, render_out["pts"].detach(),
+        render_out["mid_z_vals"].detach() if return_raw else None, rays_info["rays_o"].reshape(-1, 3).detach(),
+        bg[:, :, 0, 0].detach(), bs, P, bool(return_raw))
+    names = _MAPS_BASE + (_MAPS_RAW if return_raw else ())
+    ret = dict(zip(names, outs))
     if return_raw:
-        new("amb_shading_map", 3)
-        new("diff_shading_map", 3)
-    new("shading_map", 3)
-    if return_raw:
-        new("normal_map", 3)
-        new("no_specular_map", 3)
-        new("specular_map", 3)
-    new("image_no_bg", 3)
-    new("image", 3)
-    new("mask", 1)
-    zmin = None
-    if return_raw:
-        mid = _f32c(render_out["mid_z_vals"], dev)
-        d.mid_z_vals = mid.data_ptr()
-        new("z_map", 1)
-        zmin = torch.empty(R, device=dev)
-        d.z_min_per_ray = zmin.data_ptr()
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().oi_render_maps(C.byref(d), _lib.current_stream_ptr(dev)), "oi_render_maps")
-    if return_raw:
-        ret["z_min"] = zmin.reshape(bs, -1).min(-1).values
+        ret["z_min"] = outs[-1].reshape(bs, -1).min(-1).values
     render_out.pop("gradients", None)      # the reference deletes these two from the dict (generator.py:126,129)
     render_out.pop("pts", None)
     return ret

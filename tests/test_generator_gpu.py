@@ -105,3 +105,53 @@ def test_render_maps_on_kernel_output_full_patch():
                          bg[:, :, None, None].expand(bs, 3, res, res), True)
     for k in ref:
         assert linf(maps[k].cpu(), ref[k]) < 1e-4, (k, linf(maps[k].cpu(), ref[k]))
+
+
+@pytest.mark.parametrize("return_raw", [True, False])
+def test_render_maps_backward_matches_fp64_autograd(return_raw):
+    """oi_render_maps_backward vs torch.autograd through the oracle restatement of Generator.render_maps in fp64:
+    gradients of a random linear functional of every map w.r.t. weights / normals / albedo / weight_sum /
+    color_fine and the light's four parameters (lighting.py:13-52) and direction."""
+    from object_intrinsics_b200 import generator_ops
+    G = load()
+    amb, dif, spec, shin = [float(v) for v in G["maps/light"]]
+    bs, res = G["maps/bg"].shape[0], int(G["rays/scalars"][1])
+    gen = _fake_generator(G, bg=G["maps/bg"].cuda())
+    keys = ("weights", "gradients", "raw_color", "weight_sum", "color_fine")
+    render_out = {k[len("maps/in/"):]: v.cuda() for k, v in G.items() if k.startswith("maps/in/")}
+    for k in keys:
+        render_out[k] = render_out[k].clone().requires_grad_(True)
+    # the light as the reference parametrises it: ambient = sigmoid(p), diffuse = 1 - sigmoid(p), specular, shininess
+    p_amb = torch.tensor(amb / (amb + dif)).logit().cuda().requires_grad_(True)
+    p_spec = torch.tensor(max(spec, 0.05)).cuda().requires_grad_(True)
+    p_shin = torch.tensor(shin).cuda().requires_grad_(True)
+    p_dir = torch.tensor([0.2, -0.3, -1.0]).cuda().requires_grad_(True)
+    base = types.SimpleNamespace(param_direction=p_dir, ambient_color=torch.sigmoid(p_amb).expand(3),
+                                 diffuse_color=(1 - torch.sigmoid(p_amb)).expand(3),
+                                 specular_color=p_spec.expand(3).clamp(min=0), shininess=p_shin)
+    light = types.SimpleNamespace(light=base, w2b=G["maps/w2b"].cuda())
+    leaves = [render_out[k] for k in keys] + [p_amb, p_spec, p_shin, p_dir]
+    rays_o = G["rays/rays_o"].cuda()
+    out = generator_ops.render_maps(gen, bs, dict(render_out), {"rays_o": rays_o}, {"light": light}, return_raw)
+    gen_w = torch.Generator().manual_seed(5)
+    coef = {k: torch.randn(v.shape, generator=gen_w) for k, v in out.items() if k != "z_min"}
+    loss = sum((out[k] * coef[k].cuda()).sum() for k in coef)
+    grads = torch.autograd.grad(loss, leaves)
+    # fp64 oracle
+    ro64 = {k: v.detach().cpu().double() for k, v in render_out.items()}
+    for k in keys:
+        ro64[k].requires_grad_(True)
+    q = [t.detach().cpu().double().requires_grad_(True) for t in (p_amb, p_spec, p_shin, p_dir)]
+    direction = q[3] / torch.linalg.norm(q[3])
+    ref = GO.render_maps(bs, res, ro64, rays_o.cpu().double().reshape(-1, 3),
+                         GO.light_batch_direction(G["maps/w2b"].double(), direction),
+                         torch.sigmoid(q[0]).expand(3), (1 - torch.sigmoid(q[0])).expand(3),
+                         q[1].expand(3).clamp(min=0), q[2],
+                         G["maps/bg"].double()[:, :, None, None].expand(bs, 3, res, res), return_raw)
+    loss64 = sum((ref[k] * coef[k].double()).sum() for k in coef)
+    grads64 = torch.autograd.grad(loss64, [ro64[k] for k in keys] + q)
+    names = list(keys) + ["param_ambient", "param_specular", "param_shininess", "param_direction"]
+    for n, g, g64 in zip(names, grads, grads64):
+        scale = float(g64.abs().max()) + 1e-12
+        err = float((g.detach().cpu().double().reshape(g64.shape) - g64).abs().max()) / scale
+        assert err < 2e-4, (n, err, scale)

@@ -3,7 +3,7 @@
 Mirrors the launch sequence of one `GANPoseTrainer.train_step` (src/trainers/gan_pose_trainer.py:77-101) as far
 as the render path and its two neighbours reach:
 
-    G step   gen_rays_at -> grad-mode render -> shading/compositing of the maps -> loss -> backward   (:104-141)
+    G step   gen_rays_at -> grad-mode render -> render_maps (shading + compositing) -> loss -> backward (:104-141)
     D step   no-grad gen_rays_at + render + render_maps, AugmentPipe on fake and real image            (:85-87)
     mask-D   no-grad gen_rays_at + render + render_maps, AugmentPipe on fake and real mask             (:89-91)
     (the G step itself pushes its image and its mask through both pipes: 6 AugmentPipe forwards per step)
@@ -82,7 +82,7 @@ def _shade_torch(out, rays_d, light, bs, patch):
             out["weight_sum"].reshape(bs, patch, patch, 1).permute(0, 3, 1, 2).contiguous())
 
 
-def measure(dev, P, kernel="auto", flush=None, shape="cfg5", steps=8):
+def measure(dev, P, kernel="auto", flush=None, shape="cfg5", steps=8, shading="kernel"):
     from object_intrinsics_b200 import fields, generator_ops
     from object_intrinsics_b200.augment import AugmentPipe
     from object_intrinsics_b200.renderer import NeuSRenderer
@@ -114,7 +114,11 @@ def measure(dev, P, kernel="auto", flush=None, shape="cfg5", steps=8):
             p.grad = None
         ro, rd, near, far = rays()
         out = render(ro, rd, near, far)
-        img, mask = _shade_torch(out, rd, light, bs, patch)
+        if shading == "torch":
+            img, mask = _shade_torch(out, rd, light, bs, patch)
+        else:   # the differentiable oi_render_maps (forward + oi_render_maps_backward inside autograd)
+            maps = generator_ops.render_maps(gen, bs, out, {"rays_o": ro}, {"light": light}, False)
+            img, mask = maps["image"], maps["mask"]
         loss = (aug_img(img) ** 2).mean() + (aug_mask(mask) ** 2).mean() + 0.1 * out["gradient_error"]
         loss.backward()
 
@@ -153,7 +157,9 @@ def measure(dev, P, kernel="auto", flush=None, shape="cfg5", steps=8):
     return {"shape": shape, **cfg, "ms_per_step": med["total"], "g_step_ms": med["g_step"],
             "two_no_grad_renders_ms": med["d_step_x2"], "rays_per_step": rays_per_step,
             "rays_per_sec": rays_per_step / (med["total"] * 1e-3),
-            "what": "gen_rays -> grad render -> torch Phong shading stand-in -> 2 AugmentPipe -> quadratic loss -> "
+            "shading": shading,
+            "what": "gen_rays -> grad render -> Phong shading maps (oi_render_maps + oi_render_maps_backward, or a torch "
+                    "stand-in with shading='torch') -> 2 AugmentPipe -> quadratic loss -> "
                     "backward (oi_render_backward + augment adjoint); then 2 x (gen_rays -> no-grad render -> "
                     "oi_render_maps -> 2 AugmentPipe); mirrors gan_pose_trainer.py:77-101 without the "
                     "discriminator networks / optimisers"}
