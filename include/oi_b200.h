@@ -105,7 +105,8 @@ typedef struct OiRenderDesc {
   int32_t rays_per_instance; /* R / n_instances (src/models/fields.py:55) */
   int32_t n_samples;         /* n >= 2 */
   int32_t n_importance;      /* m >= 0 */
-  int32_t up_sample_steps;   /* only 1 is implemented (configs/train.yaml:76) */
+  int32_t up_sample_steps;   /* >= 1, must divide n_importance; step i adds n_importance / steps samples with
+                              * inv_s = 64 * 2^i (renderer.py:400-413); `lin_fine` then has n_importance / steps entries */
   int32_t depth;             /* D of the packed network */
   int32_t impl;              /* OiRenderImpl */
   int32_t flags;             /* bit 0 (OI_FLAG_DISCARD_SCRATCH): drop dead reverse-sweep scratch lines from L2 (discard.global.L2) */

@@ -23,7 +23,7 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t film, scratch, partials, ticket, sdf_coarse, z_fine, tmp_raw_color, tmp_gradients, tmp_pts_norm, tmp_sdf;
+  size_t film, scratch, partials, ticket, sdf_coarse, z_fine, z_fine2, tmp_raw_color, tmp_gradients, tmp_pts_norm, tmp_sdf;
   size_t total;
   int n_ctas;
   size_t scratch_stride;
@@ -57,8 +57,10 @@ int plan_workspace(const OiRenderDesc* d, Workspace* w) {
   w->partials = take((size_t)R * 3 * 4);
   w->ticket = take(256);
   const bool hier = d->n_importance > 0 && d->z_vals_in == nullptr;
-  w->sdf_coarse = hier ? take((size_t)R * d->n_samples * 4) : 0;
+  // multi-step up-sampling re-evaluates the SDF at the merged z of every step: [R,S] buffers, two z buffers
+  w->sdf_coarse = hier ? take((size_t)R * (d->up_sample_steps > 1 ? S : d->n_samples) * 4) : 0;
   w->z_fine = hier ? take((size_t)R * S * 4) : 0;
+  w->z_fine2 = (hier && d->up_sample_steps > 1) ? take((size_t)R * S * 4) : 0;
   w->tmp_raw_color = d->raw_color ? 0 : take((size_t)R * S * 3 * 4);
   w->tmp_gradients = d->gradients ? 0 : take((size_t)R * S * 3 * 4);
   w->tmp_pts_norm = d->pts_norm ? 0 : take((size_t)R * S * 4);
@@ -75,8 +77,13 @@ int validate_render(const OiRenderDesc* d) {
   OI_CHECK_ARG(d->n_samples >= 2, "n_samples must be >= 2 (got %d)", d->n_samples);
   OI_CHECK_ARG(d->n_importance >= 0, "n_importance must be >= 0");
   OI_CHECK_ARG(d->depth >= 1 && d->depth <= OI_MAX_DEPTH, "depth must be in [1, %d] (got %d)", OI_MAX_DEPTH, d->depth);
-  if (d->n_importance > 0 && d->up_sample_steps != 1)
-    return set_error(OI_ERR_UNSUPPORTED, "up_sample_steps=%d: only 1 is implemented", d->up_sample_steps);
+  if (d->n_importance > 0) {
+    OI_CHECK_ARG(d->up_sample_steps >= 1, "up_sample_steps must be >= 1 (got %d)", d->up_sample_steps);
+    // the reference adds n_importance // up_sample_steps samples per step (renderer.py:404) and then assumes
+    // n_samples + n_importance samples per ray (:415): only exact divisions are consistent
+    OI_CHECK_ARG(d->n_importance % d->up_sample_steps == 0, "n_importance (%d) must be a multiple of up_sample_steps (%d)",
+                 d->n_importance, d->up_sample_steps);
+  }
   if ((long long)d->n_rays * (d->n_samples + d->n_importance) >= (1ll << 30))
     return set_error(OI_ERR_UNSUPPORTED, "n_rays * samples too large for 32-bit point indices");
   OI_CHECK_ARG(d->impl >= OI_IMPL_AUTO && d->impl <= OI_IMPL_TCGEN05, "bad impl %d", d->impl);
@@ -159,7 +166,7 @@ int oi_render_launch_count(const OiRenderDesc* desc, int32_t* launches) {
   if (rc) return rc;
   OI_CHECK_ARG(launches != nullptr, "launches is NULL");
   const bool hier = desc->n_importance > 0 && desc->z_vals_in == nullptr;
-  *launches = 3 + (hier ? 2 : 0);  // film, [coarse, upsample], fine, composite
+  *launches = 3 + (hier ? 2 * desc->up_sample_steps : 0);  // film, steps x [coarse, upsample], fine, composite
   return OI_OK;
 }
 
@@ -209,21 +216,36 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   const float* z_vals = d->z_vals_in;
   const bool hier = m > 0 && z_vals == nullptr;
   if (hier) {
-    // coarse SDF pass at the n stratified z (renderer.py:389-399)
-    RenderKArgs c = a;
-    c.coarse = 1;
-    c.S = n;
-    c.pts_per_inst = d->rays_per_instance * n;
-    c.tiles_per_inst = (c.pts_per_inst + 127) / 128;
-    c.n_tiles = c.tiles_per_inst * n_inst;
-    c.sdf_coarse = reinterpret_cast<float*>(ws + w.sdf_coarse);
-    rc = (impl == OI_IMPL_TCGEN05) ? launch_render_tc(c, st) : launch_render_ffma(c, st);
-    if (rc) return rc;
-    float* z_fine = reinterpret_cast<float*>(ws + w.z_fine);
-    rc = launch_upsample(R, n, m, d->rays_o, d->rays_d, d->near, d->far, d->t_rand, d->lin_coarse, d->lin_fine,
-                         c.sdf_coarse, z_fine, st);
-    if (rc) return rc;
-    z_vals = z_fine;
+    // up_sample_steps x { SDF-only pass at the current z, up_sample + cat_z_vals } (renderer.py:389-413).  Step 0
+    // evaluates the n stratified z; every later step re-evaluates the SDF at the merged (sorted) z of the previous
+    // one -- the reference evaluates only the new points and gathers (:186-195); per point the result is the same.
+    const int steps = d->up_sample_steps, m_step = m / steps;
+    float* zbuf[2] = {reinterpret_cast<float*>(ws + w.z_fine), reinterpret_cast<float*>(ws + w.z_fine2)};
+    if (steps % 2 == 0) {   // the last step must land in z_fine
+      float* t = zbuf[0];
+      zbuf[0] = zbuf[1];
+      zbuf[1] = t;
+    }
+    const float* z_cur = nullptr;
+    for (int i = 0; i < steps; ++i) {
+      const int n_cur = n + i * m_step;
+      RenderKArgs c = a;
+      c.coarse = 1;
+      c.S = n_cur;
+      c.z_vals = z_cur;
+      c.pts_per_inst = d->rays_per_instance * n_cur;
+      c.tiles_per_inst = (c.pts_per_inst + 127) / 128;
+      c.n_tiles = c.tiles_per_inst * n_inst;
+      c.sdf_coarse = reinterpret_cast<float*>(ws + w.sdf_coarse);
+      rc = (impl == OI_IMPL_TCGEN05) ? launch_render_tc(c, st) : launch_render_ffma(c, st);
+      if (rc) return rc;
+      float* z_next = zbuf[i & 1];
+      rc = launch_upsample(R, n_cur, m_step, d->rays_o, d->rays_d, d->near, d->far, d->t_rand, d->lin_coarse,
+                           d->lin_fine, z_cur, 64.0f * (float)(1 << i), c.sdf_coarse, z_next, st);
+      if (rc) return rc;
+      z_cur = z_next;
+    }
+    z_vals = z_cur;
   }
 
   a.coarse = 0;

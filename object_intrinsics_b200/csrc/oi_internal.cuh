@@ -157,7 +157,7 @@ size_t render_ffma_scratch_floats(int depth, int* n_ctas, int n_tiles);
 size_t render_tc_scratch_floats(int depth, int* n_ctas, int n_tiles);
 int launch_upsample(int R, int n, int m, const float* rays_o, const float* rays_d, const float* near,
                     const float* far, const float* t_rand, const float* lin, const float* lin_fine,
-                    const float* sdf_coarse, float* z_fine, cudaStream_t st);
+                    const float* z_in, float inv_s, const float* sdf_coarse, float* z_fine, cudaStream_t st);
 int launch_composite(int R, int S, const float* blob, int depth, float* weights /*in: alpha*/,
                      const float* raw_color, const float* gradients, const float* pts_norm, const float* sdf,
                      float* weight_sum, float* weight_max, float* color_fine, float* s_val,

@@ -234,6 +234,7 @@ __global__ void upsample_kernel(int R, int n, int m, const float* __restrict__ r
                                 const float* __restrict__ rays_d, const float* __restrict__ near,
                                 const float* __restrict__ far, const float* __restrict__ t_rand,
                                 const float* __restrict__ lin, const float* __restrict__ lin_fine,
+                                const float* __restrict__ z_in, float inv_s,
                                 const float* __restrict__ sdf_coarse, float* __restrict__ z_fine) {
   const int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= R) return;
@@ -243,13 +244,17 @@ __global__ void upsample_kernel(int R, int n, int m, const float* __restrict__ r
   const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
   const float nr = near[ray], span = far[ray] - near[ray];
   const float jit = t_rand ? t_rand[ray] * 2.0f / (float)n : 0.f;
-  for (int i = 0; i < n; ++i) {
-    const float l = lin ? lin[i] : (float)i / (float)(n - 1);
-    float zi = nr + span * l;
-    if (t_rand) zi = zi + jit;
-    z[i] = zi;
+  if (z_in) {   // up-sampling step i > 0: the merged z of the previous step (renderer.py:400-413)
+    for (int i = 0; i < n; ++i) z[i] = z_in[(size_t)ray * n + i];
+  } else {
+    for (int i = 0; i < n; ++i) {
+      const float l = lin ? lin[i] : (float)i / (float)(n - 1);
+      float zi = nr + span * l;
+      if (t_rand) zi = zi + jit;
+      z[i] = zi;
+    }
   }
-  const float inv_s = 64.0f;  // 64 * 2^i with i = 0 (renderer.py:406)
+  // inv_s = 64 * 2^i in up-sampling step i (renderer.py:406)
   const float* sdf = sdf_coarse + (size_t)ray * n;
   // pass 1: weights (stored temporarily in cdf[1..n-1]) and their sum
   float T = 1.0f, prev_cos = 0.f, wsum = 0.f;
@@ -453,11 +458,12 @@ int launch_film(const float* blob, int depth, const float* style_w, float* film,
 
 int launch_upsample(int R, int n, int m, const float* rays_o, const float* rays_d, const float* near,
                     const float* far, const float* t_rand, const float* lin, const float* lin_fine,
-                    const float* sdf_coarse, float* z_fine, cudaStream_t st) {
+                    const float* z_in, float inv_s, const float* sdf_coarse, float* z_fine, cudaStream_t st) {
   if (n > kMaxCoarse || m > kMaxFine)
-    return set_error(OI_ERR_UNSUPPORTED, "n_samples <= %d and n_importance <= %d required", kMaxCoarse, kMaxFine);
-  upsample_kernel<<<(R + 63) / 64, 64, 0, st>>>(R, n, m, rays_o, rays_d, near, far, t_rand, lin, lin_fine,
-                                                sdf_coarse, z_fine);
+    return set_error(OI_ERR_UNSUPPORTED, "at most %d samples entering an up-sampling step and %d new ones per step",
+                     kMaxCoarse, kMaxFine);
+  upsample_kernel<<<(R + 63) / 64, 64, 0, st>>>(R, n, m, rays_o, rays_d, near, far, t_rand, lin, lin_fine, z_in,
+                                                inv_s, sdf_coarse, z_fine);
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

@@ -307,9 +307,9 @@ class NeuSRenderer:
 
     # -------------------------------------------------------------------------------------------
     def _linspaces(self, device):
-        key = (str(device), self.n_samples, self.n_importance)
+        key = (str(device), self.n_samples, self.n_importance, self.up_sample_steps)
         if key not in self._lin:
-            n, m = self.n_samples, self.n_importance
+            n, m = self.n_samples, self.n_importance // max(self.up_sample_steps, 1)   # new samples per step (:404)
             lin_c = torch.linspace(0.0, 1.0, n, device=device, dtype=torch.float32)            # renderer.py:359
             lin_f = (torch.linspace(0.5 / m, 1.0 - 0.5 / m, m, device=device, dtype=torch.float32)
                      if m > 0 else None)                                                      # renderer.py:53

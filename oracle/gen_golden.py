@@ -38,10 +38,13 @@ CASES = [
     ("cfg2_n64_m0_jit", 8, 1, 8, 64, 0, True, 0.5, True),
     ("cfg4_n64_m64",   8, 1, 6, 64, 64, True, 1.0, False),
     ("cfgd_n16_m4_D8", 8, 3, 6, 16, 4, True, 1.0, False),
+    # multi-step up-sampling (renderer.py:400-413; dead in the reference's configs, up_sample_steps: 1 in train.yaml)
+    ("cfgs_n16_m8_s2", 4, 2, 8, 16, 8, False, 1.0, False, 2),
+    ("cfgs_n16_m12_s4_D8", 8, 2, 6, 16, 12, True, 0.5, True, 4),
 ]
 
 
-def run_reference(nets, inp, n, m, anneal, dtype):
+def run_reference(nets, inp, n, m, anneal, dtype, steps=1):
     sdf, col, dev = [x.to(dtype) for x in nets]
     old = torch.get_default_dtype()
     torch.set_default_dtype(dtype)
@@ -59,7 +62,8 @@ def run_reference(nets, inp, n, m, anneal, dtype):
             torch.rand = fake_rand
         try:
             out = RH.reference_render(sdf, col, dev, ro, rd, near, far, z, w, n_samples=n, n_importance=m,
-                                      cos_anneal_ratio=anneal, perturb_overwrite=(1 if t_rand is not None else 0))
+                                      cos_anneal_ratio=anneal, perturb_overwrite=(1 if t_rand is not None else 0),
+                                      up_sample_steps=steps)
         finally:
             if t_rand is not None:
                 torch.rand = real_rand
@@ -98,15 +102,25 @@ def main():
         json.dump(kav, f, indent=1)
 
     param_sets = {}
-    for name, D, bs, patch, n, m, sphere, anneal, jitter in CASES:
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]   # python oracle/gen_golden.py [case names]
+    for case in CASES:
+        name, D, bs, patch, n, m, sphere, anneal, jitter = case[:9]
+        steps = case[9] if len(case) > 9 else 1
         key = (D, sphere)
         if key not in param_sets:
             nets = RH.build_reference_nets(D=D, sphere_init=sphere, seed=7)
             # perturb variance a little so inv_s is not the init constant everywhere
             param_sets[key] = nets
             P = O.extract_params(*nets)
-            np.savez_compressed(os.path.join(GOLDEN, f"params_D{D}.npz"), **{k: v.numpy() for k, v in P.items()})
+            if not only:
+                np.savez_compressed(os.path.join(GOLDEN, f"params_D{D}.npz"), **{k: v.numpy() for k, v in P.items()})
+            else:   # adding cases: the rebuilt reference networks must be the committed ones, bit for bit
+                with np.load(os.path.join(GOLDEN, f"params_D{D}.npz")) as f:
+                    assert all(np.array_equal(f[k], v.numpy()) for k, v in P.items()), f"params_D{D}.npz differs"
+
         nets = param_sets[key]
+        if only and name not in only:
+            continue
         seed = 1234 + len(name)
         ro, rd, near, far = O.synthetic_rays(bs, patch, seed=seed)
         g = torch.Generator().manual_seed(seed)
@@ -114,12 +128,12 @@ def main():
         inp = dict(rays_o=ro, rays_d=rd, near=near, far=far, z=z)
         if jitter:
             inp["t_rand"] = torch.rand(ro.shape[0], 1, generator=g) - 0.5
-        w32, out32 = run_reference(nets, inp, n, m, anneal, torch.float32)
-        w64, out64 = run_reference(nets, inp, n, m, anneal, torch.float64)
+        w32, out32 = run_reference(nets, inp, n, m, anneal, torch.float32, steps)
+        w64, out64 = run_reference(nets, inp, n, m, anneal, torch.float64, steps)
         blob = {f"in/{k}": v.numpy() for k, v in inp.items()}
         blob["in/w"] = w32.detach().numpy()
         blob["meta"] = np.array(json.dumps(dict(name=name, D=D, W=128, bs=bs, patch=patch, n_samples=n,
-                                                n_importance=m, cos_anneal_ratio=anneal, jitter=jitter,
+                                                n_importance=m, up_sample_steps=steps, cos_anneal_ratio=anneal, jitter=jitter,
                                                 params=f"params_D{D}.npz", torch=torch.__version__)))
         for k in OUT_KEYS:
             blob[f"ref32/{k}"] = out32[k].detach().numpy()

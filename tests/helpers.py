@@ -11,7 +11,8 @@ OUT_KEYS = ['s_val', 'cdf_fine', 'weight_sum', 'weight_max', 'gradients', 'weigh
             'inside_sphere', 'mid_z_vals', 'surface_loss', 'sdf', 'pts_norm', 'pts', 'color_fine', 'raw_color']
 
 CASES = ["cfg1_n16_m0", "cfg1_n16_m4", "cfg1_n16_m4_jit", "cfg2_n64_m0", "cfg2_n64_m0_jit", "cfg4_n64_m64",
-         "cfgd_n16_m4_D8"]
+         "cfgd_n16_m4_D8",
+         "cfgs_n16_m8_s2", "cfgs_n16_m12_s4_D8"]   # the last two: up_sample_steps = 2 / 4 (renderer.py:400-413)
 
 
 def load_params(fname, dtype=torch.float32):

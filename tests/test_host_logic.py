@@ -40,7 +40,9 @@ def test_argument_validation_without_gpu():
     assert L.oi_render_forward(C.byref(d), None) == -1                 # n_rays == 0
     d.n_rays, d.rays_per_instance, d.n_samples, d.depth = 10, 3, 16, 8
     assert L.oi_render_forward(C.byref(d), None) == -1 and b"multiple" in L.oi_last_error()
-    d.rays_per_instance, d.n_importance, d.up_sample_steps = 5, 4, 2
+    d.rays_per_instance, d.n_importance, d.up_sample_steps = 5, 4, 3
+    assert L.oi_render_workspace_bytes(C.byref(d), C.byref(n)) == -1 and b"multiple of up_sample_steps" in L.oi_last_error()
+    d.up_sample_steps, d.n_samples = 2, 1 << 30                          # 32-bit point indices
     assert L.oi_render_workspace_bytes(C.byref(d), C.byref(n)) == -2   # OI_ERR_UNSUPPORTED
     with pytest.raises(NotImplementedError):
         _lib.check(-2, "x")

@@ -22,7 +22,8 @@ def _run(name, dtype, **kw):
     w = O.style_mlp(P, a["z"])
     out = O.render(P, a["rays_o"], a["rays_d"], a["near"], a["far"], z=a["z"], w=w,
                    n_samples=meta["n_samples"], n_importance=meta["n_importance"],
-                   cos_anneal_ratio=meta["cos_anneal_ratio"], t_rand=a.get("t_rand"), **kw)
+                   cos_anneal_ratio=meta["cos_anneal_ratio"], t_rand=a.get("t_rand"),
+                   up_sample_steps=meta.get("up_sample_steps", 1), **kw)
     return meta, inp, r32, r64, w, out
 
 

@@ -24,7 +24,7 @@ def _build(meta, impl):
     fields.load_flat_params(sdf, col, dev, P)
     r = NeuSRenderer(nerf=None, sdf_network=sdf, deviation_network=dev, color_network=col,
                      n_samples=meta["n_samples"], n_importance=meta["n_importance"], n_outside=0,
-                     up_sample_steps=1, perturb=0, impl=impl)
+                     up_sample_steps=meta.get("up_sample_steps", 1), perturb=0, impl=impl)
     return P, r
 
 
@@ -69,7 +69,7 @@ def test_hierarchical_matches_reference(name, impl):
     a = {k: v.double() for k, v in inp.items()}
     o64 = O.render(P64, a["rays_o"], a["rays_d"], a["near"], a["far"], w=a["w"], n_samples=meta["n_samples"],
                    n_importance=meta["n_importance"], cos_anneal_ratio=meta["cos_anneal_ratio"],
-                   t_rand=a.get("t_rand"))
+                   t_rand=a.get("t_rand"), up_sample_steps=meta.get("up_sample_steps", 1))
     dz = (out["z_vals"].double() - o64["z_vals"]).abs()
     tol_z = max(1e-4, 2.0 * linf(r32["mid_z_vals"], r64["mid_z_vals"]))
     n_bad = int((dz > tol_z).sum())
