@@ -109,7 +109,9 @@ typedef struct OiRenderDesc {
                               * inv_s = 64 * 2^i (renderer.py:400-413); `lin_fine` then has n_importance / steps entries */
   int32_t depth;             /* D of the packed network */
   int32_t impl;              /* OiRenderImpl */
-  int32_t flags;             /* bit 0 (OI_FLAG_DISCARD_SCRATCH): drop dead reverse-sweep scratch lines from L2 (discard.global.L2) */
+  int32_t flags;             /* bit 0 (OI_FLAG_DISCARD_SCRATCH): drop dead reverse-sweep scratch lines from L2 (discard.global.L2);
+                              * bit 3 (value 8): keep the per-ray compositing in its own kernel even where the tcgen05 core
+                              * could do it (rays aligned with its 128-point tiles: 128 % (n_samples + n_importance) == 0) */
   float cos_anneal_ratio;    /* renderer.py:273-274 */
   float reserved_f;
 

@@ -29,6 +29,13 @@ struct Workspace {
   size_t scratch_stride;
 };
 
+int resolve_impl(const OiRenderDesc* d);
+// The tcgen05 core composites per ray itself when rays are aligned runs of its 128-point tiles.
+bool fused_composite(const OiRenderDesc* d, int impl) {
+  const int S = d->n_samples + d->n_importance;
+  return impl == OI_IMPL_TCGEN05 && S <= 128 && 128 % S == 0 && (d->flags & 8) == 0;
+}
+
 int resolve_impl(const OiRenderDesc* d) {
   int impl = d->impl;
   if (impl == OI_IMPL_AUTO) impl = (d->depth >= 2) ? OI_IMPL_TCGEN05 : OI_IMPL_FFMA;
@@ -166,7 +173,8 @@ int oi_render_launch_count(const OiRenderDesc* desc, int32_t* launches) {
   if (rc) return rc;
   OI_CHECK_ARG(launches != nullptr, "launches is NULL");
   const bool hier = desc->n_importance > 0 && desc->z_vals_in == nullptr;
-  *launches = 3 + (hier ? 2 * desc->up_sample_steps : 0);  // film, steps x [coarse, upsample], fine, composite
+  // film, steps x [coarse, upsample], fine, [composite unless the core does it]
+  *launches = 3 + (hier ? 2 * desc->up_sample_steps : 0) - (fused_composite(desc, resolve_impl(desc)) ? 1 : 0);
   return OI_OK;
 }
 
@@ -265,10 +273,22 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   a.pts = d->pts;
   a.raw_color = d->raw_color ? d->raw_color : reinterpret_cast<float*>(ws + w.tmp_raw_color);
   a.z_out = d->z_vals_out;
+  a.fuse_composite = fused_composite(d, impl) ? 1 : 0;
+  if (a.fuse_composite) {
+    a.weight_sum = d->weight_sum;
+    a.weight_max = d->weight_max;
+    a.color_fine = d->color_fine;
+    a.s_val = d->s_val;
+    a.gradient_error = d->gradient_error;
+    a.surface_loss = d->surface_loss;
+    a.partials = reinterpret_cast<float*>(ws + w.partials);
+    a.ticket = ticket;
+  }
   if (d->evt_core_start) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d->evt_core_start), st));
   rc = (impl == OI_IMPL_TCGEN05) ? launch_render_tc(a, st) : launch_render_ffma(a, st);
   if (rc) return rc;
   if (d->evt_core_stop) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d->evt_core_stop), st));
+  if (a.fuse_composite) return OI_OK;
 
   return launch_composite(R, S, blob, d->depth, d->weights, a.raw_color, a.gradients, a.pts_norm, a.sdf,
                           d->weight_sum, d->weight_max, d->color_fine, d->s_val, d->gradient_error, d->surface_loss,

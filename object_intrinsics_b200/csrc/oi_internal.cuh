@@ -119,6 +119,13 @@ struct RenderKArgs {
   float *cdf_fine, *gradients, *alpha, *inside_sphere, *mid_z, *sdf, *pts_norm, *pts, *raw_color;
   float* z_out;
   float* sdf_coarse;    // [R,n] (coarse pass output)
+  // Per-ray compositing inside the tcgen05 core (fine pass, rays aligned with the 128-point tiles: 128 % S == 0):
+  // the kernel then writes the final weights and the per-ray outputs itself and reduces the two global scalars in
+  // its last CTA; otherwise composite_kernel does it in a second launch.
+  int fuse_composite;
+  float *weight_sum, *weight_max, *color_fine, *s_val, *gradient_error, *surface_loss;
+  float* partials;      // [R,3] per-ray partial sums of the global scalars
+  unsigned int* ticket;
 };
 
 // launchers (each returns an OiStatus)

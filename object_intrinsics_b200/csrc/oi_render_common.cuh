@@ -78,8 +78,10 @@ __device__ __forceinline__ PointCtx point_prologue(const RenderKArgs& a, int ins
 }
 
 // NeuS section opacity and the per-point outputs (renderer.py:261-286).  rgb_pre = W_rgb h_c (bias not yet added).
+// `tail_out` (optional): {alpha, r, g, b} handed back for in-kernel compositing; the opacity is then NOT stored.
 __device__ __forceinline__ void point_tail(const RenderKArgs& a, const PointCtx& c, const float* __restrict__ cst,
-                                           float sdf, float gx, float gy, float gz, const float (&rgb_pre)[3]) {
+                                           float sdf, float gx, float gy, float gz, const float (&rgb_pre)[3],
+                                           float* tail_out = nullptr) {
   if (!c.valid) return;
   const size_t gp = (size_t)c.ray * a.S + c.si;
   const float inv_s = cst[BlobLayout::kScalars + 4];
@@ -96,7 +98,14 @@ __device__ __forceinline__ void point_tail(const RenderKArgs& a, const PointCtx&
   alpha = fminf(fmaxf(alpha, 0.f), 1.f);
   if (a.sdf) a.sdf[gp] = sdf;
   if (a.cdf_fine) a.cdf_fine[gp] = prev_cdf;
-  a.alpha[gp] = alpha;
+  if (tail_out) {
+    tail_out[0] = alpha;
+    tail_out[1] = r;
+    tail_out[2] = g;
+    tail_out[3] = b;
+  } else {
+    a.alpha[gp] = alpha;
+  }
   if (a.gradients) {
     a.gradients[gp * 3 + 0] = gx;
     a.gradients[gp * 3 + 1] = gy;

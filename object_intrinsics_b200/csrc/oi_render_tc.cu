@@ -49,6 +49,9 @@ struct __align__(1024) TcSmem {
   float xch[2][128][8];                     // per slot / point: partial sums exchanged between the column halves
   unsigned long long acc_full[2], a_ready[2][4];   // a_ready[slot][chunk]: one arrival per epilogue warp
   unsigned long long ld_full[16][2];               // per epilogue warp / staging buffer: scratch re-read landed
+  float comp[2][4][9];                             // in-kernel compositing: per slot / warp {product, 8 partial sums}
+  double red[3][20];                               // last CTA: reduction of the per-ray partials of the global scalars
+  int is_last;
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB per-CTA limit");
@@ -635,7 +638,86 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
         rgb[1] += xch[1];
         rgb[2] += xch[2];
         const PointCtx pc = point_prologue(a, inst, tin, m, false);
-        point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
+        if (!a.fuse_composite) {
+          point_tail(a, pc, cst, sdf, gx, gy, gz, rgb);
+        } else {
+          // ---- per-ray compositing (renderer.py:300-338), rays = aligned runs of S of this tile's 128 points:
+          //      weights = alpha * exclusive cumprod(1 - alpha + 1e-7), weight sum / max, colour, partial sums of the
+          //      two global scalars.  Same association as composite_kernel (carry * exclusive scan inside a warp).
+          float to[4] = {0.f, 0.f, 0.f, 0.f};
+          point_tail(a, pc, cst, sdf, gx, gy, gz, rgb, to);
+          const int S = a.S, seg = S < 32 ? S : 32, lis = lane & (seg - 1), wq = warp & 3;
+          const float alpha = pc.valid ? to[0] : 0.f;
+          float incl = pc.valid ? (1.0f - alpha + 1e-7f) : 1.0f;
+          for (int dd = 1; dd < seg; dd <<= 1) {
+            const float o = __shfl_up_sync(0xffffffffu, incl, dd);
+            if (lis >= dd) incl *= o;
+          }
+          float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+          if (lis == 0) excl = 1.0f;
+          float carry = 1.0f;
+          const int wpr = S > 32 ? (S >> 5) : 1, wir = wq & (wpr - 1);   // warps per ray, my warp's index in its ray
+          if (S > 32) {
+            if (lane == 31) sm.comp[t][wq][0] = incl;
+            named_bar_sync(3 + t, 128);
+            for (int j = 0; j < wir; ++j) carry *= sm.comp[t][wq - wir + j][0];
+          }
+          const float wgt = alpha * (carry * excl);
+          float v[8];
+          {
+            const float e = sqrtf(gx * gx + gy * gy + gz * gz) - 1.0f;
+            const float relax = sqrtf(pc.px * pc.px + pc.py * pc.py + pc.pz * pc.pz) < 1.2f ? 1.f : 0.f;
+            const bool ok = pc.valid;
+            v[0] = wgt;
+            v[1] = ok ? wgt : -1e30f;
+            v[2] = to[1] * wgt;
+            v[3] = to[2] * wgt;
+            v[4] = to[3] * wgt;
+            v[5] = ok ? relax * e * e : 0.f;
+            v[6] = ok ? relax : 0.f;
+            v[7] = ok ? expf(-100.0f * fabsf(sdf)) : 0.f;
+          }
+          for (int dd = seg >> 1; dd >= 1; dd >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float o = __shfl_xor_sync(0xffffffffu, v[i], dd);
+              v[i] = (i == 1) ? fmaxf(v[i], o) : v[i] + o;
+            }
+          }
+          if (S > 32) {
+            if (lane == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sm.comp[t][wq][1 + i] = v[i];
+            }
+            named_bar_sync(3 + t, 128);
+            if (wir == 0 && lane == 0) {
+              for (int j = 1; j < wpr; ++j) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float o = sm.comp[t][wq + j][1 + i];
+                  v[i] = (i == 1) ? fmaxf(v[i], o) : v[i] + o;
+                }
+              }
+            }
+          }
+          if (pc.valid) {
+            a.alpha[(size_t)pc.ray * S + pc.si] = wgt;   // the `weights` output
+            if (lis == 0 && wir == 0) {                  // first point of the ray: per-ray outputs
+              const int ray = pc.ray;
+              if (a.weight_sum) a.weight_sum[ray] = v[0];
+              if (a.weight_max) a.weight_max[ray] = v[1];
+              if (a.color_fine) {
+                a.color_fine[ray * 3 + 0] = v[2];
+                a.color_fine[ray * 3 + 1] = v[3];
+                a.color_fine[ray * 3 + 2] = v[4];
+              }
+              if (a.s_val) a.s_val[ray] = cst[BlobLayout::kScalars + 5];
+              a.partials[(size_t)ray * 3 + 0] = v[5];
+              a.partials[(size_t)ray * 3 + 1] = v[6];
+              a.partials[(size_t)ray * 3 + 2] = v[7];
+            }
+          }
+        }
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);  // film table / exchange buffer of this slot may be reused now
       OI_PROF(8);
@@ -661,6 +743,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == kProducerWarp) tc::tmem_dealloc(tmem_base, 512);
+  if (!a.fuse_composite) return;
+  // ---- the last CTA to finish reduces the per-ray partials of gradient_error (renderer.py:309-311) and surface_loss
+  //      (:338) in a fixed order (deterministic), as composite_kernel does for the unfused path
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sm.is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int r = tid; r < a.R; r += kTcThreads) {
+    s0 += (double)__ldcg(a.partials + (size_t)r * 3 + 0);
+    s1 += (double)__ldcg(a.partials + (size_t)r * 3 + 1);
+    s2 += (double)__ldcg(a.partials + (size_t)r * 3 + 2);
+  }
+#pragma unroll
+  for (int dd = 16; dd >= 1; dd >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, dd);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, dd);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, dd);
+  }
+  if (lane == 0) {
+    sm.red[0][warp] = s0;
+    sm.red[1][warp] = s1;
+    sm.red[2][warp] = s2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < kTcThreads / 32; ++i) {
+      t0 += sm.red[0][i];
+      t1 += sm.red[1][i];
+      t2 += sm.red[2][i];
+    }
+    if (a.gradient_error) *a.gradient_error = (float)(t0 / (t1 + 1e-5));
+    if (a.surface_loss) *a.surface_loss = (float)(t2 / ((double)a.R * (double)a.S));
+    *a.ticket = 0;  // self-reset so that the workspace can be reused without a memset
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -194,3 +194,24 @@ def test_config4_hierarchical_full_patch(impl):
         assert linf(out[k], ref[k]) <= 1e-4, (k, linf(out[k], ref[k]))
     bad = int(((zv - ref["z_vals"]).abs() > 1e-3).sum())
     assert bad <= zv.numel() // 500, bad
+
+
+@pytest.mark.parametrize("S,bs,patch", [(64, 2, 9), (128, 1, 5), (32, 3, 6), (16, 2, 7)])
+def test_in_kernel_compositing_matches_composite_kernel(S, bs, patch):
+    """The tcgen05 core composites per ray itself when 128 % S == 0 (rays = aligned runs of its tiles, ragged last
+    tile included); flags bit 3 forces the separate composite_kernel.  Same association of the cumulative product,
+    so the weights agree to the last bits; the sums differ only by summation order."""
+    meta = dict(params="params_D8.npz", D=8, n_samples=S, n_importance=0, cos_anneal_ratio=0.6)
+    P, r = _build(meta, "tcgen05")
+    ro, rd, near, far = O.synthetic_rays(bs, patch, seed=11)
+    z = torch.randn(bs, 64, generator=torch.Generator().manual_seed(11))
+    inp = dict(rays_o=ro, rays_d=rd, near=near, far=far, z=z, w=O.style_mlp(P, z))
+    fused = _run_kernel(r, inp, meta)
+    assert r.last_launches == 2                                   # film + core
+    r.flags |= 8
+    split = _run_kernel(r, inp, meta)
+    assert r.last_launches == 3                                   # film + core + composite
+    for k in OUT_KEYS:
+        scale = 1.0 + float(split[k].abs().max())
+        assert linf(fused[k], split[k]) <= 2e-6 * scale, (k, linf(fused[k], split[k]))
+    assert linf(fused["weights"].sum(-1, keepdim=True), fused["weight_sum"]) < 1e-5
