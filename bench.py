@@ -403,6 +403,7 @@ def main():
 
     line_extra = {}
     if not args.no_side_legs:
+        line_extra["contract_b"] = contract_b_leg(renderer, sdf, resident, bs, flush, args.steps)
         line_extra["grad_step"] = grad_step_leg(renderer, sdf, col, devn, resident, R // bs, flush)
         try:
             line_extra["train_step"] = train_step_leg(dev, P, args.kernel, flush)
@@ -450,6 +451,50 @@ def main():
         line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)
     dist.destroy_process_group()
+
+
+def contract_b_leg(renderer, sdf, resident, bs, flush, steps):
+    """Rank 0: the same rays through contract B -- render + Generator.render_maps in ONE library call
+    (`OiRenderDesc.maps`): shading and the maps are composited in the tile tail of the render kernel, no per-point
+    tensor is written; outputs per ray: 6 maps (14 floats) + weight_sum / weight_max / color_fine / s_val."""
+    d_ro, d_rd, d_near, d_far, d_z = resident
+    dev = d_ro.device
+    lp = torch.tensor([0.33, 0.33, 0.33, 0.67, 0.67, 0.67, 0.01, 0.01, 0.01, 10.0], device=dev)   # lighting.py:9-12
+    ldir = torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(bs, 1)
+    bg = torch.ones(bs, 3, device=dev)
+
+    def step():
+        with torch.no_grad():
+            return renderer.render_with_maps(d_ro, d_rd, d_near, d_far, w=sdf.style(d_z), light_params=lp,
+                                             light_dir=ldir, bg_color=bg, resolution=PATCH, cos_anneal_ratio=1.0,
+                                             perturb_overwrite=0)
+    def timed():
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            step()
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) / steps, renderer.last_launches
+    R = d_ro.shape[0]
+    ms, nl = timed()                       # default: compositing in the render kernel, maps kernel after it
+    flags = renderer.flags
+    renderer.flags = flags | 16            # maps composited in the tile tail as well: nothing per-point is written
+    try:
+        ms_k, nl_k = timed()
+    finally:
+        renderer.flags = flags
+    return {"ms_per_step": ms, "value": R / (ms * 1e-3), "unit": "rays/s", "launches_per_step": nl,
+            "output_bytes_per_ray": 14 * 4 + 6 * 4,
+            "in_kernel_maps": {"ms_per_step": ms_k, "value": R / (ms_k * 1e-3), "launches_per_step": nl_k,
+                               "per_point_bytes_written": 0},
+            "what": "render + render_maps in one C-ABI call (OiRenderDesc.maps): no per-point tensor is handed to the "
+                    "caller; default = per-point tensors through the workspace + maps kernel, in_kernel_maps = flags "
+                    "bit 4, maps composited in the render kernel's tile tail"}
 
 
 def grad_step_leg(renderer, sdf, col, devn, resident, r1, flush):

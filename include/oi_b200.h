@@ -99,6 +99,7 @@ int oi_style_mlp(const OiNetParams* params, const float* z, float* w, int32_t n_
  * compute_sample_dist=False, blend_background=False, background_rgb=None).
  * R = n_rays, n = n_samples, m = n_importance, S = n + m.
  * ---------------------------------------------------------------------------------------------- */
+struct OiRenderMapsDesc;
 typedef struct OiRenderDesc {
   /* sizes */
   int32_t n_rays;            /* R; rays of instance b occupy [b*rays_per_instance, (b+1)*rays_per_instance) */
@@ -111,7 +112,9 @@ typedef struct OiRenderDesc {
   int32_t impl;              /* OiRenderImpl */
   int32_t flags;             /* bit 0 (OI_FLAG_DISCARD_SCRATCH): drop dead reverse-sweep scratch lines from L2 (discard.global.L2);
                               * bit 3 (value 8): keep the per-ray compositing in its own kernel even where the tcgen05 core
-                              * could do it (rays aligned with its 128-point tiles: 128 % (n_samples + n_importance) == 0) */
+                              * could do it (rays aligned with its 128-point tiles: 128 % (n_samples + n_importance) == 0);
+                              * bit 4 (value 16): with `maps`, composite the maps in the tile tail of the render kernel too
+                              * (nothing per-point is written at all; slower than the default, see below) */
   float cos_anneal_ratio;    /* renderer.py:273-274 */
   float reserved_f;
 
@@ -128,7 +131,7 @@ typedef struct OiRenderDesc {
   const void* packed_weights;/* blob written by oi_pack_weights */
 
   /* outputs (renderer.py:448-468); any pointer may be NULL to skip that tensor except `weights`
-   * (it carries alpha between the two phases) */
+   * (it carries alpha between the two phases; optional too when `maps` is given) */
   float* s_val;          /* [R,1] */
   float* cdf_fine;       /* [R,S] */
   float* weight_sum;     /* [R,1] */
@@ -153,6 +156,16 @@ typedef struct OiRenderDesc {
    * render_core kernel (the dominant kernel), so that callers can time it in isolation; NULL = off */
   void* evt_core_start;
   void* evt_core_stop;
+
+  /* Contract B: when non-NULL the call also produces the shading / compositing maps of
+   * Generator.render_maps (generator.py:80-174) for the rays it renders.  Of *maps the light (light_dir, bg_color,
+   * light_params or the by-value colours), rays_per_instance, the output-map pointers and z_min_per_ray are used; its
+   * input pointers are ignored (the inputs are this render's own results).  Every per-point output above, `weights`
+   * included, may then be NULL: the per-point tensors the caller does not ask for live in the workspace only (L2 for
+   * typical sizes) and oi_render_maps' kernel runs after the compositing, inside this call.  With flags bit 4, the
+   * tcgen05 core and 128 % (n + m) == 0 the maps are composited in the tail of the render kernel instead and nothing
+   * per-point is written (measured slower: 2.04 vs 1.78 ms at 16 384 rays x 64 -- kept as the contract-B variant). */
+  const struct OiRenderMapsDesc* maps;
 } OiRenderDesc;
 
 int oi_render_workspace_bytes(const OiRenderDesc* desc, size_t* bytes);

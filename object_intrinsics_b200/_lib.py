@@ -48,6 +48,7 @@ class OiRenderDesc(C.Structure):
         ("raw_color", f32p), ("z_vals_out", f32p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("evt_core_start", C.c_void_p), ("evt_core_stop", C.c_void_p),
+        ("maps", C.c_void_p),      # const OiRenderMapsDesc* (host pointer) or NULL
     ]
 
 

@@ -23,7 +23,8 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t film, scratch, partials, ticket, sdf_coarse, z_fine, z_fine2, tmp_raw_color, tmp_gradients, tmp_pts_norm, tmp_sdf;
+  size_t film, scratch, partials, ticket, sdf_coarse, z_fine, z_fine2, tmp_weights, tmp_pts, tmp_mid_z, tmp_weight_sum,
+      tmp_color_fine, tmp_raw_color, tmp_gradients, tmp_pts_norm, tmp_sdf;
   size_t total;
   int n_ctas;
   size_t scratch_stride;
@@ -34,6 +35,13 @@ int resolve_impl(const OiRenderDesc* d);
 bool fused_composite(const OiRenderDesc* d, int impl) {
   const int S = d->n_samples + d->n_importance;
   return impl == OI_IMPL_TCGEN05 && S <= 128 && 128 % S == 0 && (d->flags & 8) == 0;
+}
+
+// Contract B inside the render kernel (flags bit 4): the maps are composited in the tile tail and nothing per-point is
+// written.  Off by default: the tail runs on 4 of a slot's 8 epilogue warps and on the slot's critical path, and the
+// extra code pushes the kernel past the instruction cache (+0.29 ms at 16 384 x 64 vs +0.035 ms for the maps kernel).
+bool maps_in_kernel(const OiRenderDesc* d, int impl) {
+  return d->maps != nullptr && (d->flags & 16) != 0 && fused_composite(d, impl);
 }
 
 int resolve_impl(const OiRenderDesc* d) {
@@ -68,6 +76,13 @@ int plan_workspace(const OiRenderDesc* d, Workspace* w) {
   w->sdf_coarse = hier ? take((size_t)R * (d->up_sample_steps > 1 ? S : d->n_samples) * 4) : 0;
   w->z_fine = hier ? take((size_t)R * S * 4) : 0;
   w->z_fine2 = (hier && d->up_sample_steps > 1) ? take((size_t)R * S * 4) : 0;
+  // maps without in-kernel compositing: the per-point tensors the caller did not ask for go through the workspace
+  const bool maps_unfused = d->maps != nullptr && !maps_in_kernel(d, resolve_impl(d));
+  w->tmp_weights = (d->maps && !d->weights && maps_unfused) ? take((size_t)R * S * 4) : 0;
+  w->tmp_pts = (maps_unfused && !d->pts) ? take((size_t)R * S * 3 * 4) : 0;
+  w->tmp_mid_z = (maps_unfused && !d->mid_z_vals) ? take((size_t)R * S * 4) : 0;
+  w->tmp_weight_sum = (maps_unfused && !d->weight_sum) ? take((size_t)R * 4) : 0;
+  w->tmp_color_fine = (maps_unfused && !d->color_fine) ? take((size_t)R * 3 * 4) : 0;
   w->tmp_raw_color = d->raw_color ? 0 : take((size_t)R * S * 3 * 4);
   w->tmp_gradients = d->gradients ? 0 : take((size_t)R * S * 3 * 4);
   w->tmp_pts_norm = d->pts_norm ? 0 : take((size_t)R * S * 4);
@@ -97,7 +112,13 @@ int validate_render(const OiRenderDesc* d) {
   OI_CHECK_ARG(d->rays_o && d->rays_d && d->near && d->far, "rays_o/rays_d/near/far must be non-NULL");
   OI_CHECK_ARG(d->style_w && d->packed_weights, "style_w and packed_weights must be non-NULL");
   OI_CHECK_ARG(((uintptr_t)d->packed_weights & 127) == 0, "packed_weights must be 128-byte aligned");
-  OI_CHECK_ARG(d->weights != nullptr, "the `weights` output is mandatory");
+  OI_CHECK_ARG(d->weights != nullptr || d->maps != nullptr, "the `weights` output is mandatory (unless `maps` is given)");
+  if (d->maps) {
+    const OiRenderMapsDesc* mp = d->maps;
+    OI_CHECK_ARG(mp->rays_per_instance > 0 && d->n_rays % mp->rays_per_instance == 0,
+                 "maps: n_rays (%d) must be a multiple of maps->rays_per_instance (%d)", d->n_rays, mp->rays_per_instance);
+    OI_CHECK_ARG(mp->light_dir && mp->bg_color, "maps: light_dir and bg_color must be non-NULL");
+  }
   return OI_OK;
 }
 
@@ -174,7 +195,9 @@ int oi_render_launch_count(const OiRenderDesc* desc, int32_t* launches) {
   OI_CHECK_ARG(launches != nullptr, "launches is NULL");
   const bool hier = desc->n_importance > 0 && desc->z_vals_in == nullptr;
   // film, steps x [coarse, upsample], fine, [composite unless the core does it]
-  *launches = 3 + (hier ? 2 * desc->up_sample_steps : 0) - (fused_composite(desc, resolve_impl(desc)) ? 1 : 0);
+  const bool fused = fused_composite(desc, resolve_impl(desc));
+  *launches = 3 + (hier ? 2 * desc->up_sample_steps : 0) - (fused ? 1 : 0) +
+              ((desc->maps && !maps_in_kernel(desc, resolve_impl(desc))) ? 1 : 0);
   return OI_OK;
 }
 
@@ -274,10 +297,50 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   a.raw_color = d->raw_color ? d->raw_color : reinterpret_cast<float*>(ws + w.tmp_raw_color);
   a.z_out = d->z_vals_out;
   a.fuse_composite = fused_composite(d, impl) ? 1 : 0;
+  float* weights = d->weights;
+  float* weight_sum = d->weight_sum;
+  float* color_fine = d->color_fine;
+  const bool maps_fused = maps_in_kernel(d, impl);
+  if (d->maps && !maps_fused) {   // maps kernel after the render: every input of render_maps_kernel must exist somewhere
+    if (!weights) weights = reinterpret_cast<float*>(ws + w.tmp_weights);
+    if (!weight_sum) weight_sum = reinterpret_cast<float*>(ws + w.tmp_weight_sum);
+    if (!color_fine) color_fine = reinterpret_cast<float*>(ws + w.tmp_color_fine);
+    if (!a.pts) a.pts = reinterpret_cast<float*>(ws + w.tmp_pts);
+    if (!a.mid_z) a.mid_z = reinterpret_cast<float*>(ws + w.tmp_mid_z);
+    a.alpha = weights;
+  }
+  if (maps_fused) {
+    const OiRenderMapsDesc* mp = d->maps;
+    MapsKArgs& k = a.maps;
+    k.enabled = 1;
+    k.rays_per_image = mp->rays_per_instance;
+    k.light_dir = mp->light_dir;
+    k.bg_color = mp->bg_color;
+    k.light_params = mp->light_params;
+    for (int c = 0; c < 3; ++c) {
+      k.lp[c] = mp->ambient_color[c];
+      k.lp[3 + c] = mp->diffuse_color[c];
+      k.lp[6 + c] = mp->specular_color[c];
+    }
+    k.lp[9] = mp->shininess;
+    k.image = mp->image;
+    k.image_no_bg = mp->image_no_bg;
+    k.mask = mp->mask;
+    k.shading_map = mp->shading_map;
+    k.color_map = mp->color_map;
+    k.weight_sum_map = mp->weight_sum_map;
+    k.amb_shading_map = mp->amb_shading_map;
+    k.diff_shading_map = mp->diff_shading_map;
+    k.normal_map = mp->normal_map;
+    k.no_specular_map = mp->no_specular_map;
+    k.specular_map = mp->specular_map;
+    k.z_map = mp->z_map;
+    k.z_min_per_ray = mp->z_min_per_ray;
+  }
   if (a.fuse_composite) {
-    a.weight_sum = d->weight_sum;
+    a.weight_sum = weight_sum;
     a.weight_max = d->weight_max;
-    a.color_fine = d->color_fine;
+    a.color_fine = color_fine;
     a.s_val = d->s_val;
     a.gradient_error = d->gradient_error;
     a.surface_loss = d->surface_loss;
@@ -288,11 +351,26 @@ int oi_render_forward(const OiRenderDesc* d, void* stream) {
   rc = (impl == OI_IMPL_TCGEN05) ? launch_render_tc(a, st) : launch_render_ffma(a, st);
   if (rc) return rc;
   if (d->evt_core_stop) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d->evt_core_stop), st));
-  if (a.fuse_composite) return OI_OK;
-
-  return launch_composite(R, S, blob, d->depth, d->weights, a.raw_color, a.gradients, a.pts_norm, a.sdf,
-                          d->weight_sum, d->weight_max, d->color_fine, d->s_val, d->gradient_error, d->surface_loss,
+  if (a.fuse_composite && (!d->maps || maps_fused)) return OI_OK;
+  if (!a.fuse_composite) {
+    rc = launch_composite(R, S, blob, d->depth, weights, a.raw_color, a.gradients, a.pts_norm, a.sdf, weight_sum,
+                          d->weight_max, color_fine, d->s_val, d->gradient_error, d->surface_loss,
                           reinterpret_cast<float*>(ws + w.partials), ticket, st);
+    if (rc || !d->maps) return rc;
+  }
+
+  OiRenderMapsDesc md = *d->maps;   // the render's own results are the inputs of the maps kernel
+  md.n_rays = R;
+  md.n_samples = S;
+  md.weights = weights;
+  md.gradients = a.gradients;
+  md.raw_color = a.raw_color;
+  md.pts = a.pts;
+  md.mid_z_vals = a.mid_z;
+  md.weight_sum = weight_sum;
+  md.color_fine = color_fine;
+  md.rays_o = d->rays_o;
+  return launch_render_maps(md, st);
 }
 
 namespace {

@@ -100,6 +100,18 @@ __host__ __device__ inline size_t tc_section_floats(int depth) { return (size_t)
 // ------------------------------------------------------------------------------------------------
 // kernel argument blocks
 // ------------------------------------------------------------------------------------------------
+// Shading maps composited in the tail of the tcgen05 core (contract B): the parts of OiRenderMapsDesc the kernel needs.
+struct MapsKArgs {
+  int enabled, rays_per_image;    // rays_per_image = P*P (one image per instance)
+  const float* light_dir;         // [n_inst,3]
+  const float* bg_color;          // [n_inst,3]
+  const float* light_params;      // device [10] or NULL -> lp[]
+  float lp[10];                   // ambient[3], diffuse[3], specular[3], shininess
+  float *image, *image_no_bg, *mask, *shading_map, *color_map, *weight_sum_map;
+  float *amb_shading_map, *diff_shading_map, *normal_map, *no_specular_map, *specular_map, *z_map;
+  float* z_min_per_ray;
+};
+
 struct RenderKArgs {
   int R, rays_per_inst, n_inst;
   int S;         // samples per ray seen by this launch (n for the coarse pass, n+m for the fine pass)
@@ -126,6 +138,7 @@ struct RenderKArgs {
   float *weight_sum, *weight_max, *color_fine, *s_val, *gradient_error, *surface_loss;
   float* partials;      // [R,3] per-ray partial sums of the global scalars
   unsigned int* ticket;
+  MapsKArgs maps;
 };
 
 // launchers (each returns an OiStatus)

@@ -49,7 +49,7 @@ struct __align__(1024) TcSmem {
   float xch[2][128][8];                     // per slot / point: partial sums exchanged between the column halves
   unsigned long long acc_full[2], a_ready[2][4];   // a_ready[slot][chunk]: one arrival per epilogue warp
   unsigned long long ld_full[16][2];               // per epilogue warp / staging buffer: scratch re-read landed
-  float comp[2][4][9];                             // in-kernel compositing: per slot / warp {product, 8 partial sums}
+  float comp[2][4][26];                            // in-kernel compositing: per slot / warp {product, 8 + 17 partial sums}
   double red[3][20];                               // last CTA: reduction of the per-ray partials of the global scalars
   int is_last;
   uint32_t tmem_base;
@@ -125,6 +125,111 @@ __device__ __forceinline__ void issue_chunk_mmas(uint32_t acc, uint32_t abuf, ui
   }
 }
 
+// Contract B: Phong shading of one sample and per-ray compositing of the 12 maps of Generator.render_maps
+// (generator.py:80-174, lighting.py:126-225) in the tail of a tile, same arithmetic as render_maps_kernel.  Called by
+// the 128 tail threads of a tile slot (one per sample point); rays = aligned runs of S points.  Inlined into the kMaps
+// instantiation only (`a` is the __grid_constant__ kernel parameter: every field is a constant-bank operand; behind
+// a call it became a generic pointer and every store forced the next pointer to be re-loaded -- 30 k cycles per tile).
+__device__ __forceinline__ void maps_tail(const RenderKArgs& a, float (*comp)[26], int bar_id, int inst, int ray, bool valid,
+                                       float px, float py, float pz, float mid, float gx, float gy, float gz,
+                                       float rgb0, float rgb1, float rgb2, float wgt, float ws, float col0, float col1,
+                                       float col2, int lane, int wq) {
+  const int S = a.S, seg = S < 32 ? S : 32, lis = lane & (seg - 1);
+  const int wpr = S > 32 ? (S >> 5) : 1, wir = wq & (wpr - 1);
+  const float rgbv[3] = {rgb0, rgb1, rgb2};
+  // ---- contract B: Phong shading of this sample and compositing of the 12 maps of Generator.render_maps
+  //      (generator.py:80-174, lighting.py:126-225), same arithmetic as render_maps_kernel
+  const MapsKArgs& mp = a.maps;
+  const float colf[3] = {col0, col1, col2};
+  float lpar[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) lpar[i] = mp.light_params ? mp.light_params[i] : mp.lp[i];
+  float Lx = mp.light_dir[inst * 3], Ly = mp.light_dir[inst * 3 + 1], Lz = mp.light_dir[inst * 3 + 2];
+  {
+    const float ln = fmaxf(sqrtf(Lx * Lx + Ly * Ly + Lz * Lz), 1e-6f);
+    Lx /= ln;
+    Ly /= ln;
+    Lz /= ln;
+  }
+  const float nn = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-6f);
+  const float ux = gx / nn, uy = gy / nn, uz = gz / nn;
+  const float cosv = ux * Lx + uy * Ly + uz * Lz;
+  const float ang = fmaxf(cosv, 0.f);
+  float vx = a.rays_o[ray * 3] - px, vy = a.rays_o[ray * 3 + 1] - py,
+        vz = a.rays_o[ray * 3 + 2] - pz;
+  const float vn = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-6f);
+  vx /= vn;
+  vy /= vn;
+  vz /= vn;
+  const float rx = -Lx + 2.0f * (cosv * ux), ry = -Ly + 2.0f * (cosv * uy), rz = -Lz + 2.0f * (cosv * uz);
+  const float al = fmaxf(vx * rx + vy * ry + vz * rz, 0.f) * (cosv > 0.f ? 1.f : 0.f);
+  const float spw = powf(al, lpar[9]) * wgt;
+  float q[17];   // sh[3], ns[3], sp[3], df[3], n[3], z, zmin
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float diffc = lpar[3 + c] * ang, shade = lpar[c] + diffc;
+    q[c] = shade * wgt;
+    q[3 + c] = shade * rgbv[c] * wgt;
+    q[6 + c] = lpar[6 + c] * spw;
+    q[9 + c] = diffc * wgt;
+  }
+  q[12] = gx * wgt;
+  q[13] = gy * wgt;
+  q[14] = gz * wgt;
+  q[15] = mid * wgt;
+  q[16] = valid ? mid : 3.0e38f;
+  for (int dd = seg >> 1; dd >= 1; dd >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+      const float o = __shfl_xor_sync(0xffffffffu, q[i], dd);
+      q[i] = (i == 16) ? fminf(q[i], o) : q[i] + o;
+    }
+  }
+  if (S > 32) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 17; ++i) comp[wq][9 + i] = q[i];
+    }
+    named_bar_sync(bar_id, 128);
+    if (wir == 0 && lane == 0) {
+      for (int j = 1; j < wpr; ++j) {
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+          const float o = comp[wq + j][9 + i];
+          q[i] = (i == 16) ? fminf(q[i], o) : q[i] + o;
+        }
+      }
+    }
+  }
+  if (valid && lis == 0 && wir == 0) {
+    const int PP = mp.rays_per_image, bimg = ray / PP, pix = ray - bimg * PP;
+    auto put3 = [&](float* dst, float x0, float x1, float x2) {
+      if (!dst) return;
+      dst[((size_t)bimg * 3 + 0) * PP + pix] = x0;
+      dst[((size_t)bimg * 3 + 1) * PP + pix] = x1;
+      dst[((size_t)bimg * 3 + 2) * PP + pix] = x2;
+    };
+    auto put1 = [&](float* dst, float x) {
+      if (dst) dst[(size_t)bimg * PP + pix] = x;
+    };
+    const float r0 = q[3] + q[6], r1 = q[4] + q[7], r2 = q[5] + q[8];
+    const float* bg = mp.bg_color + bimg * 3;
+    put3(mp.image, r0 + bg[0] * (1.0f - ws), r1 + bg[1] * (1.0f - ws), r2 + bg[2] * (1.0f - ws));
+    put3(mp.image_no_bg, r0, r1, r2);
+    put3(mp.shading_map, q[0], q[1], q[2]);
+    put3(mp.color_map, colf[0], colf[1], colf[2]);
+    put1(mp.weight_sum_map, ws);
+    put1(mp.mask, fminf(fmaxf(ws, 1e-3f), 1.0f - 1e-3f));
+    put3(mp.amb_shading_map, lpar[0] * ws, lpar[1] * ws, lpar[2] * ws);
+    put3(mp.diff_shading_map, q[9], q[10], q[11]);
+    put3(mp.normal_map, q[12], q[13], q[14]);
+    put3(mp.no_specular_map, q[3], q[4], q[5]);
+    put3(mp.specular_map, q[6], q[7], q[8]);
+    put1(mp.z_map, q[15]);
+    if (mp.z_min_per_ray) mp.z_min_per_ray[ray] = q[16];
+  }
+}
+
 // Panel index (in the packed blob: fwd l=1..D-1 | colour-feature | reverse l=D-1..1) of MMA stage p of a tile.
 // Fine pass order: forward layers, reverse layers, colour-feature layer LAST (its operand h_D is re-loaded from the
 // scratch, its result is consumed straight from TMEM by the colour epilogue).
@@ -133,7 +238,9 @@ __device__ __forceinline__ int stage_panel(int p, int D, int coarse) {
   return (p < 2 * D - 2) ? p + 1 : D - 1;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKArgs a) {
+// kMaps: the contract-B variant (shading maps composited in the tile tail); the plain variant carries none of its code.
+template <bool kMaps>
+__global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_constant__ RenderKArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -701,7 +808,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
             }
           }
           if (pc.valid) {
-            a.alpha[(size_t)pc.ray * S + pc.si] = wgt;   // the `weights` output
+            if (a.alpha) a.alpha[(size_t)pc.ray * S + pc.si] = wgt;   // the `weights` output
             if (lis == 0 && wir == 0) {                  // first point of the ray: per-ray outputs
               const int ray = pc.ray;
               if (a.weight_sum) a.weight_sum[ray] = v[0];
@@ -717,6 +824,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderKA
               a.partials[(size_t)ray * 3 + 2] = v[7];
             }
           }
+          if (kMaps)
+            maps_tail(a, sm.comp[t], 3 + t, inst, pc.ray, pc.valid, pc.px, pc.py, pc.pz, pc.mid, gx, gy, gz, to[1], to[2],
+                      to[3], wgt, v[0], v[2], v[3], v[4], lane, warp & 3);
         }
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);  // film table / exchange buffer of this slot may be reused now
@@ -888,8 +998,15 @@ int launch_render_tc(const RenderKArgs& a, cudaStream_t st) {
   if (a.D < 2) return set_error(OI_ERR_UNSUPPORTED, "the tcgen05 core needs depth >= 2 (use OI_IMPL_FFMA)");
   int n_ctas = 0;
   render_tc_scratch_floats(a.D, &n_ctas, a.n_tiles);
-  OI_CHECK_CUDA(cudaFuncSetAttribute(render_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem)));
-  render_tc_kernel<<<n_ctas, kTcThreads, sizeof(TcSmem), st>>>(a);
+  if (a.maps.enabled) {
+    OI_CHECK_CUDA(cudaFuncSetAttribute(render_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(TcSmem)));
+    render_tc_kernel<true><<<n_ctas, kTcThreads, sizeof(TcSmem), st>>>(a);
+  } else {
+    OI_CHECK_CUDA(cudaFuncSetAttribute(render_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(TcSmem)));
+    render_tc_kernel<false><<<n_ctas, kTcThreads, sizeof(TcSmem), st>>>(a);
+  }
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

@@ -149,3 +149,30 @@ def render_maps(generator, bs, render_out, rays_info, prior_info, return_raw):
     render_out.pop("gradients", None)      # the reference deletes these two from the dict (generator.py:126,129)
     render_out.pop("pts", None)
     return ret
+
+
+def render_and_maps(generator, renderer, bs, rays_info, prior_info, w, return_raw=False, cos_anneal_ratio=1.0,
+                    perturb_overwrite=-1):
+    """Contract B for the no-grad renders of a training step and for inference: what `Generator.forward` does between
+    generator.py:245 (`self.renderer.render(...)`) and :174 (`render_maps`) in ONE library call -- the per-point
+    tensors never leave the chip when the render kernel can composite in its tile tail.  Returns (render_out with the
+    per-ray keys and the two scalars, maps) like the two reference calls would; not differentiable."""
+    light = prior_info["light"]
+    base = light.light
+    dev = rays_info["rays_o"].device
+    direction = base.param_direction / torch.linalg.norm(base.param_direction)
+    light_dir = torch.einsum("bij,j->bi", light.w2b[:, :3, :3].to(dev), direction.to(dev))
+    light_params = torch.cat([torch.as_tensor(v, dtype=torch.float32, device=dev).reshape(-1).expand(n)
+                              for v, n in ((base.ambient_color, 3), (base.diffuse_color, 3),
+                                           (base.specular_color, 3), (base.shininess, 1))])
+    bg = generator.bg_color(bs)
+    ro = rays_info["rays_o"].reshape(-1, 3)
+    rd = rays_info["rays_d"].reshape(-1, 3)
+    near, far = rays_info.get("near"), rays_info.get("far")
+    if near is None:                                                    # near_far_from_sphere, generator.py:336-342
+        mid = -(ro * rd).sum(-1, keepdim=True) / (rd * rd).sum(-1, keepdim=True)
+        near, far = mid - 1.0, mid + 1.0
+    return renderer.render_with_maps(ro, rd, near, far, w=w, light_params=light_params, light_dir=light_dir,
+                                     bg_color=bg[:, :, 0, 0], resolution=int(generator.resolution),
+                                     return_raw=return_raw, cos_anneal_ratio=cos_anneal_ratio,
+                                     perturb_overwrite=perturb_overwrite)

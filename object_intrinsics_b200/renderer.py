@@ -384,7 +384,28 @@ class NeuSRenderer:
         return ret
 
     # -------------------------------------------------------------------------------------------
-    def _render_cuda(self, params, rays_o, rays_d, near, far, w, cos_anneal_ratio, t_rand, z_vals, return_z_vals):
+    def render_with_maps(self, rays_o, rays_d, near, far, *, w, light_params, light_dir, bg_color, resolution,
+                         return_raw=False, cos_anneal_ratio=0.0, perturb_overwrite=-1, t_rand=None):
+        """Contract B, no-grad: `render` (renderer.py:351-473) and `Generator.render_maps`
+        (generator.py:80-174) in ONE call of the C-ABI (`OiRenderDesc.maps`).  Returns (per-ray render outputs +
+        the two global scalars, maps [bs,C,P,P]); no per-point tensor is allocated or written to HBM when the tcgen05
+        core composites in its tile tail (128 % S == 0).  light_params [10] = ambient[3], diffuse[3], specular[3],
+        shininess; light_dir, bg_color [bs,3].  Differentiable callers use `render` + `generator_ops.render_maps`."""
+        if not rays_o.is_cuda:
+            raise RuntimeError("object_intrinsics_b200 has no CPU path: rays must be CUDA tensors")
+        perturb = self.perturb if perturb_overwrite < 0 else perturb_overwrite
+        R = rays_o.shape[0]
+        if t_rand is None and perturb > 0:
+            t_rand = torch.rand([R, 1], device=rays_o.device) - 0.5                           # renderer.py:372
+        params = collect_params(self.sdf_network, self.color_network, self.deviation_network, with_style=False)
+        maps = dict(light_params=light_params, light_dir=light_dir, bg_color=bg_color, resolution=int(resolution),
+                    return_raw=bool(return_raw))
+        with torch.no_grad():
+            return self._render_cuda(params, rays_o, rays_d, near, far, w, float(cos_anneal_ratio), t_rand, None, False,
+                                     maps=maps)
+
+    def _render_cuda(self, params, rays_o, rays_d, near, far, w, cos_anneal_ratio, t_rand, z_vals, return_z_vals,
+                     maps=None):
         L = _lib.lib()
         dev = rays_o.device
         f32 = dict(device=dev, dtype=torch.float32)
@@ -405,10 +426,11 @@ class NeuSRenderer:
         lin_c, lin_f = self._linspaces(dev)
 
         out = {}
-        for k in OUT_KEYS_PER_POINT:
-            out[k] = torch.empty((R, S), **f32)
-        for k in OUT_KEYS_PER_POINT3:
-            out[k] = torch.empty((R, S, 3), **f32)
+        if maps is None:
+            for k in OUT_KEYS_PER_POINT:
+                out[k] = torch.empty((R, S), **f32)
+            for k in OUT_KEYS_PER_POINT3:
+                out[k] = torch.empty((R, S, 3), **f32)
         for k in OUT_KEYS_PER_RAY:
             out[k] = torch.empty((R, 1), **f32)
         out["color_fine"] = torch.empty((R, 3), **f32)
@@ -430,8 +452,24 @@ class NeuSRenderer:
         d.packed_weights = blob.data_ptr()
         for k in OUT_KEYS_PER_POINT + OUT_KEYS_PER_POINT3 + OUT_KEYS_PER_RAY + ("color_fine", "gradient_error",
                                                                                 "surface_loss"):
-            setattr(d, k, out[k].data_ptr())
+            setattr(d, k, _lib.ptr(out.get(k)))
         d.z_vals_out = _lib.ptr(out.get("z_vals"))
+        map_out = None
+        if maps is not None:
+            from .generator_ops import _MAPS_BASE, _MAPS_RAW, _MAP_CHANNELS
+            P = maps["resolution"]
+            names = _MAPS_BASE + (_MAPS_RAW if maps["return_raw"] else ())
+            map_out = {k: torch.empty((n_inst, _MAP_CHANNELS.get(k, 3), P, P), **f32) for k in names}
+            keep = [prep(maps[k]) for k in ("light_params", "light_dir", "bg_color")]
+            md = _lib.OiRenderMapsDesc()
+            md.n_rays, md.rays_per_instance, md.n_samples = R, P * P, S
+            md.light_params, md.light_dir, md.bg_color = [t.data_ptr() for t in keep]
+            for k, t in map_out.items():
+                setattr(md, k, t.data_ptr())
+            if maps["return_raw"]:
+                zmin = torch.empty((R,), **f32)
+                md.z_min_per_ray = zmin.data_ptr()
+            d.maps = C.addressof(md)
         if self.core_events is not None:
             d.evt_core_start, d.evt_core_stop = self.core_events[0].cuda_event, self.core_events[1].cuda_event
 
@@ -445,6 +483,10 @@ class NeuSRenderer:
             nl = C.c_int32(0)
             L.oi_render_launch_count(C.byref(d), C.byref(nl))
         self.last_launches = nl.value
+        if map_out is not None:
+            if maps["return_raw"]:
+                map_out["z_min"] = zmin.reshape(n_inst, -1).min(-1).values
+            return out, map_out
         return out
 
     # -------------------------------------------------------------------------------------------

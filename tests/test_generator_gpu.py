@@ -155,3 +155,48 @@ def test_render_maps_backward_matches_fp64_autograd(return_raw):
         scale = float(g64.abs().max()) + 1e-12
         err = float((g.detach().cpu().double().reshape(g64.shape) - g64).abs().max()) / scale
         assert err < 2e-4, (n, err, scale)
+
+
+@pytest.mark.parametrize("n,m,impl,raw,in_kernel", [(64, 0, "tcgen05", True, True), (32, 0, "tcgen05", False, True),
+                                                    (64, 0, "tcgen05", True, False), (16, 4, "tcgen05", True, True),
+                                                    (16, 0, "ffma", False, False)])
+def test_contract_b_single_call_matches_render_then_maps(n, m, impl, raw, in_kernel):
+    """`render_and_maps` (OiRenderDesc.maps: maps composited in the tail of the render kernel when 128 % S == 0,
+    else render -> composite -> maps kernel inside the one call) vs the two-call path `render` + `render_maps`,
+    which the tests above pin to the reference's fixtures."""
+    from helpers import load_params
+    from oracle import neus_oracle as O
+    from object_intrinsics_b200 import fields, generator_ops
+    from object_intrinsics_b200.renderer import NeuSRenderer
+    P = load_params("params_D8.npz")
+    sdf, col, dev = fields.build_networks(D=8, device="cuda")
+    fields.load_flat_params(sdf, col, dev, P)
+    r = NeuSRenderer(None, sdf, dev, col, n_samples=n, n_importance=m, n_outside=0, up_sample_steps=1, perturb=0,
+                     impl=impl)
+    if in_kernel:
+        r.flags |= 16                                             # maps composited in the render kernel's tile tail
+    bs, res = 3, 10                                               # 300 rays: ragged last tile of every instance
+    ro, rd, near, far = [t.cuda() for t in O.synthetic_rays(bs, res, seed=4)]
+    w = O.style_mlp(P, torch.randn(bs, 64, generator=torch.Generator().manual_seed(4))).cuda()
+    direction = torch.tensor([0.3, -0.5, -0.8])
+    base = types.SimpleNamespace(param_direction=(direction / direction.norm()).cuda(),
+                                 ambient_color=torch.full((3,), 0.4), diffuse_color=torch.full((3,), 0.6),
+                                 specular_color=torch.full((3,), 0.3), shininess=torch.tensor(7.0))
+    bg = torch.tensor([[0.1, 0.5, 0.9], [0.7, 0.2, 0.4], [0.3, 0.3, 0.8]]).cuda()
+    gen = types.SimpleNamespace(resolution=res, bg_color=lambda k: bg[:, :, None, None].expand(k, 3, res, res))
+    prior = {"light": types.SimpleNamespace(light=base, w2b=torch.eye(4).repeat(bs, 1, 1).cuda())}
+    rays_info = {"rays_o": ro.reshape(bs, res, res, 3), "rays_d": rd.reshape(bs, res, res, 3), "near": near, "far": far}
+    with torch.no_grad():
+        out2 = r.render(ro, rd, near, far, cos_anneal_ratio=0.8, perturb_overwrite=0, w=w)
+        maps2 = generator_ops.render_maps(gen, bs, dict(out2), rays_info, prior, raw)
+        launches2 = r.last_launches + 1
+        out1, maps1 = generator_ops.render_and_maps(gen, r, bs, rays_info, prior, w, return_raw=raw,
+                                                    cos_anneal_ratio=0.8, perturb_overwrite=0)
+    torch.cuda.synchronize()
+    assert r.last_launches <= launches2 - (1 if in_kernel and (n + m) in (16, 32, 64, 128) and impl == "tcgen05" else 0)
+    assert set(maps1) == set(maps2)
+    for k in maps2:
+        assert linf(maps1[k].cpu(), maps2[k].cpu()) < 5e-6, (k, linf(maps1[k].cpu(), maps2[k].cpu()))
+    for k in ("weight_sum", "weight_max", "color_fine", "s_val", "gradient_error", "surface_loss"):
+        assert linf(out1[k].cpu(), out2[k].cpu()) < 5e-6, k
+    assert "weights" not in out1 and "pts" not in out1            # nothing per-point is materialised

@@ -125,8 +125,10 @@ def measure(dev, P, kernel="auto", flush=None, shape="cfg5", steps=8, shading="k
     def d_step(pipe, real, key):
         with torch.no_grad():
             ro, rd, near, far = rays()
-            out = render(ro, rd, near, far)
-            maps = generator_ops.render_maps(gen, bs, out, {"rays_o": ro}, {"light": light}, False)
+            # contract B: render + render_maps in one library call, no per-point tensor materialised for the caller
+            _, maps = generator_ops.render_and_maps(gen, renderer, bs, {"rays_o": ro, "rays_d": rd, "near": near,
+                                                                        "far": far}, {"light": light}, sdf.style(z),
+                                                    return_raw=False, cos_anneal_ratio=1.0)
             return pipe(maps[key]), pipe(real)
 
     def step():
