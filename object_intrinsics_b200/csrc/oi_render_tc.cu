@@ -102,6 +102,10 @@ using tc::named_bar_sync;
 #ifndef OI_TC_SLEEP_PRODUCER
 #define OI_TC_SLEEP_PRODUCER 400u
 #endif
+#ifndef OI_TC_CHUNK_UNROLL   // unroll factor of the four-chunk loops of the epilogue stages (code size vs I-cache)
+#define OI_TC_CHUNK_UNROLL 4
+#endif
+constexpr int kChunkUnroll = OI_TC_CHUNK_UNROLL;
 #ifndef OI_TC_SLEEP_MMA
 #define OI_TC_SLEEP_MMA 100u
 #endif
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
           }
           const uint32_t wbase = smem_u32(sm.w[stage]);
           const uint32_t abuf = buf + (p & 1) * 128, acc = buf + ((p + 1) & 1) * 128;
-#pragma unroll
+#pragma unroll kChunkUnroll
           for (int c = 0; c < 4; ++c) {
             mbar_wait_backoff(&sm.a_ready[t][c], ar_phase, OI_TC_SLEEP_MMA);
             tc::fence_after_thread_sync();
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
         OI_PROF(2);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
-#pragma unroll
+#pragma unroll kChunkUnroll
         for (int c = 0; c < 4; ++c) {
           float4* sb = reinterpret_cast<float4*>(gchunk(l, c)) + lane;   // my 16 bytes of each of the chunk's 4 quads
           tc::wait_ld();
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
         OI_PROF(2);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
-#pragma unroll
+#pragma unroll kChunkUnroll
         for (int c = 0; c < 4; ++c) {
           uint4* sb = reinterpret_cast<uint4*>(gchunk(D - 1, c)) + lane;
           tc::wait_ld();
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
         OI_PROF(6);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
-#pragma unroll
+#pragma unroll kChunkUnroll
         for (int c = 0; c < 4; ++c, ++k) {
           OI_PROF2(0);
           const float4* lb = load_wait();
@@ -645,7 +649,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
         OI_PROF(6);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
-#pragma unroll
+#pragma unroll kChunkUnroll
         for (int c = 0; c < 4; ++c, ++k) {
           const uint4* lb = reinterpret_cast<const uint4*>(load_wait());
           uint4 hs[4];
@@ -710,7 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
         OI_PROF(4);
         uint32_t ub[2][16];
         tc::tmem_ld16_async(acc, ub[0]);
-#pragma unroll
+#pragma unroll kChunkUnroll
         for (int c = 0; c < 4; ++c) {
           tc::wait_ld();
           if (c < 3) tc::tmem_ld16_async(acc + (c + 1) * 16, ub[(c + 1) & 1]);
