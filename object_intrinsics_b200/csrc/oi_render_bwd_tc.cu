@@ -34,6 +34,9 @@
 #ifndef OI_BWD_PF2
 #define OI_BWD_PF2 1   // octs of look-ahead of the scratch re-reads in stages that re-read one slab
 #endif
+#ifndef OI_BWD_L2PF
+#define OI_BWD_L2PF 1   // prefetch a stage's scratch re-reads into L2 at the start of the stage
+#endif
 #ifndef OI_BWD_PF4
 #define OI_BWD_PF4 1   // ... in stages that re-read two slabs
 #endif
@@ -303,6 +306,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       mbar_arrive(&sm.a_ready[t]);
     };
     auto no_load = [](int, float4 (&)[1]) {};
+    // L2 prefetch of everything this warp re-reads from one slab in the coming stage: 16 channel quads x 512 B
+    // (the slabs were written tens of microseconds ago and have left the L2); p_q0 = this thread's float4 of quad Q0
+    auto pf_slab = [&](const float4* p_q0) {
+#if OI_BWD_L2PF
+      const float4* base = p_q0 - lane + (lane & 3) * 8;
+      l2_prefetch(base + (size_t)(lane >> 2) * 128);
+      l2_prefetch(base + (size_t)((lane >> 2) + 8) * 128);
+#endif
+    };
 
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
       const int lt = 2 * pi + t;   // tile index inside this launch
@@ -415,6 +427,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // ---------------- colour features -> slot UC; t_{D-1} = w_sigma gamma cos(a_{D-1}) ----------------
       {
         const float4* fl = OI_FILM4(D - 1);
+        pf_slab(&OI_ARG(D - 1, Q0));
         run_stage<2, true, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
           b[0] = OI_ARG(D - 1, Q0 + 2 * o);
           b[1] = OI_ARG(D - 1, Q0 + 2 * o + 1);
@@ -443,6 +456,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = D - 1; l >= 1; --l) {
         const float4* fl = OI_FILM4(l - 1);
         const float gscale = (l - 1 == 0) ? kInvWScale : 1.0f;   // gamma'_0 is unscaled
+        pf_slab(&OI_ARG(l - 1, Q0));
         run_stage<2, true, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
           b[0] = OI_ARG(l - 1, Q0 + 2 * o);
           b[1] = OI_ARG(l - 1, Q0 + 2 * o + 1);
@@ -494,6 +508,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       float nc0 = 0.f, nc1 = 0.f, nc2 = 0.f;   // W_cg^T u_bar_c, this thread's channels
       {
         const float4* fl = OI_FILM4(OI_MAX_DEPTH);
+        pf_slab(&OI_CTA(kCtaUC, Q0));
         run_stage<2, false, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
           b[0] = OI_CTA(kCtaUC, Q0 + 2 * o);
           b[1] = OI_CTA(kCtaUC, Q0 + 2 * o + 1);
@@ -561,6 +576,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
       {
         const float4* fl = OI_FILM4(0);
+        pf_slab(&OI_ARG(0, Q0));
+        pf_slab(&OI_CTA(kCtaG + 0, Q0));
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
           b[0] = OI_ARG(0, Q0 + 2 * o);
           b[1] = OI_ARG(0, Q0 + 2 * o + 1);
@@ -611,6 +628,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // ---------------- backward of the reverse sweep, l = 1..D-2: t_bar_l = W_l g_bar_l ----------------
       for (int l = 1; l < D - 1; ++l) {
         const float4* fl = OI_FILM4(l);
+        pf_slab(&OI_ARG(l, Q0));
+        pf_slab(&OI_CTA(kCtaG + l, Q0));
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
           b[0] = OI_ARG(l, Q0 + 2 * o);
           b[1] = OI_ARG(l, Q0 + 2 * o + 1);
@@ -641,6 +660,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       {
         const int l = D - 1;
         const float4* fl = OI_FILM4(l);
+        pf_slab(&OI_ARG(l, Q0));
+        pf_slab(&OI_CTA(kCtaHB, Q0));
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
           b[0] = OI_ARG(l, Q0 + 2 * o);
           b[1] = OI_ARG(l, Q0 + 2 * o + 1);
@@ -677,6 +698,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         const int k = l - 1;
         const float4* fl = OI_FILM4(k);
         const float gsc = (k == 0) ? 1.0f : kWScale;
+        pf_slab(&OI_ARG(k, Q0));
+        pf_slab(&OI_CTA(kCtaG + k, Q0));
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
           b[0] = OI_ARG(k, Q0 + 2 * o);
           b[1] = OI_ARG(k, Q0 + 2 * o + 1);
