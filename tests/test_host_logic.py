@@ -82,6 +82,44 @@ def test_backward_and_augment_argument_validation_without_gpu():
     assert L.oi_selftest_wgrad(None, None, 1, 1, 0, 0, 1, 1, None, None, None) == -1
 
 
+def test_maps_argument_validation_without_gpu():
+    """oi_render_maps / oi_render_maps_backward / OiRenderDesc.maps (contract B): descriptors are validated before any
+    CUDA call, struct sizes match the header (ctypes mirrors are laid out field by field)."""
+    from object_intrinsics_b200 import _lib
+    L = _lib.lib()
+    n = C.c_size_t(0)
+    m = _lib.OiRenderMapsDesc()
+    assert L.oi_render_maps(C.byref(m), None) == -1                           # n_rays == 0
+    m.n_rays, m.rays_per_instance, m.n_samples = 12, 5, 4
+    assert L.oi_render_maps(C.byref(m), None) == -1 and b"bad sizes" in L.oi_last_error()
+    m.rays_per_instance = 6
+    assert L.oi_render_maps(C.byref(m), None) == -1 and b"NULL" in L.oi_last_error()
+    bd = _lib.OiRenderMapsBwdDesc()
+    assert L.oi_render_maps_backward(C.byref(bd), None) == -1
+    bd.fwd.n_rays, bd.fwd.rays_per_instance, bd.fwd.n_samples = 12, 6, 4
+    assert L.oi_render_maps_backward(C.byref(bd), None) == -1 and b"NULL" in L.oi_last_error()
+    assert C.sizeof(_lib.OiRenderMapsDesc) == 256 and C.sizeof(_lib.OiRenderMapsBwdDesc) == 408
+    assert C.sizeof(_lib.OiRenderDesc) == 288
+    # OiRenderDesc.maps: `weights` may be NULL only together with a maps descriptor; the maps descriptor is checked
+    d = _lib.OiRenderDesc()
+    d.n_rays, d.rays_per_instance, d.n_samples, d.depth = 12, 6, 16, 8
+    for k in ("rays_o", "rays_d", "near", "far", "style_w"):
+        setattr(d, k, 256)
+    d.packed_weights = 256
+    assert L.oi_render_workspace_bytes(C.byref(d), C.byref(n)) == -1 and b"weights" in L.oi_last_error()
+    d.maps = C.addressof(m)
+    assert L.oi_render_workspace_bytes(C.byref(d), C.byref(n)) == -1 and b"light_dir" in L.oi_last_error()
+    m.light_dir, m.bg_color = 256, 256
+    assert L.oi_render_workspace_bytes(C.byref(d), C.byref(n)) == 0 and n.value > 0
+    launches = C.c_int32(0)
+    assert L.oi_render_launch_count(C.byref(d), C.byref(launches)) == 0
+    assert launches.value == 3        # film, core (compositing in its tail: 128 % 16 == 0), maps kernel
+    d.flags = 16                      # maps composited in the tile tail as well
+    assert L.oi_render_launch_count(C.byref(d), C.byref(launches)) == 0 and launches.value == 2
+    d.n_samples, d.n_importance, d.up_sample_steps, d.flags = 16, 4, 1, 0      # S = 20: separate composite kernel
+    assert L.oi_render_launch_count(C.byref(d), C.byref(launches)) == 0 and launches.value == 6
+
+
 def test_grad_mode_renderer_rejects_ray_gradients_and_bad_grad_impl():
     from object_intrinsics_b200 import fields
     from object_intrinsics_b200.renderer import NeuSRenderer, film_tables
