@@ -373,6 +373,22 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    # per-rank view (every rank samples its own GPU): slowest rank's step time, lowest median SM clock, union of the
+    # throttle reasons -- at N > 1 `value` is bounded by the slowest GPU of the box
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([total_ms / args.steps, float(sum(core_ms) / len(core_ms)), float(clocks["sm_mhz"] or 0),
+                             float(sum(1 << i for i, k in enumerate(("hw_slowdown", "sw_thermal_slowdown",
+                                                                     "hw_thermal_slowdown", "hw_power_brake",
+                                                                     "sw_power_cap")) if k in clocks["reasons"]))],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(t[0]), 4) for t in allr],
+                    "core_kernel_ms": [round(float(t[1]), 4) for t in allr],
+                    "sm_mhz": [int(t[2]) for t in allr], "throttle_bits": [int(t[3]) for t in allr],
+                    "throttle_bit_names": ["hw_slowdown", "sw_thermal_slowdown", "hw_thermal_slowdown",
+                                           "hw_power_brake", "sw_power_cap"]}
 
     # whole-job numbers: units summed over ranks / max elapsed time over ranks (no data-path collective)
     value, _, total_s = aggregate_throughput(R * args.steps, total_ms * 1e-3)
@@ -442,6 +458,7 @@ def main():
                              "frac": hbm_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "path is compute-bound (8100 FLOP/B); reported because BASELINE north_star asks"}},
         "clocks": clocks,
+        "per_rank": per_rank,
         "bs1": bs1,
         "grad_step_ddp": ddp_info,
         "lib_stamp": lib_stamp(),
