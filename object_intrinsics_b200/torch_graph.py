@@ -49,8 +49,10 @@ def _excl_cumprod(x):
     return torch.cumprod(torch.cat([ones, x], -1), -1)[:, :-1]
 
 
-def _sample_fine(P, D, rays_o, rays_d, z_vals, w, n, m):
-    """renderer.py:389-413 (up_sample_steps == 1) + sample_pdf :44-74, under no_grad."""
+def _sample_fine(P, D, rays_o, rays_d, z_vals, w, n, m, inv_s=64.0):
+    """One up-sampling step: renderer.py:137-181 (`up_sample` with the given inv_s) + sample_pdf :44-74 + the sort of
+    cat_z_vals :183-197, under no_grad.  The SDF is evaluated at all n current z (the reference evaluates the new
+    points only and gathers; per point the value is the same)."""
     R = rays_o.shape[0]
     bs = w.shape[0]
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
@@ -63,8 +65,8 @@ def _sample_fine(P, D, rays_o, rays_d, z_vals, w, n, m):
     cos_val = (sdf[:, 1:] - sdf[:, :-1]) / (dz + 1e-5)
     prev_cos = torch.cat([torch.zeros_like(cos_val[:, :1]), cos_val[:, :-1]], -1)
     cos_val = torch.minimum(prev_cos, cos_val).clip(-1e3, 0.0) * inside
-    prev_cdf = torch.sigmoid((mid_sdf - cos_val * dz * 0.5) * 64.0)
-    next_cdf = torch.sigmoid((mid_sdf + cos_val * dz * 0.5) * 64.0)
+    prev_cdf = torch.sigmoid((mid_sdf - cos_val * dz * 0.5) * inv_s)
+    next_cdf = torch.sigmoid((mid_sdf + cos_val * dz * 0.5) * inv_s)
     alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)
     weights = alpha * _excl_cumprod(1.0 - alpha + 1e-7) + 1e-5
     pdf = weights / weights.sum(-1, keepdim=True)
@@ -93,11 +95,15 @@ def render_differentiable(renderer, rays_o, rays_d, near, far, w, cos_anneal_rat
         if t_rand is not None:
             z_vals = z_vals + t_rand * 2.0 / n
         if m > 0:
-            if renderer.up_sample_steps != 1:
-                raise NotImplementedError("up_sample_steps != 1")
-            with torch.no_grad():
-                z_vals = _sample_fine({k: v.detach() for k, v in named.items()}, D, rays_o.detach(), rays_d.detach(),
-                                      z_vals.detach(), w.detach(), n, m)
+            steps = max(int(renderer.up_sample_steps), 1)
+            if m % steps != 0:
+                raise ValueError(f"n_importance ({m}) must be a multiple of up_sample_steps ({steps})")
+            with torch.no_grad():                                           # renderer.py:400-413
+                Pd = {k: v.detach() for k, v in named.items()}
+                z_vals = z_vals.detach()
+                for i in range(steps):
+                    z_vals = _sample_fine(Pd, D, rays_o.detach(), rays_d.detach(), z_vals, w.detach(),
+                                          n + i * (m // steps), m // steps, 64.0 * 2 ** i)
     S = z_vals.shape[1]
     dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full_like(z_vals[:, :1], sample_dist)], -1)
     mid_z = z_vals + dists * 0.5

@@ -25,19 +25,20 @@ def _nets(P, D, dtype):
     return sdf.to(dtype), col.to(dtype), dev.to(dtype)
 
 
-def _renderer(sdf, col, dev, n, m):
+def _renderer(sdf, col, dev, n, m, steps=1):
     return types.SimpleNamespace(sdf_network=sdf, color_network=col, deviation_network=dev, n_samples=n,
-                                 n_importance=m, up_sample_steps=1)
+                                 n_importance=m, up_sample_steps=steps)
 
 
 def test_forward_matches_oracle_fp64():
-    for name in ("cfg1_n16_m0", "cfg1_n16_m4_jit", "cfgd_n16_m4_D8"):
+    # the last two: up_sample_steps = 2 / 4 (renderer.py:400-413), fixtures of the unmodified reference
+    for name in ("cfg1_n16_m0", "cfg1_n16_m4_jit", "cfgd_n16_m4_D8", "cfgs_n16_m8_s2", "cfgs_n16_m12_s4_D8"):
         meta, inp, r32, r64 = load_case(name)
         P = load_params(meta["params"], torch.float64)
         sdf, col, dev = _nets(P, meta["D"], torch.float64)
         a = {k: v.double() for k, v in inp.items()}
         a["w"] = r64["w"]      # the fp64 reference run derived w from z in fp64
-        r = _renderer(sdf, col, dev, meta["n_samples"], meta["n_importance"])
+        r = _renderer(sdf, col, dev, meta["n_samples"], meta["n_importance"], meta.get("up_sample_steps", 1))
         old = torch.get_default_dtype()
         torch.set_default_dtype(torch.float64)
         try:
