@@ -17,7 +17,8 @@
 //     buffer.  The k-blocks of a chunk are issued as soon as the chunk is stored, so a slot's tensor work runs
 //     behind its own epilogue (only the last 6 of the 24 MMAs of a layer are exposed) and the other slot fills the
 //     rest.
-// Warp roles: 0-7 epilogue of tile slot 0, 8-15 of slot 1, 16 TMA producer, 17 / 18 MMA issuer of slot 0 / 1.
+// Warp roles: 0-7 epilogue of tile slot 0, 8-15 of slot 1 (112 registers after setmaxnreg), 16 TMA producer,
+// 17 / 18 MMA issuer of slot 0 / 1, 19 idle (32 registers).
 #include "oi_internal.cuh"
 #include "oi_render_common.cuh"
 #include "oi_tc.cuh"
@@ -26,7 +27,7 @@ namespace oi {
 
 namespace {
 
-constexpr int kTcThreads = 608;            // 16 epilogue warps + TMA producer + one MMA issuer per tile slot
+constexpr int kTcThreads = 640;            // 5 warpgroups: 16 epilogue warps + {TMA producer, 2 MMA issuers, 1 idle warp}
 constexpr int kEpiThreadsPerSlot = 256;     // 8 warps per tile slot
 constexpr int kEpiWarpsPerSlot = 8;
 constexpr int kProducerWarp = 16, kMmaWarp = 17;   // MMA issuer of slot t = warp kMmaWarp + t
@@ -284,6 +285,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_base;
 
+  // the service warpgroup hands its registers to the four epilogue warpgroups: 20 x 96 = 16 x 112 + 4 x 32
+  if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == kProducerWarp) {
     // ===================== TMA producer (weight panels) =====================
     if (lane == 0) {
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp >= kMmaWarp) {
+  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
     // ===================== MMA issuer of tile slot t =====================
     if (lane == 0) {
       const int t = warp - kMmaWarp;
@@ -330,7 +333,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const __grid_c
         }
       }
     }
-  } else {
+  } else if (warp < 16) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ===================== epilogue warps =====================
     // 16 warps: slot t = warp / 8 (tile of the pair), column half h = (warp / 4) % 2, TMEM lane quarter = warp % 4.
     // Thread (m, h) owns channels [64h, 64h+64) of sample point m of its tile: four 16-column chunks per layer.
