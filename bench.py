@@ -304,7 +304,15 @@ def main():
                             impl=args.kernel)
     R = ro.shape[0]
     N = R * N_SAMPLES
-    host = [t.pin_memory() for t in (ro, rd, near, far, z)]
+    # the five input tensors live back to back in ONE pinned host buffer: one host->device copy per step
+    sizes = [t.numel() for t in (ro, rd, near, far, z)]
+    host_flat = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
+    host, off = [], 0
+    for t, n_el in zip((ro, rd, near, far, z), sizes):
+        view = host_flat[off:off + n_el].view(t.shape)
+        view.copy_(t)
+        host.append(view)
+        off += n_el
     resident = [t.to(dev) for t in host]
     d_ro, d_rd, d_near, d_far, d_z = resident
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -324,7 +332,11 @@ def main():
 
     def stage_inputs(i):
         with torch.cuda.stream(copy_stream):
-            a = [t.to(dev, non_blocking=True) for t in host]
+            flat = host_flat.to(dev, non_blocking=True)
+            a, off = [], 0
+            for t, n_el in zip(host, sizes):
+                a.append(flat[off:off + n_el].view(t.shape))
+                off += n_el
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         staged[i] = (a, ev)
@@ -337,8 +349,7 @@ def main():
             torch.cuda.current_stream(dev).wait_event(ev)
             if not last:
                 stage_inputs(i + 1)
-            for t in a:
-                t.record_stream(torch.cuda.current_stream(dev))
+            a[0].record_stream(torch.cuda.current_stream(dev))   # all five are views of one allocation
             w = sdf.style(a[4])
             out = renderer.render(a[0], a[1], a[2], a[3], cos_anneal_ratio=1.0, perturb_overwrite=0, z=a[4], w=w)
             h_color[i & 1].copy_(out["color_fine"], non_blocking=True)
