@@ -404,6 +404,19 @@ typedef struct OiAugmentGeomDesc {
  * transforms g_inv [batch,3,3] (pixel_out -> pixel_in, centred pixel coordinates); everything on the device. */
 int oi_augment_geom_setup(const float* g_inv, int32_t batch, int32_t height, int32_t width, int32_t filter_taps,
                           float* theta, int32_t* margins, void* stream);
+/* The same, with the inverse transform given as the sequence of elementary 3x3 factors the reference composes with
+ * ~15 torch launches each (augment.py:196-264: G_inv = G_inv @ scale2d_inv(..) @ rotate2d_inv(..) @ translate2d_inv(..)
+ * ...): G_inv[b] = prod_i M_i[b] in the order given.  kind 0: scale2d(p0[b], p1[b]); 1: rotate2d(p0[b]);
+ * 2: translate2d(p0[b], p1[b]); the per-sample parameters are the caller's (already gated) random draws.
+ * g_inv [batch,3,3] receives the composed transform (required). */
+typedef struct OiAugmentOp {
+  int32_t kind, reserved;
+  const float* p0;   /* [batch] */
+  const float* p1;   /* [batch] or NULL (rotate) */
+} OiAugmentOp;
+#define OI_AUGMENT_MAX_OPS 8
+int oi_augment_geom_setup_ops(const OiAugmentOp* ops, int32_t n_ops, int32_t batch, int32_t height, int32_t width,
+                              int32_t filter_taps, float* g_inv, float* theta, int32_t* margins, void* stream);
 int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* desc, size_t* bytes);
 int oi_augment_geom_forward(const OiAugmentGeomDesc* desc, void* stream);
 int oi_augment_geom_backward(const OiAugmentGeomDesc* desc, void* stream);

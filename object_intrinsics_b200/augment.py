@@ -167,6 +167,31 @@ def geometric_setup_cuda(G_inv, height, width, n_taps):
     return theta, margins
 
 
+def geometric_setup_ops_cuda(ops, batch, height, width, n_taps, device):
+    """`geometric_setup` for a transform given as its elementary factors (`AugmentPipe.sample_ops`): ONE kernel
+    composes G_inv = prod M_i and derives margins + affine matrices (oi_augment_geom_setup_ops) instead of the ~15
+    torch launches per factor of the reference's matrix helpers.  Returns (theta, margins, G_inv)."""
+    L = _lib.lib()
+    arr = (_lib.OiAugmentOp * len(ops))()
+    keep = []
+    for i, (kind, p0, p1) in enumerate(ops):
+        p0 = p0.detach().to(device=device, dtype=torch.float32).contiguous()
+        keep.append(p0)
+        arr[i].kind, arr[i].p0 = kind, p0.data_ptr()
+        if p1 is not None:
+            p1 = p1.detach().to(device=device, dtype=torch.float32).contiguous()
+            keep.append(p1)
+            arr[i].p1 = p1.data_ptr()
+    theta = torch.empty((batch, 2, 3), dtype=torch.float32, device=device)
+    g_inv = torch.empty((batch, 3, 3), dtype=torch.float32, device=device)
+    margins = torch.empty(4, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.oi_augment_geom_setup_ops(arr, len(ops), batch, height, width, n_taps, g_inv.data_ptr(),
+                                               theta.data_ptr(), margins.data_ptr(), _lib.current_stream_ptr(device)),
+                   "oi_augment_geom_setup_ops")
+    return theta, margins, g_inv
+
+
 def geometric_transform(images, G_inv, taps=None):
     """augment.py:270-301 for a given inverse transform G_inv [B,3,3] (pixel_out -> pixel_in)."""
     if not images.is_cuda:
@@ -197,53 +222,69 @@ class AugmentPipe(torch.nn.Module):
         self._taps = tuple(float(v) for v in (f / f.sum()))
         self.register_buffer("Hz_fbank", image_filter_bank())  # augment.py:179 (unused: imgfilter is disabled)
 
-    def sample_inverse_transform(self, batch, width, height, device):
-        """G_inv [B,3,3] (pixel_out -> pixel_in), random draws in the reference's order (augment.py:196-264)."""
-        G = torch.eye(3, device=device)
+    def sample_ops(self, batch, width, height, device):
+        """The elementary factors of G_inv (pixel_out -> pixel_in) as a list of (kind, p0, p1) with per-sample fp32
+        parameters [B]: kind 0 = scale2d(p0, p1), 1 = rotate2d(p0), 2 = translate2d(p0, p1); random draws in the
+        reference's order (augment.py:196-264) -- the only torch work left per call."""
         ones = torch.ones([batch], device=device)
         p = self.p
-        enabled = False
+        ops = []
         if self.xflip > 0:
             i = torch.floor(torch.rand([batch], device=device) * 2)
             i = torch.where(torch.rand([batch], device=device) < self.xflip * p, i, torch.zeros_like(i))
-            G, enabled = G @ _scale(1 / (1 - 2 * i), 1 / ones, ones), True
+            ops.append((0, 1 / (1 - 2 * i), 1 / ones))
         if self.rotate90 > 0:
             i = torch.floor(torch.rand([batch], device=device) * 4)
             i = torch.where(torch.rand([batch], device=device) < self.rotate90 * p, i, torch.zeros_like(i))
-            G, enabled = G @ _rotate(-(-math.pi / 2 * i)), True
+            ops.append((1, -(-math.pi / 2 * i), None))
         if self.xint > 0:
             t = (torch.rand([batch, 2], device=device) * 2 - 1) * self.xint_max
             t = torch.where(torch.rand([batch, 1], device=device) < self.xint * p, t, torch.zeros_like(t))
-            G, enabled = G @ _translate(-torch.round(t[:, 0] * width), -torch.round(t[:, 1] * height), ones), True
+            ops.append((2, -torch.round(t[:, 0] * width), -torch.round(t[:, 1] * height)))
         if self.scale > 0:
             s = torch.exp2(torch.randn([batch], device=device) * self.scale_std)
             s = torch.where(torch.rand([batch], device=device) < self.scale * p, s, torch.ones_like(s))
-            G, enabled = G @ _scale(1 / s, 1 / s, ones), True
+            ops.append((0, 1 / s, 1 / s))
         p_rot = 1 - torch.sqrt((1 - self.rotate * p).clamp(0, 1))
         if self.rotate > 0:
             th = (torch.rand([batch], device=device) * 2 - 1) * math.pi * self.rotate_max
             th = torch.where(torch.rand([batch], device=device) < p_rot, th, torch.zeros_like(th))
-            G, enabled = G @ _rotate(-(-th)), True
+            ops.append((1, -(-th), None))
         if self.aniso > 0:
             s = torch.exp2(torch.randn([batch], device=device) * self.aniso_std)
             s = torch.where(torch.rand([batch], device=device) < self.aniso * p, s, torch.ones_like(s))
-            G, enabled = G @ _scale(1 / s, 1 / (1 / s), ones), True
+            ops.append((0, 1 / s, 1 / (1 / s)))
         if self.rotate > 0:
             th = (torch.rand([batch], device=device) * 2 - 1) * math.pi * self.rotate_max
             th = torch.where(torch.rand([batch], device=device) < p_rot, th, torch.zeros_like(th))
-            G, enabled = G @ _rotate(-(-th)), True
+            ops.append((1, -(-th), None))
         if self.xfrac > 0:
             t = torch.randn([batch, 2], device=device) * self.xfrac_std
             t = torch.where(torch.rand([batch, 1], device=device) < self.xfrac * p, t, torch.zeros_like(t))
-            G, enabled = G @ _translate(-(t[:, 0] * width), -(t[:, 1] * height), ones), True
-        return G if enabled else None
+            ops.append((2, -(t[:, 0] * width), -(t[:, 1] * height)))
+        return ops
+
+    def sample_inverse_transform(self, batch, width, height, device):
+        """G_inv [B,3,3] composed with torch ops exactly as the reference does (augment.py:196-264); the CPU tests pin
+        it to the reference bit for bit.  `forward` composes the same factors in one kernel instead."""
+        ops = self.sample_ops(batch, width, height, device)
+        if not ops:
+            return None
+        ones = torch.ones([batch], device=device)
+        G = torch.eye(3, device=device)
+        for kind, p0, p1 in ops:
+            G = G @ (_scale(p0, p1, ones) if kind == 0 else _rotate(p0) if kind == 1 else _translate(p0, p1, ones))
+        return G
 
     def forward(self, images, debug_percentile=None):
         if debug_percentile is not None:
             raise NotImplementedError("debug_percentile is a debugging aid of the reference and is not implemented")
         assert isinstance(images, torch.Tensor) and images.ndim == 4
         B, _, H, W = images.shape
-        G_inv = self.sample_inverse_transform(B, W, H, images.device)
-        if G_inv is None:
+        if not images.is_cuda:
+            raise RuntimeError("object_intrinsics_b200.augment has no CPU path: images must be CUDA tensors")
+        ops = self.sample_ops(B, W, H, images.device)
+        if not ops:
             return images
-        return geometric_transform(images, G_inv, self._taps)
+        theta, margins, _ = geometric_setup_ops_cuda(ops, B, H, W, len(self._taps), images.device)
+        return _GeomForward.apply(images, theta, margins, self._taps)

@@ -564,6 +564,19 @@ int oi_augment_geom_setup(const float* g_inv, int32_t batch, int32_t height, int
                               static_cast<cudaStream_t>(stream));
 }
 
+int oi_augment_geom_setup_ops(const OiAugmentOp* ops, int32_t n_ops, int32_t batch, int32_t height, int32_t width,
+                              int32_t filter_taps, float* g_inv, float* theta, int32_t* margins, void* stream) {
+  OI_CHECK_ARG(ops && g_inv && theta && margins, "NULL pointer");
+  OI_CHECK_ARG(n_ops >= 1 && n_ops <= OI_AUGMENT_MAX_OPS, "n_ops must be in [1, %d] (got %d)", OI_AUGMENT_MAX_OPS, n_ops);
+  OI_CHECK_ARG(batch > 0 && height >= 2 && width >= 2 && filter_taps >= 4 && filter_taps % 4 == 0, "bad sizes");
+  for (int i = 0; i < n_ops; ++i) {
+    OI_CHECK_ARG(ops[i].kind >= 0 && ops[i].kind <= 2, "op %d: bad kind %d", i, ops[i].kind);
+    OI_CHECK_ARG(ops[i].p0 != nullptr && (ops[i].kind == 1 || ops[i].p1 != nullptr), "op %d: NULL parameter", i);
+  }
+  return launch_augment_setup_ops(ops, n_ops, batch, height, width, filter_taps / 4, g_inv, g_inv, theta, margins,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* d, size_t* bytes) {
   int rc = check_augment(d, false);
   if (rc) return rc;

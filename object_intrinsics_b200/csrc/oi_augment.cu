@@ -239,11 +239,55 @@ __device__ __forceinline__ M3 mul3(const M3& a, const M3& b) {
 __device__ __forceinline__ M3 scale3(double sx, double sy) { return M3{{sx, 0, 0, 0, sy, 0, 0, 0, 1}}; }
 __device__ __forceinline__ M3 trans3(double tx, double ty) { return M3{{1, 0, tx, 0, 1, ty, 0, 0, 1}}; }
 
-__global__ void augment_setup_kernel(const float* __restrict__ G_inv, int B, int H, int W, int hz_pad,
+struct AugOps {
+  int n;
+  OiAugmentOp op[OI_AUGMENT_MAX_OPS];
+};
+
+// G_inv[b] = prod_i M_i[b] in fp32, each product accumulated in the order of a 3x3 matmul (augment.py:196-264)
+__device__ __forceinline__ void compose_ops(const AugOps& o, int b, float (&g)[9]) {
+  g[0] = 1.f; g[1] = 0.f; g[2] = 0.f; g[3] = 0.f; g[4] = 1.f; g[5] = 0.f; g[6] = 0.f; g[7] = 0.f; g[8] = 1.f;
+  for (int i = 0; i < o.n; ++i) {
+    float m[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    const float p0 = o.op[i].p0[b];
+    if (o.op[i].kind == 0) {
+      m[0] = p0;
+      m[4] = o.op[i].p1[b];
+    } else if (o.op[i].kind == 1) {
+      const float c = cosf(p0), s = sinf(p0);
+      m[0] = c; m[1] = -s; m[3] = s; m[4] = c;
+    } else {
+      m[2] = p0;
+      m[5] = o.op[i].p1[b];
+    }
+    float r[9];
+    for (int rr = 0; rr < 3; ++rr)
+      for (int cc = 0; cc < 3; ++cc)
+        r[rr * 3 + cc] = fmaf(g[rr * 3 + 2], m[6 + cc], fmaf(g[rr * 3 + 1], m[3 + cc], g[rr * 3] * m[cc]));
+    for (int k = 0; k < 9; ++k) g[k] = r[k];
+  }
+}
+
+// G_in != NULL: the transform is given; else it is composed from `ops` (and written to G_out when that is given).
+__global__ void augment_setup_kernel(const float* __restrict__ G_in, const AugOps ops, float* __restrict__ G_out,
+                                     float* __restrict__ G_tmp, int B, int H, int W, int hz_pad,
                                      float* __restrict__ theta, int* __restrict__ margins) {
   __shared__ float red[4][32];
   __shared__ int marg[4];
   const int tid = threadIdx.x;   // 32 threads
+  const float* G_inv = G_in;
+  if (G_in == nullptr) {
+    for (int b = tid; b < B; b += 32) {
+      float g[9];
+      compose_ops(ops, b, g);
+      for (int k = 0; k < 9; ++k) {
+        G_tmp[b * 9 + k] = g[k];
+        if (G_out) G_out[b * 9 + k] = g[k];
+      }
+    }
+    __syncthreads();
+    G_inv = G_tmp;
+  }
   const float cx = (W - 1) * 0.5f, cy = (H - 1) * 0.5f;
   float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, m3 = -1e30f;   // max(-x), max(-y), max(x), max(y)
   for (int b = tid; b < B; b += 32) {
@@ -314,7 +358,20 @@ size_t augment_r_floats(const OiAugmentGeomDesc& d) {
 
 int launch_augment_setup(const float* G_inv, int B, int H, int W, int hz_pad, float* theta, int* margins,
                          cudaStream_t st) {
-  augment_setup_kernel<<<1, 32, 0, st>>>(G_inv, B, H, W, hz_pad, theta, margins);
+  AugOps none;
+  none.n = 0;
+  augment_setup_kernel<<<1, 32, 0, st>>>(G_inv, none, nullptr, nullptr, B, H, W, hz_pad, theta, margins);
+  OI_CHECK_CUDA(cudaGetLastError());
+  return OI_OK;
+}
+
+// `theta` ([B,2,3]) is followed in the caller's buffer by [B,3,3] floats of scratch for the composed transform
+int launch_augment_setup_ops(const OiAugmentOp* ops, int n_ops, int B, int H, int W, int hz_pad, float* g_inv,
+                             float* g_tmp, float* theta, int* margins, cudaStream_t st) {
+  AugOps o;
+  o.n = n_ops;
+  for (int i = 0; i < n_ops; ++i) o.op[i] = ops[i];
+  augment_setup_kernel<<<1, 32, 0, st>>>(nullptr, o, g_inv, g_tmp, B, H, W, hz_pad, theta, margins);
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }
