@@ -37,6 +37,12 @@
 #ifndef OI_BWD_L2PF
 #define OI_BWD_L2PF 1   // prefetch a stage's scratch re-reads into L2 at the start of the stage
 #endif
+#ifndef OI_BWD_PFOCT
+#define OI_BWD_PFOCT 3  // with OI_BWD_L2PF == 2: the NEXT stage's re-reads are prefetched after this oct of a stage
+#endif
+#ifndef OI_BWD_STHINT
+#define OI_BWD_STHINT 0  // experiment: L2 eviction hints on the slab stores (1: operand slabs evict-first; 2: + per-CTA
+#endif                   // slabs evict-last; 3: + ARG slabs evict-last)
 #ifndef OI_BWD_PF4
 #define OI_BWD_PF4 1   // ... in stages that re-read two slabs
 #endif
@@ -136,6 +142,21 @@ __device__ __forceinline__ void split2_bf16t(float v0, float v1, uint32_t& hi, u
 // drops the 13 low mantissa bits itself
 __device__ __forceinline__ float tf32_bias(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+__device__ __forceinline__ uint64_t l2_policy(bool last) {
+  uint64_t pol;
+  if (last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_hint(float* p, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint4(float4* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+
 // Sum over the 32 lanes of a warp (= 32 sample points) of 8 per-lane values (= 8 channels) by recursive halving;
 // lane L ends up with channel 4 b4 + 2 b3 + b2 (bits of L) and lanes with (L & 3) == 0 add it to dst[ch * stride].
 __device__ __forceinline__ void colsum8(const float (&v)[8], float* dst, int stride, int lane) {
@@ -167,8 +188,8 @@ __device__ __forceinline__ void colsum8(const float (&v)[8], float* dst, int str
 // One stage of a tile slot.  For o = 0..7: u = accumulator columns [8o, 8o+8) of this thread (if WAIT), buf = the
 // stage's scratch float4s of oct o.  `load(o, buf)` issues the global loads of oct o, PF octs ahead of their use;
 // the first PF octs are issued BEFORE the wait on the accumulator barrier (their latency sits under the MMA).
-template <int NL, bool WAIT, int PF, class Load, class Body, class WaitAcc>
-__device__ __forceinline__ void run_stage(uint32_t acc, Load load, Body body, WaitAcc wait_acc) {
+template <int NL, bool WAIT, int PF, class Load, class Body, class WaitAcc, class Next>
+__device__ __forceinline__ void run_stage(uint32_t acc, Load load, Body body, WaitAcc wait_acc, Next next) {
   float4 buf[PF + 1][NL > 0 ? NL : 1];
 #pragma unroll
   for (int o = 0; o < PF; ++o) load(o, buf[o]);
@@ -185,6 +206,7 @@ __device__ __forceinline__ void run_stage(uint32_t acc, Load load, Body body, Wa
       if (o < 7) tmem_ld8_async(acc + (o + 1) * 8, ub[(o + 1) & 1]);
     }
     body(o, ub[o & 1], buf[o % (PF + 1)]);
+    if (o == OI_BWD_PFOCT) next();
   }
 }
 
@@ -290,6 +312,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     float4* scr4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * a.scratch_stride +
                                              (size_t)t * kCtaSlabs * kSlabFloats) + m;
     uint32_t af_phase = 0u;
+    const uint64_t pol_first = (OI_BWD_STHINT >= 1) ? l2_policy(false) : 0ull;
+    const uint64_t pol_last = (OI_BWD_STHINT >= 2) ? l2_policy(true) : 0ull;
     // operand slabs: K-major SWIZZLE_128B tf32 image [32-point block][channel][32 points]; the 16-byte chunk of this
     // thread's point is XOR-permuted by (channel & 7) = the position e inside an oct
     const int mc = (m & 31) >> 2;
@@ -308,13 +332,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
     auto no_load = [](int, float4 (&)[1]) {};
     // L2 prefetch of everything this warp re-reads from one slab in the coming stage: 16 channel quads x 512 B
     // (the slabs were written tens of microseconds ago and have left the L2); p_q0 = this thread's float4 of quad Q0
-    auto pf_slab = [&](const float4* p_q0) {
-#if OI_BWD_L2PF
+    auto pf_raw = [&](const float4* p_q0) {
       const float4* base = p_q0 - lane + (lane & 3) * 8;
       l2_prefetch(base + (size_t)(lane >> 2) * 128);
       l2_prefetch(base + (size_t)((lane >> 2) + 8) * 128);
-#endif
     };
+    // OI_BWD_L2PF == 1: a stage prefetches its own re-reads when it starts; == 2: the re-reads of the NEXT stage are
+    // prefetched from the middle of the stage before (pf_nxt, called through run_stage's `next` hook)
+    auto pf_slab = [&](const float4* p_q0) {
+      if (OI_BWD_L2PF == 1) pf_raw(p_q0);
+    };
+    auto pf_nxt = [&](const float4* p_q0) {
+      if (OI_BWD_L2PF == 2) pf_raw(p_q0);
+    };
+    auto no_next = []() {};
 
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
       const int lt = 2 * pi + t;   // tile index inside this launch
@@ -358,7 +389,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       auto op8 = [&](int slab, int o, const float (&v)[8]) {
         float* p = gso + (size_t)slab * kSlabFloats + o * 256;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) p[e * 32 + (mc4 ^ (e << 2))] = tf32_bias(v[e]);
+        for (int e = 0; e < 8; ++e) {
+          if (OI_BWD_STHINT >= 1) st_hint(p + e * 32 + (mc4 ^ (e << 2)), tf32_bias(v[e]), pol_first);
+          else p[e * 32 + (mc4 ^ (e << 2))] = tf32_bias(v[e]);
+        }
+      };
+      auto st_arg = [&](float4* p, float4 v) {
+        if (OI_BWD_STHINT >= 3) st_hint4(p, v, pol_last);
+        else *p = v;
+      };
+      auto st_cta = [&](float4* p, float4 v) {
+        if (OI_BWD_STHINT >= 2) st_hint4(p, v, pol_last);
+        else *p = v;
       };
       // the 8 values of an oct -> next A operand (TMEM), fp16 or bf16 two-term split
       auto a8_f16 = [&](int o, const float (&v)[8]) {
@@ -394,11 +436,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             s[2 * i] = __sinf(arg.x);
             s[2 * i + 1] = __sinf(arg.y);
           }
-          OI_ARG(0, Q0 + 2 * o) = make_float4(ar[0], ar[1], ar[2], ar[3]);
-          OI_ARG(0, Q0 + 2 * o + 1) = make_float4(ar[4], ar[5], ar[6], ar[7]);
+          st_arg(&OI_ARG(0, Q0 + 2 * o), make_float4(ar[0], ar[1], ar[2], ar[3]));
+          st_arg(&OI_ARG(0, Q0 + 2 * o + 1), make_float4(ar[4], ar[5], ar[6], ar[7]));
           op8(kSlabH + 1, o, s);
           a8_f16(o, s);
-        }, wait_acc);
+        }, wait_acc, no_next);
         a_ready();
       }
       // ---------------- forward layers 1..D-1 ----------------
@@ -417,11 +459,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             s[2 * i] = __sinf(arg.x);
             s[2 * i + 1] = __sinf(arg.y);
           }
-          OI_ARG(l, Q0 + 2 * o) = make_float4(ar[0], ar[1], ar[2], ar[3]);
-          OI_ARG(l, Q0 + 2 * o + 1) = make_float4(ar[4], ar[5], ar[6], ar[7]);
+          st_arg(&OI_ARG(l, Q0 + 2 * o), make_float4(ar[0], ar[1], ar[2], ar[3]));
+          st_arg(&OI_ARG(l, Q0 + 2 * o + 1), make_float4(ar[4], ar[5], ar[6], ar[7]));
           op8(kSlabH + l + 1, o, s);
           a8_f16(o, s);
-        }, wait_acc);
+        }, wait_acc, no_next);
         a_ready();
       }
       // ---------------- colour features -> slot UC; t_{D-1} = w_sigma gamma cos(a_{D-1}) ----------------
@@ -432,10 +474,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           b[0] = OI_ARG(D - 1, Q0 + 2 * o);
           b[1] = OI_ARG(D - 1, Q0 + 2 * o + 1);
         }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[2]) {
-          OI_CTA(kCtaUC, Q0 + 2 * o) = make_float4(__uint_as_float(u[0]), __uint_as_float(u[1]), __uint_as_float(u[2]),
-                                                   __uint_as_float(u[3]));
-          OI_CTA(kCtaUC, Q0 + 2 * o + 1) = make_float4(__uint_as_float(u[4]), __uint_as_float(u[5]),
-                                                       __uint_as_float(u[6]), __uint_as_float(u[7]));
+          st_cta(&OI_CTA(kCtaUC, Q0 + 2 * o), make_float4(__uint_as_float(u[0]), __uint_as_float(u[1]), __uint_as_float(u[2]),
+                                                   __uint_as_float(u[3])));
+          st_cta(&OI_CTA(kCtaUC, Q0 + 2 * o + 1), make_float4(__uint_as_float(u[4]), __uint_as_float(u[5]),
+                                                       __uint_as_float(u[6]), __uint_as_float(u[7])));
           const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
           float tv[8];
 #pragma unroll
@@ -448,7 +490,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           op8(kSlabT + D - 1, o, tv);
           a8_f16(o, tv);
-        }, wait_acc);
+        }, wait_acc, [&]() { if (D >= 2) pf_nxt(&OI_ARG(D - 2, Q0)); });
         a_ready();
       }
       // ---------------- reverse sweep l = D-1 .. 1: g_l (slot G[l]), t_{l-1} (slab T[l-1]) ----------------
@@ -472,8 +514,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             tv[2 * i] = a0 * (f.x * gscale) * __cosf(ar[2 * i]);           // g_l gamma cos = t_{l-1}
             tv[2 * i + 1] = a1 * (f.y * gscale) * __cosf(ar[2 * i + 1]);
           }
-          OI_CTA(kCtaG + l - 1, Q0 + 2 * o) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-          OI_CTA(kCtaG + l - 1, Q0 + 2 * o + 1) = make_float4(gv[4], gv[5], gv[6], gv[7]);
+          st_cta(&OI_CTA(kCtaG + l - 1, Q0 + 2 * o), make_float4(gv[0], gv[1], gv[2], gv[3]));
+          st_cta(&OI_CTA(kCtaG + l - 1, Q0 + 2 * o + 1), make_float4(gv[4], gv[5], gv[6], gv[7]));
           if (l > 1) {
             op8(kSlabT + l - 1, o, tv);
             a8_f16(o, tv);
@@ -486,7 +528,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               gz = fmaf(w.z, tv[e], gz);
             }
           }
-        }, wait_acc);
+        }, wait_acc, [&]() { if (l >= 2) pf_nxt(&OI_ARG(l - 2, Q0)); else pf_nxt(&OI_CTA(kCtaUC, Q0)); });
         if (l > 1) a_ready();
       }
       // ---------------- combine the two column halves: normal ----------------
@@ -553,7 +595,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             for (int i = 0; i < 8; ++i) tmp[i] = zb2 * sn[i];
             colsum8(tmp, a.g.rgb_weight + 2 * kW + nc, 1, lane);
           }
-        }, wait_acc);
+        }, wait_acc, [&]() { pf_nxt(&OI_ARG(0, Q0)); pf_nxt(&OI_CTA(kCtaG + 0, Q0)); });
       }
       // normal_bar = direct + W_cg^T u_bar_c (both halves)
       xch[h * 4 + 1] = nc0;
@@ -603,10 +645,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               t0[e] = g1[e] * c0;   // t_0
             }
           }
-          OI_CTA(kCtaHB, Q0 + 2 * o) = make_float4(hb[0], hb[1], hb[2], hb[3]);
-          OI_CTA(kCtaHB, Q0 + 2 * o + 1) = make_float4(hb[4], hb[5], hb[6], hb[7]);
-          OI_CTA(kCtaG + 0, Q0 + 2 * o) = make_float4(cb[0], cb[1], cb[2], cb[3]);   // c_bar_0
-          OI_CTA(kCtaG + 0, Q0 + 2 * o + 1) = make_float4(cb[4], cb[5], cb[6], cb[7]);
+          st_cta(&OI_CTA(kCtaHB, Q0 + 2 * o), make_float4(hb[0], hb[1], hb[2], hb[3]));
+          st_cta(&OI_CTA(kCtaHB, Q0 + 2 * o + 1), make_float4(hb[4], hb[5], hb[6], hb[7]));
+          st_cta(&OI_CTA(kCtaG + 0, Q0 + 2 * o), make_float4(cb[0], cb[1], cb[2], cb[3]));   // c_bar_0
+          st_cta(&OI_CTA(kCtaG + 0, Q0 + 2 * o + 1), make_float4(cb[4], cb[5], cb[6], cb[7]));
           op8(kSlabGB + 1, o, gb);
           a8_bf16(o, gb);
           if (o == 7) a_ready();
@@ -623,7 +665,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             for (int i = 0; i < 8; ++i) tmp[i] = nb2 * t0[i];
             colsum8(tmp, dst + 2, 3, lane);
           }
-        }, wait_acc);
+        }, wait_acc, [&]() { if (1 < D - 1) { pf_nxt(&OI_ARG(1, Q0)); pf_nxt(&OI_CTA(kCtaG + 1, Q0)); } else { pf_nxt(&OI_ARG(D - 1, Q0)); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
       }
       // ---------------- backward of the reverse sweep, l = 1..D-2: t_bar_l = W_l g_bar_l ----------------
       for (int l = 1; l < D - 1; ++l) {
@@ -649,11 +691,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             gb[2 * i] = tb0 * gam.x * __cosf(ar[2 * i]);                 // g_bar_{l+1}
             gb[2 * i + 1] = tb1 * gam.y * __cosf(ar[2 * i + 1]);
           }
-          OI_CTA(kCtaG + l, Q0 + 2 * o) = make_float4(cb[0], cb[1], cb[2], cb[3]);
-          OI_CTA(kCtaG + l, Q0 + 2 * o + 1) = make_float4(cb[4], cb[5], cb[6], cb[7]);
+          st_cta(&OI_CTA(kCtaG + l, Q0 + 2 * o), make_float4(cb[0], cb[1], cb[2], cb[3]));
+          st_cta(&OI_CTA(kCtaG + l, Q0 + 2 * o + 1), make_float4(cb[4], cb[5], cb[6], cb[7]));
           op8(kSlabGB + l + 1, o, gb);
           a8_bf16(o, gb);
-        }, wait_acc);
+        }, wait_acc, [&]() { if (l + 1 < D - 1) { pf_nxt(&OI_ARG(l + 1, Q0)); pf_nxt(&OI_CTA(kCtaG + l + 1, Q0)); } else { pf_nxt(&OI_ARG(D - 1, Q0)); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
         a_ready();
       }
       // ---------------- top, l = D-1: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
@@ -691,7 +733,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           a8_bf16(o, ubv);
           if (o == 7) a_ready();
           colsum8(dws, a.g.sigma_weight + n0 + o * 8, 1, lane);
-        }, wait_acc);
+        }, wait_acc, [&]() { pf_nxt(&OI_ARG(D - 2, Q0)); pf_nxt(&OI_CTA(kCtaG + D - 2, Q0)); });
       }
       // ---------------- backward of the forward sweep: h_bar_l = W_l^T u_bar_l, then layer k = l-1 ----------------
       for (int l = D - 1; l >= 1; --l) {
@@ -740,7 +782,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             for (int i = 0; i < 8; ++i) tmp[i] = pz * ubv[i];
             colsum8(tmp, dst + 2, 3, lane);
           }
-        }, wait_acc);
+        }, wait_acc, [&]() { if (l >= 2) { pf_nxt(&OI_ARG(l - 2, Q0)); pf_nxt(&OI_CTA(kCtaG + l - 2, Q0)); } });
         if (k >= 1) a_ready();
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);   // film table / exchange buffer of this slot may be reused now
