@@ -563,9 +563,26 @@ def grad_step_leg(renderer, sdf, col, devn, resident, r1, flush):
     renderer.bwd_events = None
     gs.sort()
     ks.sort()
-    return {"ms": gs[len(gs) // 2], "rays": r1, "bwd_kernels_ms": ks[len(ks) // 2],
+    # free-running: the loop of a trainer (no host read-back between steps -- gan_pose_trainer.py has none), L2 flush
+    # fills in stream between the steps and their measured duration subtracted
+    n_free = 10
+    a_, b_, c_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    a_.record()
+    for i in range(n_free):
+        flush.fill_(i)
+    b_.record()
+    for i in range(n_free):
+        flush.fill_(i)
+        grad_step()
+    c_.record()
+    c_.synchronize()
+    free_ms = (b_.elapsed_time(c_) - a_.elapsed_time(b_)) / n_free
+    return {"ms": gs[len(gs) // 2], "ms_free_running": free_ms, "rays": r1, "bwd_kernels_ms": ks[len(ks) // 2],
             "what": "grad-mode render of 1 instance: forward + loss + oi_render_backward (sweep kernel on tcgen05 "
-                    "+ TMA-fed TF32 point-contraction), gradients on every nn.Parameter"}
+                    "+ TMA-fed TF32 point-contraction), gradients on every nn.Parameter; `ms` = median of steps "
+                    "synchronised one by one (the host's enqueue time is exposed), `ms_free_running` = 10 steps "
+                    "back to back as a training loop issues them (L2 flushed between steps, flush time subtracted)"}
 
 
 def train_step_leg(dev, P, kernel, flush):

@@ -155,8 +155,25 @@ def measure(dev, P, kernel="auto", flush=None, shape="cfg5", steps=8, shading="k
         parts["d_step_x2"].append(ev[1].elapsed_time(ev[2]))
         parts["total"].append(ev[0].elapsed_time(ev[2]))
     med = {k: sorted(v)[len(v) // 2] for k, v in parts.items()}
+    # free-running: `steps` steps back to back as the trainer issues them (it has no host read-back between steps),
+    # L2 flush fills in stream and their measured duration subtracted
+    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize(dev)
+    a.record()
+    if flush is not None:
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+    b.record()
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        step()
+    c.record()
+    c.synchronize()
+    free_ms = (b.elapsed_time(c) - a.elapsed_time(b)) / steps
     rays_per_step = 3 * bs * patch * patch
-    return {"shape": shape, **cfg, "ms_per_step": med["total"], "g_step_ms": med["g_step"],
+    return {"shape": shape, **cfg, "ms_per_step": med["total"], "ms_per_step_free_running": free_ms,
+            "g_step_ms": med["g_step"],
             "two_no_grad_renders_ms": med["d_step_x2"], "rays_per_step": rays_per_step,
             "rays_per_sec": rays_per_step / (med["total"] * 1e-3),
             "shading": shading,
