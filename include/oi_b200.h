@@ -417,6 +417,30 @@ typedef struct OiAugmentOp {
 #define OI_AUGMENT_MAX_OPS 8
 int oi_augment_geom_setup_ops(const OiAugmentOp* ops, int32_t n_ops, int32_t batch, int32_t height, int32_t width,
                               int32_t filter_taps, float* g_inv, float* theta, int32_t* margins, void* stream);
+/* The same from the RAW random draws: the kernel also applies the reference's gating and parameter arithmetic
+ * (augment.py:196-264) -- `torch.where(gate < prob * p, value(draw), identity)` per factor -- so that the caller's
+ * only work per call is the draws themselves (one torch.rand / randn each, in the reference's order: the RNG stream
+ * is the reference's).  form: the reference's factor
+ *   OI_AUG_XFLIP    i = floor(draw*2), gated                          scale2d(1/(1-2i), 1)          augment.py:196-201
+ *   OI_AUG_ROTATE90 i = floor(draw*4), gated                          rotate2d(pi/2 * i)            :203-208
+ *   OI_AUG_XINT     t = (draw[b,0:2]*2-1)*param, gated                translate2d(-round(t*size))   :210-215
+ *   OI_AUG_SCALE    s = exp2(draw*param), gated (else 1)              scale2d(1/s, 1/s)             :220-224
+ *   OI_AUG_ROTATE   th = (draw*2-1)*pi*param, gate < 1-sqrt(1-prob*p) rotate2d(th)                  :226-231,241-245
+ *   OI_AUG_ANISO    s = exp2(draw*param), gated (else 1)              scale2d(1/s, s)               :234-238
+ *   OI_AUG_XFRAC    t = draw[b,0:2]*param, gated                      translate2d(-t*size)          :248-252
+ * draw: [batch] ([batch,2] for XINT / XFRAC), gate: [batch], p: the module's device scalar `p`. */
+enum { OI_AUG_XFLIP = 0, OI_AUG_ROTATE90 = 1, OI_AUG_XINT = 2, OI_AUG_SCALE = 3, OI_AUG_ROTATE = 4, OI_AUG_ANISO = 5,
+       OI_AUG_XFRAC = 6 };
+typedef struct OiAugmentRawOp {
+  int32_t form, reserved;
+  const float* draw;
+  const float* gate;
+  float prob;    /* constructor probability multiplier of the factor (xflip, rotate90, xint, scale, rotate, aniso, xfrac) */
+  float param;   /* xint_max | scale_std | rotate_max | aniso_std | xfrac_std (unused: XFLIP, ROTATE90) */
+} OiAugmentRawOp;
+int oi_augment_geom_setup_raw(const OiAugmentRawOp* ops, int32_t n_ops, const float* p, int32_t batch, int32_t height,
+                              int32_t width, int32_t filter_taps, float* g_inv, float* theta, int32_t* margins,
+                              void* stream);
 int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* desc, size_t* bytes);
 int oi_augment_geom_forward(const OiAugmentGeomDesc* desc, void* stream);
 int oi_augment_geom_backward(const OiAugmentGeomDesc* desc, void* stream);

@@ -131,6 +131,14 @@ class OiAugmentOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p0", f32p), ("p1", f32p)]
 
 
+class OiAugmentRawOp(C.Structure):
+    _fields_ = [("form", C.c_int32), ("reserved", C.c_int32), ("draw", f32p), ("gate", f32p), ("prob", C.c_float),
+                ("param", C.c_float)]
+
+
+AUG_XFLIP, AUG_ROTATE90, AUG_XINT, AUG_SCALE, AUG_ROTATE, AUG_ANISO, AUG_XFRAC = range(7)
+
+
 class OiRenderMapsDesc(C.Structure):
     _fields_ = [
         ("n_rays", C.c_int32), ("rays_per_instance", C.c_int32), ("n_samples", C.c_int32), ("reserved", C.c_int32),
@@ -161,7 +169,8 @@ EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_ren
            "oi_last_error", "oi_abi_version", "oi_build_info", "oi_selftest_tc", "oi_gen_rays", "oi_render_maps",
            "oi_render_backward_workspace_bytes", "oi_render_backward", "oi_selftest_wgrad",
            "oi_augment_geom_workspace_bytes", "oi_augment_geom_forward", "oi_augment_geom_backward",
-           "oi_augment_geom_setup", "oi_render_maps_backward", "oi_augment_geom_setup_ops"]
+           "oi_augment_geom_setup", "oi_render_maps_backward", "oi_augment_geom_setup_ops",
+           "oi_augment_geom_setup_raw"]
 
 _lib = None
 
@@ -193,6 +202,8 @@ def lib():
                                         C.c_void_p]
     L.oi_augment_geom_setup_ops.argtypes = [C.POINTER(OiAugmentOp), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.oi_augment_geom_setup_raw.argtypes = [C.POINTER(OiAugmentRawOp), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.oi_augment_geom_forward.argtypes = [C.POINTER(OiAugmentGeomDesc), C.c_void_p]
     L.oi_augment_geom_backward.argtypes = [C.POINTER(OiAugmentGeomDesc), C.c_void_p]
     L.oi_upfirdn2d.argtypes = [C.POINTER(OiUpfirdnDesc), C.c_void_p]

@@ -192,6 +192,24 @@ def geometric_setup_ops_cuda(ops, batch, height, width, n_taps, device):
     return theta, margins, g_inv
 
 
+def geometric_setup_raw_cuda(raw, p, batch, height, width, n_taps, device):
+    """`geometric_setup` from the RAW random draws of `AugmentPipe.sample_raw`: gating, parameter arithmetic,
+    composition of G_inv, margins and affine matrices in ONE kernel (oi_augment_geom_setup_raw).  Returns
+    (theta, margins, G_inv)."""
+    L = _lib.lib()
+    arr = (_lib.OiAugmentRawOp * len(raw))()
+    for i, (form, draw, gate, prob, param) in enumerate(raw):
+        arr[i].form, arr[i].draw, arr[i].gate, arr[i].prob, arr[i].param = form, draw.data_ptr(), gate.data_ptr(), prob, param
+    out = torch.empty(batch * 15 + 4, dtype=torch.float32, device=device)    # theta [B,2,3] | G_inv [B,3,3] | margins
+    theta, g_inv = out[:batch * 6].view(batch, 2, 3), out[batch * 6:batch * 15].view(batch, 3, 3)
+    margins = out[batch * 15:].view(torch.int32)
+    with torch.cuda.device(device):
+        _lib.check(L.oi_augment_geom_setup_raw(arr, len(raw), p.data_ptr(), batch, height, width, n_taps,
+                                               g_inv.data_ptr(), theta.data_ptr(), margins.data_ptr(),
+                                               _lib.current_stream_ptr(device)), "oi_augment_geom_setup_raw")
+    return theta, margins, g_inv
+
+
 def geometric_transform(images, G_inv, taps=None):
     """augment.py:270-301 for a given inverse transform G_inv [B,3,3] (pixel_out -> pixel_in)."""
     if not images.is_cuda:
@@ -264,6 +282,31 @@ class AugmentPipe(torch.nn.Module):
             ops.append((2, -(t[:, 0] * width), -(t[:, 1] * height)))
         return ops
 
+    def sample_raw(self, batch, device):
+        """The random draws of `sample_ops` and nothing else -- same torch calls in the same order, so the RNG stream
+        is the reference's -- as a list of (form, draw, gate, prob, param) for oi_augment_geom_setup_raw, which applies
+        the gating and the parameter arithmetic of augment.py:196-264 itself."""
+        raw = []
+        rand = lambda *shape: torch.rand(list(shape), device=device)
+        randn = lambda *shape: torch.randn(list(shape), device=device)
+        if self.xflip > 0:
+            raw.append((_lib.AUG_XFLIP, rand(batch), rand(batch), self.xflip, 0.0))
+        if self.rotate90 > 0:
+            raw.append((_lib.AUG_ROTATE90, rand(batch), rand(batch), self.rotate90, 0.0))
+        if self.xint > 0:
+            raw.append((_lib.AUG_XINT, rand(batch, 2), rand(batch, 1), self.xint, self.xint_max))
+        if self.scale > 0:
+            raw.append((_lib.AUG_SCALE, randn(batch), rand(batch), self.scale, self.scale_std))
+        if self.rotate > 0:
+            raw.append((_lib.AUG_ROTATE, rand(batch), rand(batch), self.rotate, self.rotate_max))
+        if self.aniso > 0:
+            raw.append((_lib.AUG_ANISO, randn(batch), rand(batch), self.aniso, self.aniso_std))
+        if self.rotate > 0:
+            raw.append((_lib.AUG_ROTATE, rand(batch), rand(batch), self.rotate, self.rotate_max))
+        if self.xfrac > 0:
+            raw.append((_lib.AUG_XFRAC, randn(batch, 2), rand(batch, 1), self.xfrac, self.xfrac_std))
+        return raw
+
     def sample_inverse_transform(self, batch, width, height, device):
         """G_inv [B,3,3] composed with torch ops exactly as the reference does (augment.py:196-264); the CPU tests pin
         it to the reference bit for bit.  `forward` composes the same factors in one kernel instead."""
@@ -283,8 +326,8 @@ class AugmentPipe(torch.nn.Module):
         B, _, H, W = images.shape
         if not images.is_cuda:
             raise RuntimeError("object_intrinsics_b200.augment has no CPU path: images must be CUDA tensors")
-        ops = self.sample_ops(B, W, H, images.device)
-        if not ops:
+        raw = self.sample_raw(B, images.device)
+        if not raw:
             return images
-        theta, margins, _ = geometric_setup_ops_cuda(ops, B, H, W, len(self._taps), images.device)
+        theta, margins, _ = geometric_setup_raw_cuda(raw, self.p, B, H, W, len(self._taps), images.device)
         return _GeomForward.apply(images, theta, margins, self._taps)

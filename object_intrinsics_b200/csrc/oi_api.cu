@@ -577,6 +577,20 @@ int oi_augment_geom_setup_ops(const OiAugmentOp* ops, int32_t n_ops, int32_t bat
                                   static_cast<cudaStream_t>(stream));
 }
 
+int oi_augment_geom_setup_raw(const OiAugmentRawOp* ops, int32_t n_ops, const float* p, int32_t batch, int32_t height,
+                              int32_t width, int32_t filter_taps, float* g_inv, float* theta, int32_t* margins,
+                              void* stream) {
+  OI_CHECK_ARG(ops && p && g_inv && theta && margins, "NULL pointer");
+  OI_CHECK_ARG(n_ops >= 1 && n_ops <= OI_AUGMENT_MAX_OPS, "n_ops must be in [1, %d] (got %d)", OI_AUGMENT_MAX_OPS, n_ops);
+  OI_CHECK_ARG(batch > 0 && height >= 2 && width >= 2 && filter_taps >= 4 && filter_taps % 4 == 0, "bad sizes");
+  for (int i = 0; i < n_ops; ++i) {
+    OI_CHECK_ARG(ops[i].form >= OI_AUG_XFLIP && ops[i].form <= OI_AUG_XFRAC, "op %d: bad form %d", i, ops[i].form);
+    OI_CHECK_ARG(ops[i].draw != nullptr && ops[i].gate != nullptr, "op %d: NULL draw", i);
+  }
+  return launch_augment_setup_raw(ops, n_ops, p, batch, height, width, filter_taps / 4, g_inv, g_inv, theta, margins,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* d, size_t* bytes) {
   int rc = check_augment(d, false);
   if (rc) return rc;

@@ -268,8 +268,83 @@ __device__ __forceinline__ void compose_ops(const AugOps& o, int b, float (&g)[9
   }
 }
 
-// G_in != NULL: the transform is given; else it is composed from `ops` (and written to G_out when that is given).
-__global__ void augment_setup_kernel(const float* __restrict__ G_in, const AugOps ops, float* __restrict__ G_out,
+struct AugRawOps {
+  int n;
+  const float* p;
+  OiAugmentRawOp op[OI_AUGMENT_MAX_OPS];
+};
+
+// g = g @ m (fp32, accumulation order of a 3x3 matmul)
+__device__ __forceinline__ void mul3f(float (&g)[9], const float (&m)[9]) {
+  float r[9];
+  for (int rr = 0; rr < 3; ++rr)
+    for (int cc = 0; cc < 3; ++cc)
+      r[rr * 3 + cc] = fmaf(g[rr * 3 + 2], m[6 + cc], fmaf(g[rr * 3 + 1], m[3 + cc], g[rr * 3] * m[cc]));
+  for (int k = 0; k < 9; ++k) g[k] = r[k];
+}
+
+// The reference's per-factor arithmetic on the raw draws (augment.py:196-264), every step rounded as torch rounds it
+// (fp32 products of a tensor with a python scalar, IEEE division / square root, round-half-even).
+__device__ __forceinline__ void compose_raw(const AugRawOps& o, int b, int H, int W, float (&g)[9]) {
+  g[0] = 1.f; g[1] = 0.f; g[2] = 0.f; g[3] = 0.f; g[4] = 1.f; g[5] = 0.f; g[6] = 0.f; g[7] = 0.f; g[8] = 1.f;
+  const float p = *o.p;
+  const float kPi = 3.14159265358979323846f;
+  for (int i = 0; i < o.n; ++i) {
+    const OiAugmentRawOp& r = o.op[i];
+    float m[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    float thr = __fmul_rn(r.prob, p);
+    if (r.form == OI_AUG_ROTATE)
+      thr = __fsub_rn(1.f, __fsqrt_rn(fminf(fmaxf(__fsub_rn(1.f, thr), 0.f), 1.f)));
+    const bool on = r.gate[b] < thr;
+    switch (r.form) {
+      case OI_AUG_XFLIP: {
+        const float k = on ? floorf(__fmul_rn(r.draw[b], 2.f)) : 0.f;
+        m[0] = __fdiv_rn(1.f, __fsub_rn(1.f, __fmul_rn(2.f, k)));
+        break;
+      }
+      case OI_AUG_ROTATE90:
+      case OI_AUG_ROTATE: {
+        float th;
+        if (r.form == OI_AUG_ROTATE90) {
+          const float k = on ? floorf(__fmul_rn(r.draw[b], 4.f)) : 0.f;
+          th = -__fmul_rn(-0.5f * kPi, k);
+        } else {
+          th = on ? __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(r.draw[b], 2.f), 1.f), kPi), r.param) : 0.f;
+        }
+        const float c = cosf(th), sn = sinf(th);
+        m[0] = c; m[1] = -sn; m[3] = sn; m[4] = c;
+        break;
+      }
+      case OI_AUG_XINT: {
+        const float t0 = on ? __fmul_rn(__fsub_rn(__fmul_rn(r.draw[2 * b], 2.f), 1.f), r.param) : 0.f;
+        const float t1 = on ? __fmul_rn(__fsub_rn(__fmul_rn(r.draw[2 * b + 1], 2.f), 1.f), r.param) : 0.f;
+        m[2] = -rintf(__fmul_rn(t0, (float)W));
+        m[5] = -rintf(__fmul_rn(t1, (float)H));
+        break;
+      }
+      case OI_AUG_SCALE:
+      case OI_AUG_ANISO: {
+        const float sc = on ? (float)exp2((double)__fmul_rn(r.draw[b], r.param)) : 1.f;
+        const float inv = __fdiv_rn(1.f, sc);
+        m[0] = inv;
+        m[4] = (r.form == OI_AUG_SCALE) ? inv : __fdiv_rn(1.f, inv);
+        break;
+      }
+      default: {   // OI_AUG_XFRAC
+        const float t0 = on ? __fmul_rn(r.draw[2 * b], r.param) : 0.f;
+        const float t1 = on ? __fmul_rn(r.draw[2 * b + 1], r.param) : 0.f;
+        m[2] = -__fmul_rn(t0, (float)W);
+        m[5] = -__fmul_rn(t1, (float)H);
+        break;
+      }
+    }
+    mul3f(g, m);
+  }
+}
+
+// G_in != NULL: the transform is given; else it is composed from `ops` / `raw` (and written to G_out when given).
+__global__ void augment_setup_kernel(const float* __restrict__ G_in, const AugOps ops, const AugRawOps raw,
+                                     float* __restrict__ G_out,
                                      float* __restrict__ G_tmp, int B, int H, int W, int hz_pad,
                                      float* __restrict__ theta, int* __restrict__ margins) {
   __shared__ float red[4][32];
@@ -279,7 +354,8 @@ __global__ void augment_setup_kernel(const float* __restrict__ G_in, const AugOp
   if (G_in == nullptr) {
     for (int b = tid; b < B; b += 32) {
       float g[9];
-      compose_ops(ops, b, g);
+      if (raw.n > 0) compose_raw(raw, b, H, W, g);
+      else compose_ops(ops, b, g);
       for (int k = 0; k < 9; ++k) {
         G_tmp[b * 9 + k] = g[k];
         if (G_out) G_out[b * 9 + k] = g[k];
@@ -360,7 +436,9 @@ int launch_augment_setup(const float* G_inv, int B, int H, int W, int hz_pad, fl
                          cudaStream_t st) {
   AugOps none;
   none.n = 0;
-  augment_setup_kernel<<<1, 32, 0, st>>>(G_inv, none, nullptr, nullptr, B, H, W, hz_pad, theta, margins);
+  AugRawOps no_raw;
+  no_raw.n = 0;
+  augment_setup_kernel<<<1, 32, 0, st>>>(G_inv, none, no_raw, nullptr, nullptr, B, H, W, hz_pad, theta, margins);
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }
@@ -371,7 +449,22 @@ int launch_augment_setup_ops(const OiAugmentOp* ops, int n_ops, int B, int H, in
   AugOps o;
   o.n = n_ops;
   for (int i = 0; i < n_ops; ++i) o.op[i] = ops[i];
-  augment_setup_kernel<<<1, 32, 0, st>>>(nullptr, o, g_inv, g_tmp, B, H, W, hz_pad, theta, margins);
+  AugRawOps no_raw;
+  no_raw.n = 0;
+  augment_setup_kernel<<<1, 32, 0, st>>>(nullptr, o, no_raw, g_inv, g_tmp, B, H, W, hz_pad, theta, margins);
+  OI_CHECK_CUDA(cudaGetLastError());
+  return OI_OK;
+}
+
+int launch_augment_setup_raw(const OiAugmentRawOp* ops, int n_ops, const float* p, int B, int H, int W, int hz_pad,
+                             float* g_inv, float* g_tmp, float* theta, int* margins, cudaStream_t st) {
+  AugOps none;
+  none.n = 0;
+  AugRawOps r;
+  r.n = n_ops;
+  r.p = p;
+  for (int i = 0; i < n_ops; ++i) r.op[i] = ops[i];
+  augment_setup_kernel<<<1, 32, 0, st>>>(nullptr, none, r, g_inv, g_tmp, B, H, W, hz_pad, theta, margins);
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

@@ -156,6 +156,8 @@ int launch_augment_setup(const float* G_inv, int B, int H, int W, int hz_pad, fl
                          cudaStream_t st);
 int launch_augment_setup_ops(const OiAugmentOp* ops, int n_ops, int B, int H, int W, int hz_pad, float* g_inv,
                              float* g_tmp, float* theta, int* margins, cudaStream_t st);
+int launch_augment_setup_raw(const OiAugmentRawOp* ops, int n_ops, const float* p, int B, int H, int W, int hz_pad,
+                             float* g_inv, float* g_tmp, float* theta, int* margins, cudaStream_t st);
 size_t augment_u_floats(const OiAugmentGeomDesc& d);
 size_t augment_r_floats(const OiAugmentGeomDesc& d);
 int launch_render_maps(const OiRenderMapsDesc& d, cudaStream_t st);

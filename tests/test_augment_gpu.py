@@ -115,3 +115,48 @@ def test_op_list_setup_kernel_matches_torch_composition(name):
     from object_intrinsics_b200.augment import _GeomForward
     y = _GeomForward.apply(x.cuda(), th, m, pipe._taps)
     assert float((y.cpu() - y_ref).abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("kwargs", [dict(xint=1, scale=1),
+                                    dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1),
+                                    dict(xflip=0.5, rotate90=0.5, xint=0.5, scale=0.5, rotate=0.5, aniso=0.5, xfrac=0.5)])
+@pytest.mark.parametrize("p", [1.0, 0.6])
+def test_raw_setup_kernel_matches_sample_ops(kwargs, p):
+    """oi_augment_geom_setup_raw (gating + parameter arithmetic + composition from the RAW draws, what
+    `AugmentPipe.forward` runs) vs `sample_ops` / `sample_inverse_transform` (the reference's torch arithmetic on the
+    SAME draws: both consume the CPU generator identically).  The integer translations and the gates must agree
+    exactly; the composed transform to fp32 rounding of the trigonometric factors."""
+    from object_intrinsics_b200.augment import AugmentPipe, geometric_setup, geometric_setup_raw_cuda
+    B, H, W = 16, 64, 48
+    pipe = AugmentPipe(**kwargs)
+    pipe.p.fill_(p)
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        G = pipe.sample_inverse_transform(B, W, H, torch.device("cpu"))
+        after_ops = torch.rand(1)
+        torch.manual_seed(seed)
+        raw = pipe.sample_raw(B, torch.device("cpu"))
+        assert torch.equal(torch.rand(1), after_ops), "sample_raw must consume the generator exactly like sample_ops"
+        raw = [(f, d.cuda(), g.cuda(), pr, pa) for f, d, g, pr, pa in raw]
+        th, m, g_inv = geometric_setup_raw_cuda(raw, pipe.p.cuda(), B, H, W, 12, torch.device("cuda"))
+        th_ref, m_ref = geometric_setup(G, H, W, 3)
+        scale = 1.0 + float(G.abs().max())
+        assert float((g_inv.cpu() - G).abs().max()) < 2e-6 * scale
+        assert m.cpu().tolist() == m_ref.tolist()
+        assert float((th.cpu() - th_ref).abs().max()) < 1e-5
+
+
+def test_module_forward_uses_the_reference_rng_stream():
+    """`AugmentPipe.forward` on the GPU draws with the same torch calls as `sample_ops`: after a forward the CUDA
+    generator is where the torch-composed path leaves it, and both give the same image."""
+    from object_intrinsics_b200.augment import AugmentPipe, geometric_transform
+    pipe = AugmentPipe(xint=1, scale=1, rotate=0.5, xfrac=0.3).cuda()
+    x = torch.rand(4, 3, 64, 64, device="cuda")
+    torch.manual_seed(11)
+    y = pipe(x)
+    probe = torch.rand(1, device="cuda")
+    torch.manual_seed(11)
+    G = pipe.sample_inverse_transform(4, 64, 64, x.device)
+    assert torch.equal(torch.rand(1, device="cuda"), probe)
+    y_ref = geometric_transform(x, G, pipe._taps)
+    assert float((y - y_ref).abs().max()) < 5e-5

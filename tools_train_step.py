@@ -164,15 +164,19 @@ def measure(dev, P, kernel="auto", flush=None, shape="cfg5", steps=8, shading="k
         for i in range(steps):
             flush.fill_(i & 0xFF)
     b.record()
+    import time
+    t0 = time.perf_counter()
     for i in range(steps):
         if flush is not None:
             flush.fill_(i & 0xFF)
         step()
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps      # host time to ENQUEUE a step
     c.record()
     c.synchronize()
     free_ms = (b.elapsed_time(c) - a.elapsed_time(b)) / steps
     rays_per_step = 3 * bs * patch * patch
     return {"shape": shape, **cfg, "ms_per_step": med["total"], "ms_per_step_free_running": free_ms,
+            "host_enqueue_ms_per_step": host_ms,
             "g_step_ms": med["g_step"],
             "two_no_grad_renders_ms": med["d_step_x2"], "rays_per_step": rays_per_step,
             "rays_per_sec": rays_per_step / (med["total"] * 1e-3),
