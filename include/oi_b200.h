@@ -210,7 +210,10 @@ typedef struct OiRenderBwdDesc {
   int32_t n_samples;         /* n (sample_dist = 2/n, renderer.py:356) */
   int32_t depth;             /* D >= 2 */
   int32_t impl;              /* OiRenderImpl: FFMA = one FP32 kernel; TCGEN05 (= AUTO) = two tensor-core kernels */
-  int32_t flags;
+  int32_t flags;             /* tensor-core backward, format of the per-point operands of the weight-gradient contraction:
+                              * default = chosen per call on the device from the adjoints' dynamic range (scaled fp16 when
+                              * the points more than 2^18 below the largest adjoint carry < 2^-12 of the adjoint mass, else
+                              * TF32); bit 5 (value 32): always TF32; bit 6 (value 64): always scaled fp16 */
   int32_t reserved;
   float cos_anneal_ratio;
   float reserved_f;

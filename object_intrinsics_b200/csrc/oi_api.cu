@@ -498,7 +498,7 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
   return launch_render_bwd_tc(*d, a, adj, invs_partial, d_film,
                               reinterpret_cast<float*>(ws + w.scratch), reinterpret_cast<float*>(ws + w.slabs),
                               reinterpret_cast<float*>(ws + w.aux), reinterpret_cast<float*>(ws + w.dw_inst),
-                              w.chunk_tiles, w.n_ctas, st);
+                              reinterpret_cast<const unsigned int*>(ws + w.relax_count), w.chunk_tiles, w.n_ctas, st);
 }
 
 int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,

@@ -22,6 +22,7 @@
 // t_{D-1} = w_s c_{D-1}, g_l = W_l^T t_l, t_{l-1} = g_l c_{l-1}, normal = g_0.
 #include "oi_internal.cuh"
 #include "oi_render_common.cuh"
+#include "oi_wgrad.cuh"
 
 namespace oi {
 
@@ -861,6 +862,7 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
   // ---- pass 2: back to front
   float suffix_carry = 0.f, invs_bar = 0.f;
   float sum_sb = 0.f, sum_z0 = 0.f, sum_z1 = 0.f, sum_z2 = 0.f;
+  float amax = 0.f;   // max |adjoint component| over this warp's points
   for (int blk = n_blk - 1; blk >= 0; --blk) {
     const int i = blk * 32 + lane;
     const bool ok = i < S;
@@ -932,6 +934,8 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
       float4* out = reinterpret_cast<float4*>(a.adj + gp * 8);
       out[0] = make_float4(sdf_bar, nb0, nb1, nb2);
       out[1] = make_float4(z0, z1, z2, 0.f);
+      amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(sdf_bar), fabsf(nb0)), fmaxf(fabsf(nb1), fabsf(nb2))),
+                               fmaxf(fmaxf(fabsf(z0), fabsf(z1)), fabsf(z2))));
       sum_sb += sdf_bar;
       sum_z0 += z0;
       sum_z1 += z1;
@@ -940,9 +944,13 @@ __global__ void tail_bwd_kernel(const TailArgs a) {
   }
   __syncwarp();
   invs_bar = warp_sum(invs_bar);
+  for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
   if (live && lane == 0) {
     if (a.g_s_val) invs_bar -= a.g_s_val[ray] / (inv_s * inv_s);
     a.invs_partial[ray] = invs_bar;
+    // global max |adj| (non-negative floats order like their bit patterns; inf / NaN saturate the exponent field and
+    // bwd_mode() then keeps the TF32 operands)
+    if (amax > 0.f) atomicMax(a.relax_count + 1, __float_as_uint(amax));
   }
   if (a.d_sigma_bias) {
     sum_sb = warp_sum(sum_sb);
@@ -1009,6 +1017,35 @@ int render_bwd_ctas(int n_tiles) {
 size_t render_bwd_scratch_floats() { return (size_t)kNumSlots * kSlot; }
 
 // relax count + per-ray tail: fills adj [N][8] and invs_partial [R]; zeroes d_film.
+// Adjoint statistics for bwd_mode() (oi_wgrad.cuh): total "mass" sum_m A_m / 2^e_max in 2^-20 fixed point (A_m = max
+// |adjoint component| of point m) and the mass of the points more than 2^kF16LowShift below the global maximum --
+// integer sums, so the decision is the same in every run.
+__global__ void adj_stats_kernel(const float* __restrict__ adj, size_t n_points, unsigned int* ctl) {
+  const unsigned int mb = ctl[1];
+  const int ex = (int)((mb >> 23) & 0xFFu);
+  if (ex == 0 || ex == 255) return;
+  const int e_max = ex - 127;
+  const float unit = pow2i(20 - e_max);
+  unsigned long long tot = 0, low = 0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += (size_t)gridDim.x * blockDim.x) {
+    const float4* q = reinterpret_cast<const float4*>(adj + p * 8);
+    const float4 q0 = q[0], q1 = q[1];
+    const float am = fmaxf(fmaxf(fmaxf(fabsf(q0.x), fabsf(q0.y)), fmaxf(fabsf(q0.z), fabsf(q0.w))),
+                           fmaxf(fmaxf(fabsf(q1.x), fabsf(q1.y)), fabsf(q1.z)));
+    const unsigned long long v = (unsigned long long)(am * unit);
+    tot += v;
+    if (adj_exponent(q0, q1) < e_max - kF16LowShift) low += v;
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, d);
+    low += __shfl_xor_sync(0xffffffffu, low, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(ctl + 2), tot);
+    if (low) atomicAdd(reinterpret_cast<unsigned long long*>(ctl + 4), low);
+  }
+}
+
 int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
                     unsigned int* relax_count, float* d_film, bool head_biases, cudaStream_t st) {
   TailArgs t;
@@ -1048,6 +1085,10 @@ int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj
   }
   tail_bwd_kernel<<<(t.R + 7) / 8, 256, 0, st>>>(t);   // 8 warps per block, one ray per warp
   OI_CHECK_CUDA(cudaGetLastError());
+  if (head_biases && !(d.flags & (OI_BWD_FLAG_FORCE_TF32 | OI_BWD_FLAG_FORCE_F16))) {   // tensor-core backward, automatic
+    adj_stats_kernel<<<296, 256, 0, st>>>(adj, (size_t)t.R * t.S, relax_count);
+    OI_CHECK_CUDA(cudaGetLastError());
+  }
   return OI_OK;
 }
 

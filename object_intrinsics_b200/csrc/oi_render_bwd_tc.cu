@@ -79,6 +79,7 @@ struct BwdTcArgs {
   OiNetGrads g;            // per-channel sums over points of the narrow heads (warp butterflies + atomics)
   float* d_film;           // [n_inst][9][2][128] (unused | db)
   float* dw0;              // [n_inst][128][3] per-instance dW_0 (both parts)
+  const unsigned int* ctl; // control block of the call (oi_wgrad.cuh: bwd_mode)
 };
 
 struct __align__(1024) BwdTcSmem {
@@ -210,10 +211,15 @@ __device__ __forceinline__ void run_stage(uint32_t acc, Load load, Body body, Wa
   }
 }
 
+// F16: the operand slabs are written as scaled fp16 (oi_wgrad.cuh) instead of TF32; both variants are launched and the
+// one bwd_mode() does not select exits at once.
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   BwdTcSmem& sm = *reinterpret_cast<BwdTcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BwdMode mode = bwd_mode(a.ctl, a.r.flags);
+  if (mode.f16 != F16) return;
   const int D = a.r.D;
   const BlobLayout L = blob_layout(D);
   const float* cst = a.r.blob + L.const_off;
@@ -358,6 +364,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       float* gso = slab_tile + (m >> 5) * 4096 + (m & 3) + n0 * 32;           // operand slabs, this thread's channels
       // aux operand (N = 16, rows 0..3 used): [32-point block][4 rows][32 points], same swizzle
       float* auxo = a.aux + (size_t)lt * 512 + (m >> 5) * 128 + (m & 3);
+      // fp16 operand slabs: 64-point block m >> 6, row = channel (128 B), 16-byte chunk ((m & 63) >> 3) ^ (channel & 7),
+      // this lane PAIR's 4 bytes (points m & ~1, m | 1) at ((m & 6) * 2); channel & 7 = the position e inside an oct
+      unsigned char* gso16 = reinterpret_cast<unsigned char*>(slab_tile) + (m >> 6) * 16384 + n0 * 128 + (m & 6) * 2;
+      const int mc16 = ((m & 63) >> 3) << 4;   // byte offset of the chunk before the XOR: (chunk ^ e) << 4 = mc16 ^ (e << 4)
+      unsigned char* auxo16 = reinterpret_cast<unsigned char*>(a.aux + (size_t)lt * 512) + (m >> 6) * 512 + (m & 7) * 2;
       float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][unused | db][128]
       float* dw0 = a.dw0 + (size_t)inst * kW * 3;
       {
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         for (int i = sub; i < kFilm * kW; i += kEpiThreadsPerSlot) dst[i] = src[i];
       }
       float px, py, pz, sdf_bar, nb0, nb1, nb2, zb0, zb1, zb2;
+      float sc_adj = 1.f, sc_fwd = 1.f;   // fp16 slabs: power-of-two scales of the adjoint- / forward-type operands
       {
         const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
         px = pc.px;
@@ -379,6 +391,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         }
         sdf_bar = q0.x; nb0 = q0.y; nb1 = q0.z; nb2 = q0.w;
         zb0 = q1.x; zb1 = q1.y; zb2 = q1.z;
+        if (F16) {
+          const int e_m = adj_exponent(q0, q1);
+          sc_adj = pow2i(-e_m);
+          sc_fwd = pow2i(e_m - mode.e_ref);
+        }
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
 
@@ -386,7 +403,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
 #define OI_CTA(slab, quad) scr4[((size_t)(slab) * 32 + (quad)) * 128]
 #define OI_FILM4(l) (reinterpret_cast<const float4*>(sm.film[t][(l)]) + n0 / 2)   /* (g0, g1, d0, d1) per pair */
       // the 8 values of an oct -> operand slab `slab` (rounded to TF32)
-      auto op8 = [&](int slab, int o, const float (&v)[8]) {
+      auto op8 = [&](int slab, int o, const float (&v)[8], bool adjoint) {
+        if (F16) {
+          // lanes 2j / 2j+1 swap one value per channel pair: the even lane then holds channel 2i of both points, the odd
+          // lane channel 2i+1, and each stores ONE packed fp16x2 (4 stores per oct instead of 8)
+          const float sc = adjoint ? sc_adj : sc_fwd;
+          unsigned char* p = gso16 + slab16_offset(slab) + o * 1024;
+          const bool odd = (lane & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float mine = (odd ? v[2 * i + 1] : v[2 * i]) * sc;
+            const float send = (odd ? v[2 * i] : v[2 * i + 1]) * sc;
+            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+            const float first = odd ? got : mine, second = odd ? mine : got;   // points m & ~1, m | 1
+            uint32_t pk;
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(second), "f"(first));
+            const int e = 2 * i + (odd ? 1 : 0);
+            *reinterpret_cast<uint32_t*>(p + e * 128 + (mc16 ^ (e << 4))) = pk;
+          }
+          return;
+        }
         float* p = gso + (size_t)slab * kSlabFloats + o * 256;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -438,7 +474,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           st_arg(&OI_ARG(0, Q0 + 2 * o), make_float4(ar[0], ar[1], ar[2], ar[3]));
           st_arg(&OI_ARG(0, Q0 + 2 * o + 1), make_float4(ar[4], ar[5], ar[6], ar[7]));
-          op8(kSlabH + 1, o, s);
+          op8(kSlabH + 1, o, s, false);
           a8_f16(o, s);
         }, wait_acc, no_next);
         a_ready();
@@ -461,7 +497,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           st_arg(&OI_ARG(l, Q0 + 2 * o), make_float4(ar[0], ar[1], ar[2], ar[3]));
           st_arg(&OI_ARG(l, Q0 + 2 * o + 1), make_float4(ar[4], ar[5], ar[6], ar[7]));
-          op8(kSlabH + l + 1, o, s);
+          op8(kSlabH + l + 1, o, s, false);
           a8_f16(o, s);
         }, wait_acc, no_next);
         a_ready();
@@ -488,7 +524,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             tv[2 * i] = sm.head[n].x * f.x * __cosf(ar[2 * i]);
             tv[2 * i + 1] = sm.head[n + 1].x * f.y * __cosf(ar[2 * i + 1]);
           }
-          op8(kSlabT + D - 1, o, tv);
+          op8(kSlabT + D - 1, o, tv, false);
           a8_f16(o, tv);
         }, wait_acc, [&]() { if (D >= 2) pf_nxt(&OI_ARG(D - 2, Q0)); });
         a_ready();
@@ -517,7 +553,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           st_cta(&OI_CTA(kCtaG + l - 1, Q0 + 2 * o), make_float4(gv[0], gv[1], gv[2], gv[3]));
           st_cta(&OI_CTA(kCtaG + l - 1, Q0 + 2 * o + 1), make_float4(gv[4], gv[5], gv[6], gv[7]));
           if (l > 1) {
-            op8(kSlabT + l - 1, o, tv);
+            op8(kSlabT + l - 1, o, tv, false);
             a8_f16(o, tv);
           } else {
 #pragma unroll
@@ -579,7 +615,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               nc2 = fmaf(hd.w * kInvWScale, ub_[e], nc2);
             }
           }
-          op8(kSlabUBC, o, ub_);
+          op8(kSlabUBC, o, ub_, true);
           a8_bf16(o, ub_);
           if (o == 7) a_ready();   // the tensor core starts on W_cf^T u_bar_c while the column sums are reduced
           {
@@ -609,10 +645,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         nb2 += nc2 + xch[o + 3];
       }
       if (h == 0) {
-        auxo[0 * 32 + ((mc ^ 0) << 2)] = tf32_bias(gx);
-        auxo[1 * 32 + ((mc ^ 1) << 2)] = tf32_bias(gy);
-        auxo[2 * 32 + ((mc ^ 2) << 2)] = tf32_bias(gz);
-        auxo[3 * 32 + ((mc ^ 3) << 2)] = 1.0f;
+        if (F16) {   // rows of 128 B = 64 points, chunk XOR row
+          const float av[4] = {gx * sc_fwd, gy * sc_fwd, gz * sc_fwd, sc_fwd};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            unsigned short hbits;
+            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(av[r]));
+            *reinterpret_cast<unsigned short*>(auxo16 + r * 128 + (mc16 ^ (r << 4))) = hbits;
+          }
+        } else {
+          auxo[0 * 32 + ((mc ^ 0) << 2)] = tf32_bias(gx);
+          auxo[1 * 32 + ((mc ^ 1) << 2)] = tf32_bias(gy);
+          auxo[2 * 32 + ((mc ^ 2) << 2)] = tf32_bias(gz);
+          auxo[3 * 32 + ((mc ^ 3) << 2)] = 1.0f;
+        }
       }
       // ---------------- h_bar_D = W_cf^T u_bar_c + sdf_bar w_s -> slot HB;
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
@@ -649,7 +695,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           st_cta(&OI_CTA(kCtaHB, Q0 + 2 * o + 1), make_float4(hb[4], hb[5], hb[6], hb[7]));
           st_cta(&OI_CTA(kCtaG + 0, Q0 + 2 * o), make_float4(cb[0], cb[1], cb[2], cb[3]));   // c_bar_0
           st_cta(&OI_CTA(kCtaG + 0, Q0 + 2 * o + 1), make_float4(cb[4], cb[5], cb[6], cb[7]));
-          op8(kSlabGB + 1, o, gb);
+          op8(kSlabGB + 1, o, gb, true);
           a8_bf16(o, gb);
           if (o == 7) a_ready();
           {  // dW_0 += t_0 (x) normal_bar (per instance)
@@ -693,7 +739,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           st_cta(&OI_CTA(kCtaG + l, Q0 + 2 * o), make_float4(cb[0], cb[1], cb[2], cb[3]));
           st_cta(&OI_CTA(kCtaG + l, Q0 + 2 * o + 1), make_float4(cb[4], cb[5], cb[6], cb[7]));
-          op8(kSlabGB + l + 1, o, gb);
+          op8(kSlabGB + l + 1, o, gb, true);
           a8_bf16(o, gb);
         }, wait_acc, [&]() { if (l + 1 < D - 1) { pf_nxt(&OI_ARG(l + 1, Q0)); pf_nxt(&OI_CTA(kCtaG + l + 1, Q0)); } else { pf_nxt(&OI_ARG(D - 1, Q0)); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
         a_ready();
@@ -729,7 +775,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               ubv[e] = ab * gam;   // u_bar_{D-1}
             }
           }
-          op8(kSlabUB + l, o, ubv);
+          op8(kSlabUB + l, o, ubv, true);
           a8_bf16(o, ubv);
           if (o == 7) a_ready();
           colsum8(dws, a.g.sigma_weight + n0 + o * 8, 1, lane);
@@ -765,7 +811,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             }
           }
           if (k >= 1) {
-            op8(kSlabUB + k, o, ubv);
+            op8(kSlabUB + k, o, ubv, true);
             a8_bf16(o, ubv);
           } else {
             const int nc = n0 + o * 8;
@@ -898,10 +944,12 @@ size_t render_bwd_tc_dw_floats(int n_inst, int depth) {
 
 // Runs the two tensor-core kernels over tiles [0, n_tiles) in chunks of at most `chunk_tiles`.
 int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
-                         float* d_film, float* scratch, float* slabs, float* aux, float* dw_inst, int chunk_tiles,
-                         int n_ctas, cudaStream_t st) {
+                         float* d_film, float* scratch, float* slabs, float* aux, float* dw_inst,
+                         const unsigned int* ctl, int chunk_tiles, int n_ctas, cudaStream_t st) {
   const int n_inst = geo.n_inst, D = geo.D;
-  OI_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  OI_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(BwdTcSmem)));
+  OI_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(BwdTcSmem)));
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
@@ -927,8 +975,16 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     a.d_film = d_film;
     a.dw0 = dw0;
     const int ctas = render_bwd_tc_ctas(t1 - t0) < n_ctas ? render_bwd_tc_ctas(t1 - t0) : n_ctas;
-    bwd_tc_kernel<<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
-    OI_CHECK_CUDA(cudaGetLastError());
+    a.ctl = ctl;
+    // both operand formats are launched; bwd_mode() (adjoint statistics, on the device) lets one of them exit at once
+    if (!(geo.flags & OI_BWD_FLAG_FORCE_F16)) {
+      bwd_tc_kernel<false><<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
+      OI_CHECK_CUDA(cudaGetLastError());
+    }
+    if (!(geo.flags & OI_BWD_FLAG_FORCE_TF32)) {
+      bwd_tc_kernel<true><<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
+      OI_CHECK_CUDA(cudaGetLastError());
+    }
 
     // ---- contraction over the points of this chunk (per-instance outputs: the finalize kernel needs them)
     WgArgs w;
@@ -938,6 +994,8 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     w.slabs_per_tile = kSlabsPerTile;
     w.slabs = slabs;
     w.aux = aux;
+    w.ctl = ctl;
+    w.flags = geo.flags;
     w.tile0 = t0;
     float* dfilm0 = d_film;
     auto dbia = [&](int slot) { return dfilm0 + (size_t)slot * 2 * kW + kW; };

@@ -20,6 +20,56 @@ constexpr int kSlabsPerTile = 38;
 constexpr int kSlabFloats = 128 * 128;
 // ---- aux: per tile four 32-point blocks of [4 rows][32 points] fp32 (same swizzle): rows = normal.xyz, 1 ----
 
+// ---- 16-bit operand slabs (OI_BWD_FLAG_* / automatic): the 30 operand slabs are stored as fp16 instead -- 32 KB per
+//      slab: two 64-point blocks of the K-major SWIZZLE_128B fp16 image [128 channels][64 points]; the ARG slabs stay
+//      fp32; slab s >= kSlabOperand0 lives at 8 * 64 KB + (s - 8) * 32 KB inside the tile's (unchanged) region.
+//      fp16 has TF32's 10 mantissa bits but 5 exponent bits, so every operand is scaled by an exact power of two:
+//        adjoint-type operands (UB, GB, UBC)   x 2^-e_m              e_m = exponent of max |adj[m][0..6]| of the point
+//        forward-type operands (H, T, aux)     x 2^(e_m - e_ref)     e_ref = (exponent of the global max |adj|) - 10
+//      => every product carries 2^-e_ref, undone when the contraction kernel flushes its accumulators.  The adjoint
+//      operands are then bounded by the network's Jacobians alone, the forward operands by 2^10 |value|; points whose
+//      adjoint is more than 2^18 below the global maximum lose precision gradually.  bwd_mode() (below) selects the
+//      path per call ON THE DEVICE from the adjoint statistics adj_stats_kernel leaves in the control block: fp16 when
+//      those points carry < 2^-12 of the total adjoint mass, TF32 otherwise; both kernel variants are launched and the
+//      one not selected exits at once (no host round trip).
+constexpr int kSlabOperand0 = 8;
+constexpr int kSlabBytes = 65536, kSlab16Bytes = 32768;
+__host__ __device__ constexpr size_t slab16_offset(int s) {
+  return s < kSlabOperand0 ? (size_t)s * kSlabBytes : (size_t)kSlabOperand0 * kSlabBytes + (size_t)(s - kSlabOperand0) * kSlab16Bytes;
+}
+constexpr int OI_BWD_FLAG_FORCE_TF32 = 32, OI_BWD_FLAG_FORCE_F16 = 64;
+constexpr int kF16RefShift = 10, kF16LowShift = 18, kF16MassShift = 12;
+
+// control block of one backward call (32-bit words, zeroed by launch_bwd_tail):
+//   [0] relax count   [1] bits of max |adj|   [2,3] u64 total adjoint mass   [4,5] u64 mass of the low points
+struct BwdMode {
+  bool f16;
+  int e_ref;
+};
+__device__ __forceinline__ BwdMode bwd_mode(const unsigned int* ctl, int flags) {
+  const unsigned int mb = ctl[1];
+  const int ex = (int)((mb >> 23) & 0xFFu);
+  const unsigned long long tot = *reinterpret_cast<const unsigned long long*>(ctl + 2);
+  const unsigned long long low = *reinterpret_cast<const unsigned long long*>(ctl + 4);
+  BwdMode m;
+  m.f16 = ex > 0 && ex < 255 && low <= (tot >> kF16MassShift);
+  if (flags & OI_BWD_FLAG_FORCE_TF32) m.f16 = false;
+  if ((flags & OI_BWD_FLAG_FORCE_F16) && ex > 0 && ex < 255) m.f16 = true;
+  m.e_ref = ex - 127 - kF16RefShift;
+  return m;
+}
+// 2^e as a float, e clamped to the normal range (e < -126 -> 0)
+__device__ __forceinline__ float pow2i(int e) {
+  return e < -126 ? 0.f : __uint_as_float((unsigned int)((e > 127 ? 127 : e) + 127) << 23);
+}
+// exponent of max |adj| of a point (its first 7 adjoint components); zero / denormal -> -126
+__device__ __forceinline__ int adj_exponent(float4 q0, float4 q1) {
+  const float a = fmaxf(fmaxf(fmaxf(fabsf(q0.x), fabsf(q0.y)), fmaxf(fabsf(q0.z), fabsf(q0.w))),
+                        fmaxf(fmaxf(fabsf(q1.x), fabsf(q1.y)), fabsf(q1.z)));
+  const int ex = (int)((__float_as_uint(a) >> 23) & 0xFFu);
+  return ex == 0 ? -126 : ex - 127;
+}
+
 constexpr int WG_MAX_GROUPS = 12;
 
 struct WgPair {
@@ -44,6 +94,8 @@ struct WgArgs {
   int tile0;           // global index of slab tile 0 (instance of slab tile t = (tile0 + t) / tiles_per_inst)
   const float* slabs;  // [n_tiles][slabs_per_tile][4 blocks][128 channels][32 points]
   const float* aux;    // [n_tiles][4 blocks][4 rows][32 points]
+  const unsigned int* ctl;   // control block of the backward call (bwd_mode); NULL = TF32 slabs unconditionally
+  int flags;
   WgGroup groups[WG_MAX_GROUPS];
 };
 

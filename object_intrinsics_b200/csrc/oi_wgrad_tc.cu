@@ -50,10 +50,37 @@ __device__ __forceinline__ void mma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+__device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// F16 = false: TF32 slabs, one pipeline stage = 64 points of an operand pair (two per tile);
+// F16 = true : fp16 slabs (oi_wgrad.cuh), one stage = all 128 points of a tile; same 32 KB per operand and stage, same
+//              eight MMAs per stage (K = 8 tf32 / K = 16 fp16 elements = 32 bytes of a 128-byte row each).
+template <bool F16>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float out_scale = 1.0f;
+  if (a.ctl != nullptr) {
+    const BwdMode mode = bwd_mode(a.ctl, a.flags);
+    if (mode.f16 != F16) return;   // the other variant of this launch pair does the work
+    if (F16) out_scale = pow2i(mode.e_ref);
+  } else if (F16) {
+    return;
+  }
+  constexpr int kHalves = F16 ? 1 : 2;
+  constexpr uint32_t kIdMain = F16 ? tc::make_idesc_f16(128, 128) : idesc_tf32(128);
+  constexpr uint32_t kIdAux = F16 ? tc::make_idesc_f16(128, 16) : idesc_tf32(16);
   int group = 0;
   while (group + 1 < a.n_groups && (int)blockIdx.x >= a.groups[group + 1].cta0) ++group;
   const WgGroup& G = a.groups[group];
@@ -91,18 +118,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       for (int tile = t_begin; tile < t_end; ++tile) {
         const unsigned char* slabs = reinterpret_cast<const unsigned char*>(a.slabs) +
                                      (size_t)tile * a.slabs_per_tile * (2 * kHalfBytes);
-        const unsigned char* aux = reinterpret_cast<const unsigned char*>(a.aux) + (size_t)tile * 2048;   // 4 x 512 B
-        for (int half = 0; half < 2; ++half) {
+        // aux: TF32 4 x 512 B per tile (32-point blocks of [4 rows][32 points] fp32); fp16 2 x 512 B (64-point blocks
+        // of [4 rows][64 points] fp16) in the first half of the same 2 KB
+        const unsigned char* aux = reinterpret_cast<const unsigned char*>(a.aux) + (size_t)tile * 2048;
+        for (int half = 0; half < kHalves; ++half) {
           for (int p = 0; p < n_pairs; ++p, ++it) {
             const int stage = it % kWgStages;
             if (it >= kWgStages) mbar_wait_sleep(&sm.empty[stage], ((it / kWgStages) - 1) & 1, 1000u);
             const bool with_aux = (p == 0) && use_aux;
             mbar_expect_tx(&sm.full[stage], 2 * kHalfBytes + (with_aux ? 1024 : 0));
-            tma_bulk_g2s(sm.x[stage], slabs + ((size_t)G.pairs[p].x_slab * 2 + half) * kHalfBytes, kHalfBytes,
-                         &sm.full[stage]);
-            tma_bulk_g2s(sm.y[stage], slabs + ((size_t)G.pairs[p].y_slab * 2 + half) * kHalfBytes, kHalfBytes,
-                         &sm.full[stage]);
-            if (with_aux) {   // rows 0..3 of each 32-point block; rows 4..15 stay zero
+            const size_t xo = F16 ? slab16_offset(G.pairs[p].x_slab) : ((size_t)G.pairs[p].x_slab * 2 + half) * kHalfBytes;
+            const size_t yo = F16 ? slab16_offset(G.pairs[p].y_slab) : ((size_t)G.pairs[p].y_slab * 2 + half) * kHalfBytes;
+            tma_bulk_g2s(sm.x[stage], slabs + xo, kHalfBytes, &sm.full[stage]);
+            tma_bulk_g2s(sm.y[stage], slabs + yo, kHalfBytes, &sm.full[stage]);
+            if (with_aux) {   // rows 0..3 of each block; rows 4..15 stay zero
               tma_bulk_g2s(sm.aux[stage], aux + (half * 2) * 512, 512, &sm.full[stage]);
               tma_bulk_g2s(sm.aux[stage] + 2048, aux + (half * 2 + 1) * 512, 512, &sm.full[stage]);
             }
@@ -127,7 +156,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
           cur_inst = inst;
           fresh = true;
         }
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < kHalves; ++half) {
           for (int p = 0; p < n_pairs; ++p, ++it) {
             const int stage = it % kWgStages;
             mbar_wait_sleep(&sm.full[stage], (it / kWgStages) & 1, 1000u);
@@ -135,15 +164,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
             const uint32_t xb = smem_u32(sm.x[stage]), yb = smem_u32(sm.y[stage]), ab = smem_u32(sm.aux[stage]);
             const bool with_aux = (p == 0) && use_aux;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {   // 8 points per instruction: block k / 4, 32-byte step k % 4 in the row
+            for (int k = 0; k < 8; ++k) {   // 8 (tf32) / 16 (fp16) points per instruction: block k / 4, 32-byte step k % 4
               const uint32_t xo = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
               const uint64_t xd = tc::make_desc_k_sw128(xb + xo);
-              mma_ss_tf32(tmem_base, xd, tc::make_desc_k_sw128(yb + xo), idesc_tf32(128),
-                          (fresh && k == 0) ? 0u : 1u);
-              if (with_aux)
-                mma_ss_tf32(tmem_base + 128, xd,
-                            tc::make_desc_k_sw128(ab + (uint32_t)(k >> 2) * 2048u + (uint32_t)(k & 3) * 32u),
-                            idesc_tf32(16), (fresh && k == 0) ? 0u : 1u);
+              const uint64_t yd = tc::make_desc_k_sw128(yb + xo);
+              const uint64_t ad = tc::make_desc_k_sw128(ab + (uint32_t)(k >> 2) * 2048u + (uint32_t)(k & 3) * 32u);
+              const uint32_t acc = (fresh && k == 0) ? 0u : 1u;
+              if (F16) {
+                mma_ss_f16(tmem_base, xd, yd, kIdMain, acc);
+                if (with_aux) mma_ss_f16(tmem_base + 128, xd, ad, kIdAux, acc);
+              } else {
+                mma_ss_tf32(tmem_base, xd, yd, kIdMain, acc);
+                if (with_aux) mma_ss_tf32(tmem_base + 128, xd, ad, kIdAux, acc);
+              }
             }
             fresh = false;
             tc::mma_commit(&sm.empty[stage]);
@@ -172,12 +205,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
         if ((G.out_ld & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + c * 32 + j), "f"(u[j]),
-                         "f"(u[j + 1]), "f"(u[j + 2]), "f"(u[j + 3])
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + c * 32 + j),
+                         "f"(u[j] * out_scale), "f"(u[j + 1] * out_scale), "f"(u[j + 2] * out_scale),
+                         "f"(u[j + 3] * out_scale)
                          : "memory");
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(row + c * 32 + j, u[j]);
+          for (int j = 0; j < 32; ++j) atomicAdd(row + c * 32 + j, u[j] * out_scale);
         }
       }
       if (use_aux) {
@@ -189,7 +223,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
           float* dst = G.aux_out[c];
           if (dst != nullptr)
             atomicAdd(dst + (size_t)cur_inst * G.aux_inst_stride[c] + (size_t)i * G.aux_ch_stride[c],
-                      __uint_as_float(r[c]));
+                      __uint_as_float(r[c]) * out_scale);
         }
       }
       tc::fence_before_thread_sync();
@@ -222,10 +256,16 @@ int launch_wgrad_tc(const WgArgs& a_in, cudaStream_t st) {
     a.groups[g].n_splits = n;
     cta += n;
   }
-  OI_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  OI_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(WgSmem)));
-  wgrad_tc_kernel<<<cta, kWgThreads, sizeof(WgSmem), st>>>(a);
+  wgrad_tc_kernel<false><<<cta, kWgThreads, sizeof(WgSmem), st>>>(a);
   OI_CHECK_CUDA(cudaGetLastError());
+  if (a.ctl != nullptr && !(a.flags & OI_BWD_FLAG_FORCE_TF32)) {   // the fp16-slab variant; one of the two exits at once
+    OI_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(WgSmem)));
+    wgrad_tc_kernel<true><<<cta, kWgThreads, sizeof(WgSmem), st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+  }
   return OI_OK;
 }
 
