@@ -43,6 +43,9 @@
 #ifndef OI_BWD_STHINT
 #define OI_BWD_STHINT 0  // experiment: L2 eviction hints on the slab stores (1: operand slabs evict-first; 2: + per-CTA
 #endif                   // slabs evict-last; 3: + ARG slabs evict-last)
+#ifndef OI_BWD_OCT_UNROLL
+#define OI_BWD_OCT_UNROLL 4   // octs per unrolled group of a stage's oct loop (2, 4 or 8)
+#endif
 #ifndef OI_BWD_PF4
 #define OI_BWD_PF4 1   // ... in stages that re-read two slabs
 #endif
@@ -199,15 +202,23 @@ __device__ __forceinline__ void run_stage(uint32_t acc, Load load, Body body, Wa
     wait_acc();
     tmem_ld8_async(acc, ub[0]);
   }
+  // the oct loop is unrolled in groups of kOctUnroll (a multiple of the buffer depths, so that every buffer index is
+  // static): fully unrolled the kernel is ~17 000 instructions and stalls on instruction fetch
+  constexpr int U = OI_BWD_OCT_UNROLL;
+  static_assert(8 % U == 0 && U % 2 == 0 && U % (PF + 1) == 0, "oct unroll must divide 8 and cover the buffer rotation");
+#pragma unroll 1
+  for (int oo = 0; oo < 8; oo += U) {
 #pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    if (o + PF < 8) load(o + PF, buf[(o + PF) % (PF + 1)]);
-    if (WAIT) {
-      tc::wait_ld();
-      if (o < 7) tmem_ld8_async(acc + (o + 1) * 8, ub[(o + 1) & 1]);
+    for (int u = 0; u < U; ++u) {
+      const int o = oo + u;
+      if (o + PF < 8) load(o + PF, buf[(u + PF) % (PF + 1)]);
+      if (WAIT) {
+        tc::wait_ld();
+        if (o < 7) tmem_ld8_async(acc + (o + 1) * 8, ub[(u + 1) & 1]);
+      }
+      body(o, ub[u & 1], buf[u % (PF + 1)]);
+      if (o == OI_BWD_PFOCT) next();
     }
-    body(o, ub[o & 1], buf[o % (PF + 1)]);
-    if (o == OI_BWD_PFOCT) next();
   }
 }
 
