@@ -43,6 +43,12 @@
 #ifndef OI_BWD_STHINT
 #define OI_BWD_STHINT 0  // experiment: L2 eviction hints on the slab stores (1: operand slabs evict-first; 2: + per-CTA
 #endif                   // slabs evict-last; 3: + ARG slabs evict-last)
+#ifndef OI_BWD_ARG16
+#define OI_BWD_ARG16 1   // pre-activations kept for later stages as 16-bit phases (a mod 2 pi in 2^-16 turns), not fp32
+#endif
+#ifndef OI_BWD_G16
+#define OI_BWD_G16 1     // with fp16 operand slabs: the per-CTA g / c_bar slabs as fp16 too
+#endif
 #ifndef OI_BWD_OCT_UNROLL
 #define OI_BWD_OCT_UNROLL 4   // octs per unrolled group of a stage's oct loop (2, 4 or 8)
 #endif
@@ -159,6 +165,48 @@ __device__ __forceinline__ void st_hint4(float4* p, float4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w), "l"(pol)
                : "memory");
+}
+
+// ---- 16-bit forms of what later stages re-read (8 values of an oct <-> one uint4) ----
+// Pre-activation a -> phase: a mod 2 pi in units of 2^-16 turn.  Later stages only take sin / cos of it, for gradient
+// terms: |error| <= 2 pi 2^-17 = 4.8e-5 rad, below the 2^-11 rounding of the tensor-core operands it feeds.
+__device__ __forceinline__ uint32_t phase16(float a) {
+  const float kMagic = 12582912.0f;                              // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float k = fmaf(a, 0.15915494309189535f, kMagic) - kMagic;   // round(a / 2 pi)
+  float r = fmaf(-k, 6.2831854820251465f, a);                    // Cody-Waite: 2 pi = hi + lo
+  r = fmaf(-k, -1.7484555314695172e-07f, r);                     // r in [-pi, pi]
+  return __float_as_uint(fmaf(r, 10430.378350470453f, kMagic));  // caller keeps the low 16 bits (two's complement)
+}
+__device__ __forceinline__ uint4 pack_phase8(const float (&a)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = __byte_perm(phase16(a[2 * i]), phase16(a[2 * i + 1]), 0x5410);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void unpack_phase8(const float4& b, float (&a)[8]) {
+  const uint32_t w[4] = {__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)};
+  const float kTwo23 = 8388608.0f, kStep = 9.587379924285257e-05f;   // 2 pi / 65536; angle in [0, 2 pi)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[2 * i] = (__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7610)) - kTwo23) * kStep;
+    a[2 * i + 1] = (__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7632)) - kTwo23) * kStep;
+  }
+}
+__device__ __forceinline__ uint4 pack_half8(const float (&v)[8], float sc) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(v[2 * i + 1] * sc), "f"(v[2 * i] * sc));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void unpack_half8(const float4& b, float inv_sc, float (&v)[8]) {
+  const uint32_t w[4] = {__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x * inv_sc;
+    v[2 * i + 1] = f.y * inv_sc;
+  }
 }
 
 // Sum over the 32 lanes of a warp (= 32 sample points) of 8 per-lane values (= 8 channels) by recursive halving;
@@ -389,6 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       }
       float px, py, pz, sdf_bar, nb0, nb1, nb2, zb0, zb1, zb2;
       float sc_adj = 1.f, sc_fwd = 1.f;   // fp16 slabs: power-of-two scales of the adjoint- / forward-type operands
+      float sc_adj_inv = 1.f;
       {
         const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
         px = pc.px;
@@ -405,6 +454,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         if (F16) {
           const int e_m = adj_exponent(q0, q1);
           sc_adj = pow2i(-e_m);
+          sc_adj_inv = pow2i(e_m);
           sc_fwd = pow2i(e_m - mode.e_ref);
         }
       }
@@ -449,6 +499,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         if (OI_BWD_STHINT >= 2) st_hint4(p, v, pol_last);
         else *p = v;
       };
+      // ---- what later stages re-read: pre-activations (ARG slabs) and the per-CTA g / c_bar slabs ----
+      constexpr bool kArg16 = OI_BWD_ARG16 != 0;
+      constexpr bool kG16 = F16 && (OI_BWD_G16 != 0);
+      // 16-bit layout of a slab: [oct 0..15][128 points] uint4 (32 KB, the first half of the slab's 64 KB)
+      uint4* arg16 = reinterpret_cast<uint4*>(slab_tile) + (size_t)(h * 8) * 128 + m;
+      uint4* cta16 = reinterpret_cast<uint4*>(scr4 - m) + (size_t)(h * 8) * 128 + m;
+      auto arg_st = [&](int l, int o, const float (&ar)[8]) {
+        if (kArg16) {
+          arg16[(size_t)l * (kSlabFloats / 4) + o * 128] = pack_phase8(ar);
+        } else {
+          st_arg(&OI_ARG(l, Q0 + 2 * o), make_float4(ar[0], ar[1], ar[2], ar[3]));
+          st_arg(&OI_ARG(l, Q0 + 2 * o + 1), make_float4(ar[4], ar[5], ar[6], ar[7]));
+        }
+      };
+      auto arg_ld = [&](int l, int o, float4& b0, float4& b1) {
+        if (kArg16) {
+          b0 = *reinterpret_cast<const float4*>(&arg16[(size_t)l * (kSlabFloats / 4) + o * 128]);
+        } else {
+          b0 = OI_ARG(l, Q0 + 2 * o);
+          b1 = OI_ARG(l, Q0 + 2 * o + 1);
+        }
+      };
+      auto arg_get = [&](const float4& b0, const float4& b1, float (&ar)[8]) {
+        if (kArg16) {
+          unpack_phase8(b0, ar);
+        } else {
+          ar[0] = b0.x; ar[1] = b0.y; ar[2] = b0.z; ar[3] = b0.w;
+          ar[4] = b1.x; ar[5] = b1.y; ar[6] = b1.z; ar[7] = b1.w;
+        }
+      };
+      // g (forward-type, stored as is) / c_bar (adjoint-type, scaled like the adjoint operands)
+      auto g_st = [&](int slab, int o, const float (&v)[8], bool adjoint) {
+        if (kG16) {
+          cta16[(size_t)slab * (kSlabFloats / 4) + o * 128] = pack_half8(v, adjoint ? sc_adj : 1.0f);
+        } else {
+          st_cta(&OI_CTA(slab, Q0 + 2 * o), make_float4(v[0], v[1], v[2], v[3]));
+          st_cta(&OI_CTA(slab, Q0 + 2 * o + 1), make_float4(v[4], v[5], v[6], v[7]));
+        }
+      };
+      auto g_ld = [&](int slab, int o, float4& b0, float4& b1) {
+        if (kG16) {
+          b0 = *reinterpret_cast<const float4*>(&cta16[(size_t)slab * (kSlabFloats / 4) + o * 128]);
+        } else {
+          b0 = OI_CTA(slab, Q0 + 2 * o);
+          b1 = OI_CTA(slab, Q0 + 2 * o + 1);
+        }
+      };
+      auto g_get = [&](const float4& b0, const float4& b1, float (&v)[8], bool adjoint) {
+        if (kG16) {
+          unpack_half8(b0, adjoint ? sc_adj_inv : 1.0f, v);
+        } else {
+          v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w;
+          v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+        }
+      };
+      // L2 prefetch of this warp's part of a 16-bit slab: 8 octs x 512 B = 32 lines, one per lane
+      auto pf16 = [&](const uint4* p_oct0) { l2_prefetch(p_oct0 - lane + (size_t)(lane >> 2) * 128 + (lane & 3) * 8); };
+      auto arg_pf = [&](int l, bool next) {
+        if (OI_BWD_L2PF != (next ? 2 : 1)) return;
+        if (kArg16) pf16(arg16 + (size_t)l * (kSlabFloats / 4));
+        else pf_raw(&OI_ARG(l, Q0));
+      };
+      auto g_pf = [&](int slab, bool next) {
+        if (OI_BWD_L2PF != (next ? 2 : 1)) return;
+        if (kG16) pf16(cta16 + (size_t)slab * (kSlabFloats / 4));
+        else pf_raw(&OI_CTA(slab, Q0));
+      };
       // the 8 values of an oct -> next A operand (TMEM), fp16 or bf16 two-term split
       auto a8_f16 = [&](int o, const float (&v)[8]) {
         uint32_t hi[4], lo[4];
@@ -483,8 +600,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             s[2 * i] = __sinf(arg.x);
             s[2 * i + 1] = __sinf(arg.y);
           }
-          st_arg(&OI_ARG(0, Q0 + 2 * o), make_float4(ar[0], ar[1], ar[2], ar[3]));
-          st_arg(&OI_ARG(0, Q0 + 2 * o + 1), make_float4(ar[4], ar[5], ar[6], ar[7]));
+          arg_st(0, o, ar);
           op8(kSlabH + 1, o, s, false);
           a8_f16(o, s);
         }, wait_acc, no_next);
@@ -506,8 +622,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             s[2 * i] = __sinf(arg.x);
             s[2 * i + 1] = __sinf(arg.y);
           }
-          st_arg(&OI_ARG(l, Q0 + 2 * o), make_float4(ar[0], ar[1], ar[2], ar[3]));
-          st_arg(&OI_ARG(l, Q0 + 2 * o + 1), make_float4(ar[4], ar[5], ar[6], ar[7]));
+          arg_st(l, o, ar);
           op8(kSlabH + l + 1, o, s, false);
           a8_f16(o, s);
         }, wait_acc, no_next);
@@ -516,16 +631,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // ---------------- colour features -> slot UC; t_{D-1} = w_sigma gamma cos(a_{D-1}) ----------------
       {
         const float4* fl = OI_FILM4(D - 1);
-        pf_slab(&OI_ARG(D - 1, Q0));
+        arg_pf(D - 1, false);
         run_stage<2, true, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
-          b[0] = OI_ARG(D - 1, Q0 + 2 * o);
-          b[1] = OI_ARG(D - 1, Q0 + 2 * o + 1);
+          arg_ld(D - 1, o, b[0], b[1]);
         }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[2]) {
           st_cta(&OI_CTA(kCtaUC, Q0 + 2 * o), make_float4(__uint_as_float(u[0]), __uint_as_float(u[1]), __uint_as_float(u[2]),
                                                    __uint_as_float(u[3])));
           st_cta(&OI_CTA(kCtaUC, Q0 + 2 * o + 1), make_float4(__uint_as_float(u[4]), __uint_as_float(u[5]),
                                                        __uint_as_float(u[6]), __uint_as_float(u[7])));
-          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          float ar[8];
+          arg_get(b[0], b[1], ar);
           float tv[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -537,7 +652,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           op8(kSlabT + D - 1, o, tv, false);
           a8_f16(o, tv);
-        }, wait_acc, [&]() { if (D >= 2) pf_nxt(&OI_ARG(D - 2, Q0)); });
+        }, wait_acc, [&]() { if (D >= 2) arg_pf(D - 2, true); });
         a_ready();
       }
       // ---------------- reverse sweep l = D-1 .. 1: g_l (slot G[l]), t_{l-1} (slab T[l-1]) ----------------
@@ -545,12 +660,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       for (int l = D - 1; l >= 1; --l) {
         const float4* fl = OI_FILM4(l - 1);
         const float gscale = (l - 1 == 0) ? kInvWScale : 1.0f;   // gamma'_0 is unscaled
-        pf_slab(&OI_ARG(l - 1, Q0));
+        arg_pf(l - 1, false);
         run_stage<2, true, OI_BWD_PF2>(acc, [&](int o, float4 (&b)[2]) {
-          b[0] = OI_ARG(l - 1, Q0 + 2 * o);
-          b[1] = OI_ARG(l - 1, Q0 + 2 * o + 1);
+          arg_ld(l - 1, o, b[0], b[1]);
         }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[2]) {
-          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          float ar[8];
+          arg_get(b[0], b[1], ar);
           float gv[8], tv[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -561,8 +676,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             tv[2 * i] = a0 * (f.x * gscale) * __cosf(ar[2 * i]);           // g_l gamma cos = t_{l-1}
             tv[2 * i + 1] = a1 * (f.y * gscale) * __cosf(ar[2 * i + 1]);
           }
-          st_cta(&OI_CTA(kCtaG + l - 1, Q0 + 2 * o), make_float4(gv[0], gv[1], gv[2], gv[3]));
-          st_cta(&OI_CTA(kCtaG + l - 1, Q0 + 2 * o + 1), make_float4(gv[4], gv[5], gv[6], gv[7]));
+          g_st(kCtaG + l - 1, o, gv, false);
           if (l > 1) {
             op8(kSlabT + l - 1, o, tv, false);
             a8_f16(o, tv);
@@ -575,7 +689,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
               gz = fmaf(w.z, tv[e], gz);
             }
           }
-        }, wait_acc, [&]() { if (l >= 2) pf_nxt(&OI_ARG(l - 2, Q0)); else pf_nxt(&OI_CTA(kCtaUC, Q0)); });
+        }, wait_acc, [&]() { if (l >= 2) arg_pf(l - 2, true); else pf_nxt(&OI_CTA(kCtaUC, Q0)); });
         if (l > 1) a_ready();
       }
       // ---------------- combine the two column halves: normal ----------------
@@ -642,7 +756,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             for (int i = 0; i < 8; ++i) tmp[i] = zb2 * sn[i];
             colsum8(tmp, a.g.rgb_weight + 2 * kW + nc, 1, lane);
           }
-        }, wait_acc, [&]() { pf_nxt(&OI_ARG(0, Q0)); pf_nxt(&OI_CTA(kCtaG + 0, Q0)); });
+        }, wait_acc, [&]() { arg_pf(0, true); g_pf(kCtaG + 0, true); });
       }
       // normal_bar = direct + W_cg^T u_bar_c (both halves)
       xch[h * 4 + 1] = nc0;
@@ -675,16 +789,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       //                  backward of the reverse sweep, l = 0 (K = 3): A <- g_bar_1 ----------------
       {
         const float4* fl = OI_FILM4(0);
-        pf_slab(&OI_ARG(0, Q0));
-        pf_slab(&OI_CTA(kCtaG + 0, Q0));
+        arg_pf(0, false);
+        g_pf(kCtaG + 0, false);
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
-          b[0] = OI_ARG(0, Q0 + 2 * o);
-          b[1] = OI_ARG(0, Q0 + 2 * o + 1);
-          b[2] = OI_CTA(kCtaG + 0, Q0 + 2 * o);       // g_1
-          b[3] = OI_CTA(kCtaG + 0, Q0 + 2 * o + 1);
+          arg_ld(0, o, b[0], b[1]);
+          g_ld(kCtaG + 0, o, b[2], b[3]);
         }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
-          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
-          const float g1[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+          float ar[8];
+          arg_get(b[0], b[1], ar);
+          float g1[8];
+          g_get(b[2], b[3], g1, false);
           float hb[8], cb[8], gb[8], t0[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -704,8 +818,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
           st_cta(&OI_CTA(kCtaHB, Q0 + 2 * o), make_float4(hb[0], hb[1], hb[2], hb[3]));
           st_cta(&OI_CTA(kCtaHB, Q0 + 2 * o + 1), make_float4(hb[4], hb[5], hb[6], hb[7]));
-          st_cta(&OI_CTA(kCtaG + 0, Q0 + 2 * o), make_float4(cb[0], cb[1], cb[2], cb[3]));   // c_bar_0
-          st_cta(&OI_CTA(kCtaG + 0, Q0 + 2 * o + 1), make_float4(cb[4], cb[5], cb[6], cb[7]));
+          g_st(kCtaG + 0, o, cb, true);
           op8(kSlabGB + 1, o, gb, true);
           a8_bf16(o, gb);
           if (o == 7) a_ready();
@@ -722,21 +835,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             for (int i = 0; i < 8; ++i) tmp[i] = nb2 * t0[i];
             colsum8(tmp, dst + 2, 3, lane);
           }
-        }, wait_acc, [&]() { if (1 < D - 1) { pf_nxt(&OI_ARG(1, Q0)); pf_nxt(&OI_CTA(kCtaG + 1, Q0)); } else { pf_nxt(&OI_ARG(D - 1, Q0)); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
+        }, wait_acc, [&]() { if (1 < D - 1) { arg_pf(1, true); g_pf(kCtaG + 1, true); } else { arg_pf(D - 1, true); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
       }
       // ---------------- backward of the reverse sweep, l = 1..D-2: t_bar_l = W_l g_bar_l ----------------
       for (int l = 1; l < D - 1; ++l) {
         const float4* fl = OI_FILM4(l);
-        pf_slab(&OI_ARG(l, Q0));
-        pf_slab(&OI_CTA(kCtaG + l, Q0));
+        arg_pf(l, false);
+        g_pf(kCtaG + l, false);
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
-          b[0] = OI_ARG(l, Q0 + 2 * o);
-          b[1] = OI_ARG(l, Q0 + 2 * o + 1);
-          b[2] = OI_CTA(kCtaG + l, Q0 + 2 * o);       // g_{l+1}
-          b[3] = OI_CTA(kCtaG + l, Q0 + 2 * o + 1);
+          arg_ld(l, o, b[0], b[1]);
+          g_ld(kCtaG + l, o, b[2], b[3]);
         }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
-          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
-          const float gn[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+          float ar[8];
+          arg_get(b[0], b[1], ar);
+          float gn[8];
+          g_get(b[2], b[3], gn, false);
           float cb[8], gb[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -748,26 +861,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             gb[2 * i] = tb0 * gam.x * __cosf(ar[2 * i]);                 // g_bar_{l+1}
             gb[2 * i + 1] = tb1 * gam.y * __cosf(ar[2 * i + 1]);
           }
-          st_cta(&OI_CTA(kCtaG + l, Q0 + 2 * o), make_float4(cb[0], cb[1], cb[2], cb[3]));
-          st_cta(&OI_CTA(kCtaG + l, Q0 + 2 * o + 1), make_float4(cb[4], cb[5], cb[6], cb[7]));
+          g_st(kCtaG + l, o, cb, true);
           op8(kSlabGB + l + 1, o, gb, true);
           a8_bf16(o, gb);
-        }, wait_acc, [&]() { if (l + 1 < D - 1) { pf_nxt(&OI_ARG(l + 1, Q0)); pf_nxt(&OI_CTA(kCtaG + l + 1, Q0)); } else { pf_nxt(&OI_ARG(D - 1, Q0)); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
+        }, wait_acc, [&]() { if (l + 1 < D - 1) { arg_pf(l + 1, true); g_pf(kCtaG + l + 1, true); } else { arg_pf(D - 1, true); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
         a_ready();
       }
       // ---------------- top, l = D-1: t_{D-1} = w_s c_{D-1}; then the backward of the forward sweep for layer D-1
       {
         const int l = D - 1;
         const float4* fl = OI_FILM4(l);
-        pf_slab(&OI_ARG(l, Q0));
+        arg_pf(l, false);
         pf_slab(&OI_CTA(kCtaHB, Q0));
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
-          b[0] = OI_ARG(l, Q0 + 2 * o);
-          b[1] = OI_ARG(l, Q0 + 2 * o + 1);
+          arg_ld(l, o, b[0], b[1]);
           b[2] = OI_CTA(kCtaHB, Q0 + 2 * o);          // h_bar_D
           b[3] = OI_CTA(kCtaHB, Q0 + 2 * o + 1);
         }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
-          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          float ar[8];
+          arg_get(b[0], b[1], ar);
           const float hb[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
           float ubv[8], dws[8];
 #pragma unroll
@@ -790,23 +902,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           a8_bf16(o, ubv);
           if (o == 7) a_ready();
           colsum8(dws, a.g.sigma_weight + n0 + o * 8, 1, lane);
-        }, wait_acc, [&]() { pf_nxt(&OI_ARG(D - 2, Q0)); pf_nxt(&OI_CTA(kCtaG + D - 2, Q0)); });
+        }, wait_acc, [&]() { arg_pf(D - 2, true); g_pf(kCtaG + D - 2, true); });
       }
       // ---------------- backward of the forward sweep: h_bar_l = W_l^T u_bar_l, then layer k = l-1 ----------------
       for (int l = D - 1; l >= 1; --l) {
         const int k = l - 1;
         const float4* fl = OI_FILM4(k);
         const float gsc = (k == 0) ? 1.0f : kWScale;
-        pf_slab(&OI_ARG(k, Q0));
-        pf_slab(&OI_CTA(kCtaG + k, Q0));
+        arg_pf(k, false);
+        g_pf(kCtaG + k, false);
         run_stage<4, true, OI_BWD_PF4>(acc, [&](int o, float4 (&b)[4]) {
-          b[0] = OI_ARG(k, Q0 + 2 * o);
-          b[1] = OI_ARG(k, Q0 + 2 * o + 1);
-          b[2] = OI_CTA(kCtaG + k, Q0 + 2 * o);       // c_bar_k
-          b[3] = OI_CTA(kCtaG + k, Q0 + 2 * o + 1);
+          arg_ld(k, o, b[0], b[1]);
+          g_ld(kCtaG + k, o, b[2], b[3]);
         }, [&](int o, const uint32_t (&u)[8], const float4 (&b)[4]) {
-          const float ar[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
-          const float cb[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+          float ar[8];
+          arg_get(b[0], b[1], ar);
+          float cb[8];
+          g_get(b[2], b[3], cb, true);
           float ubv[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -839,7 +951,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             for (int i = 0; i < 8; ++i) tmp[i] = pz * ubv[i];
             colsum8(tmp, dst + 2, 3, lane);
           }
-        }, wait_acc, [&]() { if (l >= 2) { pf_nxt(&OI_ARG(l - 2, Q0)); pf_nxt(&OI_CTA(kCtaG + l - 2, Q0)); } });
+        }, wait_acc, [&]() { if (l >= 2) { arg_pf(l - 2, true); g_pf(kCtaG + l - 2, true); } });
         if (k >= 1) a_ready();
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);   // film table / exchange buffer of this slot may be reused now
