@@ -171,11 +171,9 @@ __device__ __forceinline__ void st_hint4(float4* p, float4 v, uint64_t pol) {
 // Pre-activation a -> phase: a mod 2 pi in units of 2^-16 turn.  Later stages only take sin / cos of it, for gradient
 // terms: |error| <= 2 pi 2^-17 = 4.8e-5 rad, below the 2^-11 rounding of the tensor-core operands it feeds.
 __device__ __forceinline__ uint32_t phase16(float a) {
-  const float kMagic = 12582912.0f;                              // 1.5 * 2^23: integer part lands in the low mantissa bits
-  const float k = fmaf(a, 0.15915494309189535f, kMagic) - kMagic;   // round(a / 2 pi)
-  float r = fmaf(-k, 6.2831854820251465f, a);                    // Cody-Waite: 2 pi = hi + lo
-  r = fmaf(-k, -1.7484555314695172e-07f, r);                     // r in [-pi, pi]
-  return __float_as_uint(fmaf(r, 10430.378350470453f, kMagic));  // caller keeps the low 16 bits (two's complement)
+  // round(a * 65536 / 2 pi) as a 32-bit integer (saturating); the caller keeps its low 16 bits = the phase mod 2 pi.
+  // Exact to one unit while |a| < 1600 rad, where fp32 itself still resolves 2^-16 turn.
+  return (uint32_t)__float2int_rn(a * 10430.378350470453f);
 }
 __device__ __forceinline__ uint4 pack_phase8(const float (&a)[8]) {
   uint32_t w[4];
@@ -185,11 +183,11 @@ __device__ __forceinline__ uint4 pack_phase8(const float (&a)[8]) {
 }
 __device__ __forceinline__ void unpack_phase8(const float4& b, float (&a)[8]) {
   const uint32_t w[4] = {__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)};
-  const float kTwo23 = 8388608.0f, kStep = 9.587379924285257e-05f;   // 2 pi / 65536; angle in [0, 2 pi)
+  const float kStep = 9.587379924285257e-05f, kOff = -8388608.0f * 9.587379924285257e-05f;   // 2 pi / 65536
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    a[2 * i] = (__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7610)) - kTwo23) * kStep;
-    a[2 * i + 1] = (__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7632)) - kTwo23) * kStep;
+  for (int i = 0; i < 4; ++i) {   // (2^23 + n) * step - 2^23 * step, one rounding: angle in [0, 2 pi)
+    a[2 * i] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7610)), kStep, kOff);
+    a[2 * i + 1] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7632)), kStep, kOff);
   }
 }
 __device__ __forceinline__ uint4 pack_half8(const float (&v)[8], float sc) {
@@ -427,6 +425,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // this lane PAIR's 4 bytes (points m & ~1, m | 1) at ((m & 6) * 2); channel & 7 = the position e inside an oct
       unsigned char* gso16 = reinterpret_cast<unsigned char*>(slab_tile) + (m >> 6) * 16384 + n0 * 128 + (m & 6) * 2;
       const int mc16 = ((m & 63) >> 3) << 4;   // byte offset of the chunk before the XOR: (chunk ^ e) << 4 = mc16 ^ (e << 4)
+      const uint32_t pair_sel = (lane & 1) ? 0x3276u : 0x5410u;
+      int pair_off[4];   // row + chunk of channel e = 2i + (lane & 1) inside an oct
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = 2 * i + (lane & 1);
+        pair_off[i] = e * 128 + (mc16 ^ (e << 4));
+      }
       unsigned char* auxo16 = reinterpret_cast<unsigned char*>(a.aux + (size_t)lt * 512) + (m >> 6) * 512 + (m & 7) * 2;
       float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][unused | db][128]
       float* dw0 = a.dw0 + (size_t)inst * kW * 3;
@@ -470,17 +475,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           // lane channel 2i+1, and each stores ONE packed fp16x2 (4 stores per oct instead of 8)
           const float sc = adjoint ? sc_adj : sc_fwd;
           unsigned char* p = gso16 + slab16_offset(slab) + o * 1024;
-          const bool odd = (lane & 1) != 0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float mine = (odd ? v[2 * i + 1] : v[2 * i]) * sc;
-            const float send = (odd ? v[2 * i] : v[2 * i + 1]) * sc;
-            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
-            const float first = odd ? got : mine, second = odd ? mine : got;   // points m & ~1, m | 1
-            uint32_t pk;
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(second), "f"(first));
-            const int e = 2 * i + (odd ? 1 : 0);
-            *reinterpret_cast<uint32_t*>(p + e * 128 + (mc16 ^ (e << 4))) = pk;
+            uint32_t own;   // (channel 2i+1, channel 2i) of this lane's point
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(own) : "f"(v[2 * i + 1] * sc), "f"(v[2 * i] * sc));
+            const uint32_t nbr = __shfl_xor_sync(0xffffffffu, own, 1);
+            // even lane: channel 2i of points (m, m+1) = (own.lo, nbr.lo); odd lane: channel 2i+1 of (m-1, m) = (nbr.hi, own.hi)
+            const uint32_t pk = __byte_perm(own, nbr, pair_sel);
+            *reinterpret_cast<uint32_t*>(p + pair_off[i]) = pk;
           }
           return;
         }
