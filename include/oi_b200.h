@@ -448,6 +448,10 @@ int oi_augment_geom_workspace_bytes(const OiAugmentGeomDesc* desc, size_t* bytes
 int oi_augment_geom_forward(const OiAugmentGeomDesc* desc, void* stream);
 int oi_augment_geom_backward(const OiAugmentGeomDesc* desc, void* stream);
 
+/* Which operand format the LAST oi_render_backward on desc->workspace used for the weight-gradient contraction
+ * (see OiRenderBwdDesc.flags): *format = 0 TF32, 1 scaled fp16.  Diagnostic: synchronises `stream`. */
+int oi_render_backward_operand_format(const OiRenderBwdDesc* desc, int32_t* format, void* stream);
+
 /* Self-test of the tcgen05 building blocks: d[128,128] = a[128,128] * B^T through the split-fp16 UMMA path.
  * B = b[128,128] ([n][k] row-major) when packed_weights is NULL, else panel `panel` of the packed blob
  * (order: forward l=1..D-1, colour features, reverse l=D-1..1; each is 2^8 * W in [n][k] orientation). */

@@ -501,6 +501,23 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
                               reinterpret_cast<const unsigned int*>(ws + w.relax_count), w.chunk_tiles, w.n_ctas, st);
 }
 
+int oi_render_backward_operand_format(const OiRenderBwdDesc* d, int32_t* format, void* stream) {
+  int rc = validate_bwd(d);
+  if (rc) return rc;
+  OI_CHECK_ARG(format != nullptr && d->workspace != nullptr, "NULL pointer");
+  BwdWorkspace w;
+  plan_bwd(d, &w);
+  if (d->workspace_bytes < w.total)
+    return set_error(OI_ERR_WORKSPACE, "workspace too small: %zu < %zu", d->workspace_bytes, w.total);
+  unsigned int ctl[8];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  OI_CHECK_CUDA(cudaMemcpyAsync(ctl, static_cast<const char*>(d->workspace) + w.relax_count, sizeof(ctl),
+                                cudaMemcpyDeviceToHost, st));
+  OI_CHECK_CUDA(cudaStreamSynchronize(st));
+  *format = (w.tc && bwd_mode(ctl, d->flags).f16) ? 1 : 0;
+  return OI_OK;
+}
+
 int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,
                    float* d, void* stream) {
   OI_CHECK_ARG(a && d, "a and d must be non-NULL");

@@ -46,11 +46,11 @@ struct BwdMode {
   bool f16;
   int e_ref;
 };
-__device__ __forceinline__ BwdMode bwd_mode(const unsigned int* ctl, int flags) {
+__host__ __device__ __forceinline__ BwdMode bwd_mode(const unsigned int* ctl, int flags) {
   const unsigned int mb = ctl[1];
   const int ex = (int)((mb >> 23) & 0xFFu);
-  const unsigned long long tot = *reinterpret_cast<const unsigned long long*>(ctl + 2);
-  const unsigned long long low = *reinterpret_cast<const unsigned long long*>(ctl + 4);
+  const unsigned long long tot = (unsigned long long)ctl[2] | ((unsigned long long)ctl[3] << 32);
+  const unsigned long long low = (unsigned long long)ctl[4] | ((unsigned long long)ctl[5] << 32);
   BwdMode m;
   m.f16 = ex > 0 && ex < 255 && low <= (tot >> kF16MassShift);
   if (flags & OI_BWD_FLAG_FORCE_TF32) m.f16 = false;

@@ -245,6 +245,7 @@ class _RenderFunction(torch.autograd.Function):
                 r._bwd_workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             d.workspace, d.workspace_bytes = r._bwd_workspace.data_ptr(), r._bwd_workspace.numel()
             _lib.check(L.oi_render_backward(C.byref(d), _lib.current_stream_ptr(dev)), "oi_render_backward")
+        r._last_bwd_desc = d
         # slots 0..D-1 and OI_MAX_DEPTH (slices, not a list index: that would copy an index tensor host->device
         # and stall the host until the kernels above have finished)
         last = _lib.OI_MAX_DEPTH
@@ -326,6 +327,21 @@ class NeuSRenderer:
                                                with_style=False), self._mode_key())
 
     # -------------------------------------------------------------------------------------------
+    def last_backward_operand_format(self) -> str:
+        """'fp16' or 'tf32': the format the last tensor-core backward of this renderer chose for the per-point operands
+        of the weight-gradient contraction (OiRenderBwdDesc.flags; `self.flags |= 32` forces TF32, `|= 64` fp16).
+        Diagnostic: synchronises the stream."""
+        d = getattr(self, "_last_bwd_desc", None)
+        if d is None:
+            raise RuntimeError("no backward has run on this renderer yet")
+        fmt = C.c_int32(-1)
+        dev = self._bwd_workspace.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().oi_render_backward_operand_format(C.byref(d), C.byref(fmt),
+                                                                    _lib.current_stream_ptr(dev)),
+                       "oi_render_backward_operand_format")
+        return "fp16" if fmt.value == 1 else "tf32"
+
     def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0,
                siren_network=None, z=None, w=None, second_order=None, compute_color=True,
                compute_sample_dist=False, blend_background=False, *, t_rand=None, z_vals=None,

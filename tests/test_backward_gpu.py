@@ -56,9 +56,10 @@ def _reference_grads(meta, c, w, z_vals, adj, cos_anneal, dtype, m):
     return {k: (v.double() if v is not None else None) for k, v in zip([k for k, _ in named] + ["w"], g)}
 
 
-def _check(meta, c, w, adj_keys, cos_anneal, n_importance=0, t_rand=None, impl="auto", seed=0):
+def _check(meta, c, w, adj_keys, cos_anneal, n_importance=0, t_rand=None, impl="auto", seed=0, flags=0, expect=None):
     torch.manual_seed(seed)
     r = _build(meta, n_importance=n_importance, impl=impl)
+    r.flags |= flags
     wk = w.detach().clone().requires_grad_(True)
     out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=cos_anneal, perturb_overwrite=0,
                    w=wk, t_rand=t_rand, return_z_vals=True)
@@ -67,6 +68,8 @@ def _check(meta, c, w, adj_keys, cos_anneal, n_importance=0, t_rand=None, impl="
     named = _params(r)
     gk = torch.autograd.grad(_loss(out, adj), [t for _, t in named] + [wk], allow_unused=True)
     torch.cuda.synchronize()
+    if expect is not None:
+        assert r.last_backward_operand_format() == expect
     gk = dict(zip([k for k, _ in named] + ["w"], gk))
     z_vals = out["z_vals"].detach()
     g64 = _reference_grads(meta, c, w, z_vals, adj, cos_anneal, torch.float64, n_importance)
@@ -102,7 +105,8 @@ def test_all_adjoints_small(name, impl):
 
 
 def test_adjoint_scale_invariance_tcgen05():
-    """bf16-split adjoint sweeps: gradients of 1e-6 * loss are 1e-6 * gradients (no fp16-style range loss)."""
+    """bf16-split adjoint sweeps and per-point power-of-two scales of the fp16 operands: gradients of 1e-6 * loss are
+    1e-6 * gradients (no range loss)."""
     meta, c, w = _inputs("cfgd_n16_m4_D8", 64)
     r = _build(meta, n_importance=0, impl="tcgen05")
     named = _params(r)
@@ -114,6 +118,52 @@ def test_adjoint_scale_invariance_tcgen05():
     for (k, _), g1, g2 in zip(named, *grads):
         s = float(g1.abs().max()) + 1e-30
         assert float((g2 * 1e6 - g1).abs().max()) / s < 2e-3, k   # TF32 operand rounding differs between the two scales
+
+
+@pytest.mark.parametrize("flags,expect", [(32, "tf32"), (64, "fp16"), (0, "fp16")])
+def test_operand_formats_of_the_contraction(flags, expect):
+    """The per-point operands of the weight-gradient contraction as TF32 (flags bit 5) and as scaled fp16 (bit 6; what
+    the device-side rule picks for ordinary adjoints): both inside the tolerance of the fp64 reference gradients."""
+    meta, c, w = _inputs("cfgd_n16_m4_D8", 64)
+    _check(meta, c, w, ADJ_KEYS, 0.3, impl="tcgen05", flags=flags, expect=expect)
+    meta, c, w = _inputs("cfgd_n16_m4_D8", 50, n_inst=2)
+    _check(meta, c, w, ["color_fine", "weight_sum", "gradient_error", "weights", "gradients", "raw_color"], 1.0,
+           impl="tcgen05", flags=flags, expect=expect)
+
+
+def test_operand_format_follows_the_adjoint_statistics():
+    """fp16 operands need the adjoint mass to sit within 2^18 of the largest adjoint.  One point with an adjoint 2^20
+    above all others (which then carry 1e-3 of the mass, > 2^-12): the device-side rule keeps TF32, and the gradients
+    agree with the forced-TF32 run; ordinary adjoints: fp16."""
+    meta, c, w = _inputs("cfgd_n16_m4_D8", 64)
+    r = _build(meta, n_importance=0, impl="tcgen05")
+    with pytest.raises(RuntimeError):
+        r.last_backward_operand_format()
+    named = _params(r)
+
+    def grads(adj_sdf, flags):
+        r.flags = (r.flags & ~96) | flags
+        out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0, perturb_overwrite=0, w=w)
+        g = torch.autograd.grad((out["sdf"] * adj_sdf).sum(), [t for _, t in named], allow_unused=True)
+        return g, r.last_backward_operand_format()
+
+    ones = torch.ones(64, meta["n_samples"], device="cuda")
+    _, fmt = grads(ones, 0)
+    assert fmt == "fp16"
+    heavy = ones.clone()
+    heavy[3, 5] = 2.0 ** 20
+    g_auto, fmt = grads(heavy, 0)
+    assert fmt == "tf32"
+    g_tf32, fmt = grads(heavy, 32)
+    assert fmt == "tf32"
+    g_f16, fmt = grads(heavy, 64)
+    assert fmt == "fp16"
+    for (k, _), a, b, h in zip(named, g_auto, g_tf32, g_f16):
+        if a is None:
+            continue
+        s = float(b.abs().max()) + 1e-30
+        assert float((a - b).abs().max()) / s < 1e-5, k      # same kernels (atomics reorder the sums)
+        assert float((h - b).abs().max()) / s < 2e-3, k      # the forced fp16 path degrades gracefully here
 
 
 @pytest.mark.parametrize("impl", ["ffma", "tcgen05"])
