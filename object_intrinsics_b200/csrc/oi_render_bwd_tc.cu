@@ -426,11 +426,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       unsigned char* gso16 = reinterpret_cast<unsigned char*>(slab_tile) + (m >> 6) * 16384 + n0 * 128 + (m & 6) * 2;
       const int mc16 = ((m & 63) >> 3) << 4;   // byte offset of the chunk before the XOR: (chunk ^ e) << 4 = mc16 ^ (e << 4)
       const uint32_t pair_sel = (lane & 1) ? 0x3276u : 0x5410u;
-      int pair_off[4];   // row + chunk of channel e = 2i + (lane & 1) inside an oct
+      unsigned char* pair_ptr[4];   // + row and chunk of channel e = 2i + (lane & 1) inside an oct
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int e = 2 * i + (lane & 1);
-        pair_off[i] = e * 128 + (mc16 ^ (e << 4));
+        pair_ptr[i] = gso16 + e * 128 + (mc16 ^ (e << 4));
       }
       unsigned char* auxo16 = reinterpret_cast<unsigned char*>(a.aux + (size_t)lt * 512) + (m >> 6) * 512 + (m & 7) * 2;
       float* dfilm = a.d_film + (size_t)inst * kFilm * 2 * kW;   // [slot][unused | db][128]
@@ -441,8 +441,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         for (int i = sub; i < kFilm * kW; i += kEpiThreadsPerSlot) dst[i] = src[i];
       }
       float px, py, pz, sdf_bar, nb0, nb1, nb2, zb0, zb1, zb2;
-      float sc_adj = 1.f, sc_fwd = 1.f;   // fp16 slabs: power-of-two scales of the adjoint- / forward-type operands
-      float sc_adj_inv = 1.f;
+      // fp16 slabs: the point's upstream adjoints are scaled by sc_adj = 2^-e_m right here, so that EVERY adjoint of the
+      // sweep carries the scale (exact: a power of two; the bf16-split MMA operands have fp32's exponent range) and the
+      // adjoint-type operands / c_bar need no multiply; sums over points taken on the FMA pipe un-scale first
+      // (sc_adj_inv, the un-scaled z_bar / normal_bar below).  Forward-type operands are multiplied by sc_fwd.
+      float sc_fwd = 1.f, sc_adj_inv = 1.f;
+      float zu0, zu1, zu2;   // un-scaled z_bar
       {
         const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
         px = pc.px;
@@ -458,9 +462,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         zb0 = q1.x; zb1 = q1.y; zb2 = q1.z;
         if (F16) {
           const int e_m = adj_exponent(q0, q1);
-          sc_adj = pow2i(-e_m);
+          const float sc_adj = pow2i(-e_m);
           sc_adj_inv = pow2i(e_m);
           sc_fwd = pow2i(e_m - mode.e_ref);
+          zu0 = zb0; zu1 = zb1; zu2 = zb2;
+          sdf_bar *= sc_adj; nb0 *= sc_adj; nb1 *= sc_adj; nb2 *= sc_adj;
+          zb0 *= sc_adj; zb1 *= sc_adj; zb2 *= sc_adj;
+        } else {
+          zu0 = zb0; zu1 = zb1; zu2 = zb2;
         }
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
@@ -473,8 +482,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         if (F16) {
           // lanes 2j / 2j+1 swap one value per channel pair: the even lane then holds channel 2i of both points, the odd
           // lane channel 2i+1, and each stores ONE packed fp16x2 (4 stores per oct instead of 8)
-          const float sc = adjoint ? sc_adj : sc_fwd;
-          unsigned char* p = gso16 + slab16_offset(slab) + o * 1024;
+          const float sc = adjoint ? 1.0f : sc_fwd;
+          const uint32_t uoff = (uint32_t)slab16_offset(slab) + (uint32_t)o * 1024u;   // warp-uniform part of the address
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t own;   // (channel 2i+1, channel 2i) of this lane's point
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             const uint32_t nbr = __shfl_xor_sync(0xffffffffu, own, 1);
             // even lane: channel 2i of points (m, m+1) = (own.lo, nbr.lo); odd lane: channel 2i+1 of (m-1, m) = (nbr.hi, own.hi)
             const uint32_t pk = __byte_perm(own, nbr, pair_sel);
-            *reinterpret_cast<uint32_t*>(p + pair_off[i]) = pk;
+            *reinterpret_cast<uint32_t*>(pair_ptr[i] + uoff) = pk;
           }
           return;
         }
@@ -534,7 +543,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // g (forward-type, stored as is) / c_bar (adjoint-type, scaled like the adjoint operands)
       auto g_st = [&](int slab, int o, const float (&v)[8], bool adjoint) {
         if (kG16) {
-          cta16[(size_t)slab * (kSlabFloats / 4) + o * 128] = pack_half8(v, adjoint ? sc_adj : 1.0f);
+          cta16[(size_t)slab * (kSlabFloats / 4) + o * 128] = pack_half8(v, 1.0f);   // c_bar carries the adjoint scale already
         } else {
           st_cta(&OI_CTA(slab, Q0 + 2 * o), make_float4(v[0], v[1], v[2], v[3]));
           st_cta(&OI_CTA(slab, Q0 + 2 * o + 1), make_float4(v[4], v[5], v[6], v[7]));
@@ -550,7 +559,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       };
       auto g_get = [&](const float4& b0, const float4& b1, float (&v)[8], bool adjoint) {
         if (kG16) {
-          unpack_half8(b0, adjoint ? sc_adj_inv : 1.0f, v);
+          unpack_half8(b0, 1.0f, v);
         } else {
           v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w;
           v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
@@ -749,13 +758,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             float tmp[8];
             const int nc = n0 + o * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tmp[i] = zb0 * sn[i];
+            for (int i = 0; i < 8; ++i) tmp[i] = zu0 * sn[i];
             colsum8(tmp, a.g.rgb_weight + 0 * kW + nc, 1, lane);                       // dW_rgb = z_bar (x) h_c
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tmp[i] = zb1 * sn[i];
+            for (int i = 0; i < 8; ++i) tmp[i] = zu1 * sn[i];
             colsum8(tmp, a.g.rgb_weight + 1 * kW + nc, 1, lane);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tmp[i] = zb2 * sn[i];
+            for (int i = 0; i < 8; ++i) tmp[i] = zu2 * sn[i];
             colsum8(tmp, a.g.rgb_weight + 2 * kW + nc, 1, lane);
           }
         }, wait_acc, [&]() { arg_pf(0, true); g_pf(kCtaG + 0, true); });
@@ -771,6 +780,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         nb1 += nc1 + xch[o + 2];
         nb2 += nc2 + xch[o + 3];
       }
+      const float nu0 = F16 ? nb0 * sc_adj_inv : nb0, nu1 = F16 ? nb1 * sc_adj_inv : nb1,
+                  nu2 = F16 ? nb2 * sc_adj_inv : nb2;   // un-scaled normal_bar
       if (h == 0) {
         if (F16) {   // rows of 128 B = 64 points, chunk XOR row
           const float av[4] = {gx * sc_fwd, gy * sc_fwd, gz * sc_fwd, sc_fwd};
@@ -828,13 +839,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             float* dst = dw0 + (size_t)(n0 + o * 8) * 3;
             float tmp[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tmp[i] = nb0 * t0[i];
+            for (int i = 0; i < 8; ++i) tmp[i] = nu0 * t0[i];
             colsum8(tmp, dst + 0, 3, lane);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tmp[i] = nb1 * t0[i];
+            for (int i = 0; i < 8; ++i) tmp[i] = nu1 * t0[i];
             colsum8(tmp, dst + 1, 3, lane);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tmp[i] = nb2 * t0[i];
+            for (int i = 0; i < 8; ++i) tmp[i] = nu2 * t0[i];
             colsum8(tmp, dst + 2, 3, lane);
           }
         }, wait_acc, [&]() { if (1 < D - 1) { arg_pf(1, true); g_pf(kCtaG + 1, true); } else { arg_pf(D - 1, true); pf_nxt(&OI_CTA(kCtaHB, Q0)); } });
@@ -903,6 +914,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           op8(kSlabUB + l, o, ubv, true);
           a8_bf16(o, ubv);
           if (o == 7) a_ready();
+          if (F16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dws[i] *= sc_adj_inv;
+          }
           colsum8(dws, a.g.sigma_weight + n0 + o * 8, 1, lane);
         }, wait_acc, [&]() { arg_pf(D - 2, true); g_pf(kCtaG + D - 2, true); });
       }
@@ -940,6 +955,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             a8_bf16(o, ubv);
           } else {
             const int nc = n0 + o * 8;
+            if (F16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ubv[i] *= sc_adj_inv;
+            }
             colsum8(ubv, dfilm + kW + nc, 1, lane);                  // d b_0 = sum u_bar_0
             float* dst = dw0 + (size_t)nc * 3;                       // dW_0 += u_bar_0 (x) x (per instance)
             float tmp[8];
