@@ -49,6 +49,9 @@
 #ifndef OI_BWD_G16
 #define OI_BWD_G16 1     // with fp16 operand slabs: the per-CTA g / c_bar slabs as fp16 too
 #endif
+#ifndef OI_BWD_EPI_REGS
+#define OI_BWD_EPI_REGS 112   // registers of the epilogue warps after setmaxnreg (16 x this + 4 x 32 <= 2048)
+#endif
 #ifndef OI_BWD_OCT_UNROLL
 #define OI_BWD_OCT_UNROLL 4   // octs per unrolled group of a stage's oct loop (2, 4 or 8)
 #endif
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OI_BWD_EPI_REGS));
     // ===================== epilogue warps =====================
     const int t = warp >> 3;
     const int h = (warp >> 2) & 1;
