@@ -580,7 +580,7 @@ def grad_step_leg(renderer, sdf, col, devn, resident, r1, flush):
     free_ms = (b_.elapsed_time(c_) - a_.elapsed_time(b_)) / n_free
     return {"ms": gs[len(gs) // 2], "ms_free_running": free_ms, "rays": r1, "bwd_kernels_ms": ks[len(ks) // 2],
             "what": "grad-mode render of 1 instance: forward + loss + oi_render_backward (sweep kernel on tcgen05 "
-                    "+ TMA-fed TF32 point-contraction), gradients on every nn.Parameter; `ms` = median of steps "
+                    "+ TMA-fed point-contraction on fp16 / TF32 operands), gradients on every nn.Parameter; `ms` = median of steps "
                     "synchronised one by one (the host's enqueue time is exposed), `ms_free_running` = 10 steps "
                     "back to back as a training loop issues them (L2 flushed between steps, flush time subtracted)"}
 

@@ -36,8 +36,8 @@ for r in rows[1:]:
 tot = sum(v[0] for v in agg.values())
 with open(os.path.join(P, "r02_train_step_launches.txt"), "w") as f:
     f.write("ncu --metrics gpu__time_duration.sum --clock-control none python tools_train_step.py --shape cfg5 --steps 1\n"
-            "(3 warm-up steps + 1 measured step = 4 training-shaped steps, bs=4 x 64x64 x 64; cold-cache, serialised: "
-            "compare shares)\n")
+            "(3 warm-up + 1 synchronised + 1 free-running step = 5 training-shaped steps, bs=4 x 64x64 x 64; cold-cache, "
+            "serialised: compare shares)\n")
     f.write(f"total {tot / 1e3:.2f} ms in {sum(v[1] for v in agg.values())} launches\n\n share   us/launch  launches  kernel\n")
     for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:50]:
         f.write(f"{100 * us / tot:6.2f}  {us / n:10.1f}  {n:8d}  {name}\n")
