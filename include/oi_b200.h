@@ -451,6 +451,12 @@ int oi_augment_geom_backward(const OiAugmentGeomDesc* desc, void* stream);
 /* Which operand format the LAST oi_render_backward on desc->workspace used for the weight-gradient contraction
  * (see OiRenderBwdDesc.flags): *format = 0 TF32, 1 scaled fp16.  Diagnostic: synchronises `stream`. */
 int oi_render_backward_operand_format(const OiRenderBwdDesc* desc, int32_t* format, void* stream);
+/* The 8 control words the last oi_render_backward on desc->workspace left behind (diagnostic, synchronises `stream`):
+ * [0] points inside the relaxed sphere (gradient_error), [1] float bits of the largest |adjoint component|,
+ * [2,3] u64 adjoint mass of all points / [4,5] of the points more than 2^18 below the maximum (2^-20 fixed point,
+ * relative to the maximum's binade; zero when the format is forced), [6,7] float bits of the largest forward-type /
+ * adjoint-type fp16 operand written (builds with -DOI_BWD_RANGE_STATS=1 only, else 0). */
+int oi_render_backward_control_words(const OiRenderBwdDesc* desc, uint32_t* words, void* stream);
 
 /* Self-test of the tcgen05 building blocks: d[128,128] = a[128,128] * B^T through the split-fp16 UMMA path.
  * B = b[128,128] ([n][k] row-major) when packed_weights is NULL, else panel `panel` of the packed blob

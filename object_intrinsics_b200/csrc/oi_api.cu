@@ -501,20 +501,27 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
                               reinterpret_cast<const unsigned int*>(ws + w.relax_count), w.chunk_tiles, w.n_ctas, st);
 }
 
-int oi_render_backward_operand_format(const OiRenderBwdDesc* d, int32_t* format, void* stream) {
+int oi_render_backward_control_words(const OiRenderBwdDesc* d, uint32_t* words, void* stream) {
   int rc = validate_bwd(d);
   if (rc) return rc;
-  OI_CHECK_ARG(format != nullptr && d->workspace != nullptr, "NULL pointer");
+  OI_CHECK_ARG(words != nullptr && d->workspace != nullptr, "NULL pointer");
   BwdWorkspace w;
   plan_bwd(d, &w);
   if (d->workspace_bytes < w.total)
     return set_error(OI_ERR_WORKSPACE, "workspace too small: %zu < %zu", d->workspace_bytes, w.total);
-  unsigned int ctl[8];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  OI_CHECK_CUDA(cudaMemcpyAsync(ctl, static_cast<const char*>(d->workspace) + w.relax_count, sizeof(ctl),
+  OI_CHECK_CUDA(cudaMemcpyAsync(words, static_cast<const char*>(d->workspace) + w.relax_count, 8 * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, st));
   OI_CHECK_CUDA(cudaStreamSynchronize(st));
-  *format = (w.tc && bwd_mode(ctl, d->flags).f16) ? 1 : 0;
+  return OI_OK;
+}
+
+int oi_render_backward_operand_format(const OiRenderBwdDesc* d, int32_t* format, void* stream) {
+  OI_CHECK_ARG(format != nullptr, "NULL pointer");
+  unsigned int ctl[8];
+  int rc = oi_render_backward_control_words(d, ctl, stream);
+  if (rc) return rc;
+  *format = (d->impl != OI_IMPL_FFMA && bwd_mode(ctl, d->flags).f16) ? 1 : 0;
   return OI_OK;
 }
 

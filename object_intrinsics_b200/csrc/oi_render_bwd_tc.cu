@@ -52,6 +52,9 @@
 #ifndef OI_BWD_EPI_REGS
 #define OI_BWD_EPI_REGS 112   // registers of the epilogue warps after setmaxnreg (16 x this + 4 x 32 <= 2048)
 #endif
+#ifndef OI_BWD_RANGE_STATS
+#define OI_BWD_RANGE_STATS 0   // diagnostic build: max |fp16 operand| (forward- / adjoint-type) into ctl[6] / ctl[7]
+#endif
 #ifndef OI_BWD_OCT_UNROLL
 #define OI_BWD_OCT_UNROLL 4   // octs per unrolled group of a stage's oct loop (2, 4 or 8)
 #endif
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       // (sc_adj_inv, the un-scaled z_bar / normal_bar below).  Forward-type operands are multiplied by sc_fwd.
       float sc_fwd = 1.f, sc_adj_inv = 1.f;
       float zu0, zu1, zu2;   // un-scaled z_bar
+      float rs_fwd = 0.f, rs_adj = 0.f;
       {
         const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
         px = pc.px;
@@ -486,6 +490,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           // lanes 2j / 2j+1 swap one value per channel pair: the even lane then holds channel 2i of both points, the odd
           // lane channel 2i+1, and each stores ONE packed fp16x2 (4 stores per oct instead of 8)
           const float sc = adjoint ? 1.0f : sc_fwd;
+          if (OI_BWD_RANGE_STATS) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (adjoint) rs_adj = fmaxf(rs_adj, fabsf(v[e]));
+              else rs_fwd = fmaxf(rs_fwd, fabsf(v[e] * sc));
+            }
+          }
           const uint32_t uoff = (uint32_t)slab16_offset(slab) + (uint32_t)o * 1024u;   // warp-uniform part of the address
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -977,6 +988,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           }
         }, wait_acc, [&]() { if (l >= 2) { arg_pf(l - 2, true); g_pf(kCtaG + l - 2, true); } });
         if (k >= 1) a_ready();
+      }
+      if (OI_BWD_RANGE_STATS) {
+        atomicMax(const_cast<unsigned int*>(a.ctl) + 6, __float_as_uint(rs_fwd));
+        atomicMax(const_cast<unsigned int*>(a.ctl) + 7, __float_as_uint(rs_adj));
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);   // film table / exchange buffer of this slot may be reused now
     }

@@ -342,6 +342,18 @@ class NeuSRenderer:
                        "oi_render_backward_operand_format")
         return "fp16" if fmt.value == 1 else "tf32"
 
+    def last_backward_control_words(self):
+        """The 8 control words of the last backward (oi_render_backward_control_words): diagnostic, synchronises."""
+        d = getattr(self, "_last_bwd_desc", None)
+        if d is None:
+            raise RuntimeError("no backward has run on this renderer yet")
+        words = (C.c_uint32 * 8)()
+        dev = self._bwd_workspace.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().oi_render_backward_control_words(C.byref(d), words, _lib.current_stream_ptr(dev)),
+                       "oi_render_backward_control_words")
+        return list(words)
+
     def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0,
                siren_network=None, z=None, w=None, second_order=None, compute_color=True,
                compute_sample_dist=False, blend_background=False, *, t_rand=None, z_vals=None,
