@@ -469,8 +469,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         zb0 = q1.x; zb1 = q1.y; zb2 = q1.z;
         if (F16) {
           const int e_m = adj_exponent(q0, q1);
-          const float sc_adj = pow2i(-e_m);
-          sc_adj_inv = pow2i(e_m);
+          const float sc_adj = pow2i(-e_m - kF16AdjShift);
+          sc_adj_inv = pow2i(e_m + kF16AdjShift);
           sc_fwd = pow2i(e_m - mode.e_ref);
           zu0 = zb0; zu1 = zb1; zu2 = zb2;
           sdf_bar *= sc_adj; nb0 *= sc_adj; nb1 *= sc_adj; nb2 *= sc_adj;

@@ -25,9 +25,9 @@ constexpr int kSlabFloats = 128 * 128;
 //      fp32; slab s >= kSlabOperand0 lives at 8 * 64 KB + (s - 8) * 32 KB inside the tile's (unchanged) region.
 //      fp16 has TF32's 10 mantissa bits but 5 exponent bits, so every operand is scaled by an exact power of two:
 //        adjoint-type operands (UB, GB, UBC)   x 2^-e_m              e_m = exponent of max |adj[m][0..6]| of the point
-//        forward-type operands (H, T, aux)     x 2^(e_m - e_ref)     e_ref = (exponent of the global max |adj|) - 10
+//        forward-type operands (H, T, aux)     x 2^(e_m - e_ref)     e_ref = (exponent of the global max |adj|) - 8
 //      => every product carries 2^-e_ref, undone when the contraction kernel flushes its accumulators.  The adjoint
-//      operands are then bounded by the network's Jacobians alone, the forward operands by 2^10 |value|; points whose
+//      operands are then bounded by the network's Jacobians alone, the forward operands by 2^8 |value|; points whose
 //      adjoint is more than 2^18 below the global maximum lose precision gradually.  bwd_mode() (below) selects the
 //      path per call ON THE DEVICE from the adjoint statistics adj_stats_kernel leaves in the control block: fp16 when
 //      those points carry < 2^-12 of the total adjoint mass, TF32 otherwise; both kernel variants are launched and the
@@ -38,7 +38,13 @@ __host__ __device__ constexpr size_t slab16_offset(int s) {
   return s < kSlabOperand0 ? (size_t)s * kSlabBytes : (size_t)kSlabOperand0 * kSlabBytes + (size_t)(s - kSlabOperand0) * kSlab16Bytes;
 }
 constexpr int OI_BWD_FLAG_FORCE_TF32 = 32, OI_BWD_FLAG_FORCE_F16 = 64;
-constexpr int kF16RefShift = 10, kF16LowShift = 18, kF16MassShift = 12;
+// placement inside fp16's range (measured with -DOI_BWD_RANGE_STATS=1, tools_bwd_range.py: at shifts 10 / 0 the largest
+// forward-type operand was 1 000 - 5 200 and the largest adjoint-type operand 180 - 2 000 over the bench networks, a
+// random initialisation and two losses): forward-type x 2^(e_m - e_max + kF16RefShift), adjoint-type x 2^(-e_m -
+// kF16AdjShift); the contraction kernel multiplies its result by 2^(e_max - kF16RefShift + kF16AdjShift).  The adjoint
+// side is tight at its LOW end (small Jacobians from the colour adjoint to the SDF layers put entries near fp16's
+// subnormals: with kF16AdjShift = 2 a single-ray loss lost 2.5x in accuracy), so it stays 0 (headroom 32x - 350x).
+constexpr int kF16RefShift = 8, kF16AdjShift = 0, kF16LowShift = 18, kF16MassShift = 12;
 
 // control block of one backward call (32-bit words, zeroed by launch_bwd_tail):
 //   [0] relax count   [1] bits of max |adj|   [2,3] u64 total adjoint mass   [4,5] u64 mass of the low points

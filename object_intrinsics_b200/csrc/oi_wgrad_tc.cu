@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
   if (a.ctl != nullptr) {
     const BwdMode mode = bwd_mode(a.ctl, a.flags);
     if (mode.f16 != F16) return;   // the other variant of this launch pair does the work
-    if (F16) out_scale = pow2i(mode.e_ref);
+    if (F16) out_scale = pow2i(mode.e_ref + kF16AdjShift);
   } else if (F16) {
     return;
   }
