@@ -11,11 +11,19 @@
 // Contractions over POINTS (weight gradients, bias sums) are not done here: every per-point operand they need is left
 // as a slab per tile (oi_wgrad.cuh) and contracted by wgrad_tc_kernel.
 //
+// What the sweep leaves in memory is 16 bits wide (it was HBM-bound on fp32 / TF32 slabs):
+//   * contraction operands as fp16 in the UMMA image, with exact power-of-two scales: the point's upstream adjoints are
+//     multiplied by 2^-e_m when the tile starts (so every adjoint of the sweep carries the scale), forward-type
+//     operands by 2^(e_m - e_ref); template parameter F16, selected per call on the device (bwd_mode, oi_wgrad.cuh),
+//     F16 = false keeps the TF32 slabs;
+//   * pre-activations as 16-bit phases (a mod 2 pi; later stages only take sin / cos of them), OI_BWD_ARG16;
+//   * g_l / c_bar_l as fp16 with F16, OI_BWD_G16.
+//
 // Round-2 structure of the epilogues:
 //   * every stage walks its 64 channels in eight OCTS of 8 columns: tcgen05.ld.x8 (double-buffered), the two
-//     scratch float4 pairs it re-reads (pre-activations a_l, g_{l+1} / c_bar_l) prefetched TWO octs ahead -- the
-//     first two octs before the wait on the accumulator barrier, so that the L2 / DRAM latency of the re-reads sits
-//     under the MMA -- and no per-stage arrays that outlive an oct (no spills);
+//     scratch words it re-reads (pre-activations a_l, g_{l+1} / c_bar_l) loaded one oct ahead -- the first before the
+//     wait on the accumulator barrier, after an L2 prefetch of the whole stage's re-reads -- and no per-stage arrays
+//     that outlive an oct; the oct loop is unrolled in groups of 4 (fully unrolled: instruction-fetch stalls);
 //   * dL/dgamma needs NO per-point column sums: with a = gamma u + beta, u = W h + b,
 //         sum_m a_bar u + c_bar cos a = (1/gamma) [ sum_k W[j][k] dW[j][k] + b[j] db[j] ]
 //     (dW = both parts of the layer's weight gradient, per instance; db = sum_m u_bar), because
