@@ -159,6 +159,48 @@ def film_tables(sdf_network, color_network, w):
     return gam, bet
 
 
+class _FilmGraph(torch.autograd.Function):
+    """The autograd edge of `film_tables` without its forward arithmetic: the CUDA kernels compute their own FiLM tables
+    from the packed blob and `w`, so the forward only hands out two uninitialised [bs, L, 128] place-holders (no
+    launch); the backward turns dL/dgamma, dL/dbeta (written by oi_render_backward) into the gradients of the L FiLM
+    linears and of `w` with two batched products instead of the ~25 nodes of the einsum / stack graph:
+        gamma = 15 (Wg w + bg) + 30,  beta = 0.25 (Wb w + bb)          (volume_renderer.py:27-30,47-48,56-57)."""
+
+    @staticmethod
+    def forward(ctx, w, *flat):
+        L = len(flat) // 4
+        ctx.L = L
+        ctx.save_for_backward(w, *flat[:L], *flat[2 * L:3 * L])          # w, gamma weights, beta weights
+        gam = torch.empty(w.shape[0], L, flat[0].shape[0], device=w.device, dtype=torch.float32)
+        return gam, torch.empty_like(gam)
+
+    @staticmethod
+    def backward(ctx, g_gam, g_bet):
+        L = ctx.L
+        w, Ws = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        if g_gam is None and g_bet is None:
+            return (None,) * (1 + 4 * L)
+        zeros = lambda: torch.zeros(w.shape[0], L, Ws[0].shape[0], device=w.device, dtype=torch.float32)
+        G = torch.cat([15.0 * (g_gam if g_gam is not None else zeros()),
+                       0.25 * (g_bet if g_bet is not None else zeros())], 1)           # [bs, 2L, 128]
+        wf = w.detach().to(torch.float32)
+        dW = torch.einsum("bln,bk->lnk", G, wf)                                          # [2L, 128, 64]
+        db = G.sum(0)                                                                    # [2L, 128]
+        dw = None
+        if ctx.needs_input_grad[0]:
+            dw = torch.einsum("bln,lnk->bk", G, torch.stack([t.detach() for t in Ws])).to(w.dtype)
+        return (dw, *dW[:L].unbind(0), *db[:L].unbind(0), *dW[L:].unbind(0), *db[L:].unbind(0))
+
+
+def film_graph(sdf_network, color_network, w):
+    """gamma / beta place-holders [bs, L, 128] carrying the autograd edges to the FiLM linears and to `w` (_FilmGraph);
+    `film_tables` is the plain-torch statement of the same map (tests compare the two)."""
+    mods = _film_modules(sdf_network, color_network)
+    flat = [m.gamma.weight for m in mods] + [m.gamma.bias for m in mods] + \
+           [m.beta.weight for m in mods] + [m.beta.bias for m in mods]
+    return _FilmGraph.apply(w, *flat)
+
+
 class _RenderFunction(torch.autograd.Function):
     """Forward = the fused CUDA render; backward = oi_render_backward.  Differentiable inputs: the FiLM tables
     (depth+1 slots) and the tensors of `_direct_params`."""
@@ -394,7 +436,7 @@ class NeuSRenderer:
                 raise NotImplementedError("gradients w.r.t. rays / near / far / z_vals are not produced by the CUDA "
                                           "backward (the training path samples poses); build the renderer with "
                                           "grad_impl='torch' for that")
-            gam, bet = film_tables(self.sdf_network, self.color_network, w)
+            gam, bet = film_graph(self.sdf_network, self.color_network, w)
             geo = (params, rays_o, rays_d, near, far, w, float(cos_anneal_ratio), t_rand, z_vals)
             res = _RenderFunction.apply(self, geo, gam, bet, *_direct_params(self.sdf_network, self.color_network,
                                                                              self.deviation_network))

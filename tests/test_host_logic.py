@@ -219,3 +219,27 @@ def test_augment_pipe_state_dict_matches_reference_checkpoints():
     pipe.load_state_dict(ref_sd, strict=True)
     assert float(pipe.p) == pytest.approx(0.37)
     AugmentPipe().load_state_dict(pipe.state_dict(), strict=True)
+
+
+def test_film_graph_edge_matches_the_torch_formulation():
+    """renderer._FilmGraph (place-holder forward, hand-written backward of gamma = 15 (Wg w + bg) + 30,
+    beta = 0.25 (Wb w + bb)) routes the same gradients to the FiLM linears and to w as autograd through film_tables."""
+    import torch
+    from object_intrinsics_b200 import fields
+    from object_intrinsics_b200.renderer import film_graph, film_tables
+    torch.manual_seed(0)
+    sdf, col, _ = fields.build_networks(D=4, device="cpu")
+    w = torch.randn(3, 64, requires_grad=True)
+    gam, bet = film_tables(sdf, col, w)
+    gg, gb = torch.randn_like(gam), torch.randn_like(bet)
+    params = [p for m in list(sdf.pts_linears) + [col.views_linears]
+              for p in (m.gamma.weight, m.gamma.bias, m.beta.weight, m.beta.bias)]
+    ref = torch.autograd.grad((gam * gg).sum() + (bet * gb).sum(), [w] + params)
+    g2, b2 = film_graph(sdf, col, w)
+    assert g2.shape == gam.shape and b2.shape == bet.shape
+    got = torch.autograd.grad([g2, b2], [w] + params, [gg, gb])
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max()) <= 1e-5 * (float(b.abs().max()) + 1e-30)
+    # w without grad: no gradient is formed for it
+    g3, _ = film_graph(sdf, col, w.detach())
+    assert torch.autograd.grad([g3], params[:1], [gg])[0] is not None
