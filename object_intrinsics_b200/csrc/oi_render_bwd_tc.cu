@@ -1147,14 +1147,11 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     const int ctas = render_bwd_tc_ctas(t1 - t0) < n_ctas ? render_bwd_tc_ctas(t1 - t0) : n_ctas;
     a.ctl = ctl;
     // both operand formats are launched; bwd_mode() (adjoint statistics, on the device) lets one of them exit at once
-    if (!(geo.flags & OI_BWD_FLAG_FORCE_F16)) {
-      bwd_tc_kernel<false><<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
-      OI_CHECK_CUDA(cudaGetLastError());
-    }
-    if (!(geo.flags & OI_BWD_FLAG_FORCE_TF32)) {
-      bwd_tc_kernel<true><<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
-      OI_CHECK_CUDA(cudaGetLastError());
-    }
+    // (also with a forced format: bwd_mode() overrides a forced fp16 when the adjoints are not finite)
+    bwd_tc_kernel<false><<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
+    bwd_tc_kernel<true><<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
+    OI_CHECK_CUDA(cudaGetLastError());
 
     // ---- contraction over the points of this chunk (per-instance outputs: the finalize kernel needs them)
     WgArgs w;

@@ -260,7 +260,7 @@ int launch_wgrad_tc(const WgArgs& a_in, cudaStream_t st) {
                                      (int)sizeof(WgSmem)));
   wgrad_tc_kernel<false><<<cta, kWgThreads, sizeof(WgSmem), st>>>(a);
   OI_CHECK_CUDA(cudaGetLastError());
-  if (a.ctl != nullptr && !(a.flags & OI_BWD_FLAG_FORCE_TF32)) {   // the fp16-slab variant; one of the two exits at once
+  if (a.ctl != nullptr) {   // the fp16-slab variant; one of the two exits at once
     OI_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(WgSmem)));
     wgrad_tc_kernel<true><<<cta, kWgThreads, sizeof(WgSmem), st>>>(a);

@@ -166,6 +166,24 @@ def test_operand_format_follows_the_adjoint_statistics():
         assert float((h - b).abs().max()) / s < 2e-3, k      # the forced fp16 path degrades gracefully here
 
 
+@pytest.mark.parametrize("flags", [0, 64])
+@pytest.mark.parametrize("bad", [float("inf"), float("nan")])
+def test_non_finite_adjoints_propagate(flags, bad):
+    """An inf / NaN upstream adjoint must surface as non-finite gradients (not as silently clamped or skipped work), also
+    with the fp16 operand format forced: inf keeps the TF32 operands, NaN survives the fp16 conversion."""
+    meta, c, w = _inputs("cfgd_n16_m4_D8", 64)
+    r = _build(meta, n_importance=0, impl="tcgen05")
+    r.flags |= flags
+    named = _params(r)
+    out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0, perturb_overwrite=0, w=w)
+    adj = torch.ones_like(out["sdf"])
+    adj[7, 3] = bad
+    g = torch.autograd.grad((out["sdf"] * adj).sum(), [t for _, t in named], allow_unused=True)
+    assert any(x is not None and not bool(torch.isfinite(x).all()) for x in g)
+    if bad == float("inf"):
+        assert r.last_backward_operand_format() == "tf32"
+
+
 @pytest.mark.parametrize("impl", ["ffma", "tcgen05"])
 def test_training_loss_two_instances_ragged_tiles(impl):
     # 2 instances x 50 rays x 16 samples = 800 points per instance: 7 tiles each, the last one 32 points
