@@ -213,7 +213,12 @@ typedef struct OiRenderBwdDesc {
   int32_t flags;             /* tensor-core backward, format of the per-point operands of the weight-gradient contraction:
                               * default = chosen per call on the device from the adjoints' dynamic range (scaled fp16 when
                               * the points more than 2^18 below the largest adjoint carry < 2^-12 of the adjoint mass, else
-                              * TF32); bit 5 (value 32): always TF32; bit 6 (value 64): always scaled fp16 */
+                              * TF32); bit 5 (value 32): always TF32; bit 6 (value 64): always scaled fp16.
+                              * Overflow guard (one word of the workspace, which the caller zeroes ONCE after
+                              * allocating it): the first call on a workspace keeps TF32 and samples what the fp16
+                              * operands would be; fp16 is used from the next call on if none reached half of fp16's
+                              * largest number, and is switched off for the life of the workspace as soon as a sampled
+                              * operand does (nothing has saturated at that point) */
   int32_t reserved;
   float cos_anneal_ratio;
   float reserved_f;
@@ -451,11 +456,12 @@ int oi_augment_geom_backward(const OiAugmentGeomDesc* desc, void* stream);
 /* Which operand format the LAST oi_render_backward on desc->workspace used for the weight-gradient contraction
  * (see OiRenderBwdDesc.flags): *format = 0 TF32, 1 scaled fp16.  Diagnostic: synchronises `stream`. */
 int oi_render_backward_operand_format(const OiRenderBwdDesc* desc, int32_t* format, void* stream);
-/* The 8 control words the last oi_render_backward on desc->workspace left behind (diagnostic, synchronises `stream`):
+/* The 12 control words the last oi_render_backward on desc->workspace left behind (diagnostic, synchronises `stream`):
  * [0] points inside the relaxed sphere (gradient_error), [1] float bits of the largest |adjoint component|,
  * [2,3] u64 adjoint mass of all points / [4,5] of the points more than 2^18 below the maximum (2^-20 fixed point,
  * relative to the maximum's binade; zero when the format is forced), [6,7] float bits of the largest forward-type /
- * adjoint-type fp16 operand written (builds with -DOI_BWD_RANGE_STATS=1 only, else 0). */
+ * adjoint-type fp16 operand written (builds with -DOI_BWD_RANGE_STATS=1 only, else 0), [8] state of the workspace's fp16
+ * overflow guard: 0 unknown (next call probes), 1 safe, 2 unsafe (see OiRenderBwdDesc.flags), [9..11] 0. */
 int oi_render_backward_control_words(const OiRenderBwdDesc* desc, uint32_t* words, void* stream);
 
 /* Self-test of the tcgen05 building blocks: d[128,128] = a[128,128] * B^T through the split-fp16 UMMA path.

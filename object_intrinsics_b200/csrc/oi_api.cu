@@ -379,6 +379,7 @@ struct BwdWorkspace {
   int n_ctas, n_inst, tiles_per_inst, n_tiles, chunk_tiles;
   bool tc;
 };
+constexpr int kBwdStickyWord = 8;   // word of the `ticket` block that holds the fp16 overflow guard (oi_wgrad.cuh); never reset
 constexpr int kBwdChunkTiles = 2048;  // tiles per (bwd_tc_kernel, wgrad_tc_kernel) round: 5.8 GB of slabs
 
 int validate_bwd(const OiRenderBwdDesc* d) {
@@ -498,7 +499,8 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
   return launch_render_bwd_tc(*d, a, adj, invs_partial, d_film,
                               reinterpret_cast<float*>(ws + w.scratch), reinterpret_cast<float*>(ws + w.slabs),
                               reinterpret_cast<float*>(ws + w.aux), reinterpret_cast<float*>(ws + w.dw_inst),
-                              reinterpret_cast<const unsigned int*>(ws + w.relax_count), w.chunk_tiles, w.n_ctas, st);
+                              reinterpret_cast<const unsigned int*>(ws + w.relax_count),
+                              reinterpret_cast<unsigned int*>(ws + w.ticket) + kBwdStickyWord, w.chunk_tiles, w.n_ctas, st);
 }
 
 int oi_render_backward_control_words(const OiRenderBwdDesc* d, uint32_t* words, void* stream) {
@@ -512,16 +514,24 @@ int oi_render_backward_control_words(const OiRenderBwdDesc* d, uint32_t* words, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   OI_CHECK_CUDA(cudaMemcpyAsync(words, static_cast<const char*>(d->workspace) + w.relax_count, 8 * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, st));
+  uint32_t sticky = 0;
+  OI_CHECK_CUDA(cudaMemcpyAsync(&sticky, static_cast<const char*>(d->workspace) + w.ticket + kBwdStickyWord * 4,
+                                sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OI_CHECK_CUDA(cudaStreamSynchronize(st));
+  words[8] = sticky == kF16Safe ? 1u : (sticky == kF16Unsafe ? 2u : 0u);
+  words[9] = words[10] = words[11] = 0u;
   return OI_OK;
 }
 
 int oi_render_backward_operand_format(const OiRenderBwdDesc* d, int32_t* format, void* stream) {
   OI_CHECK_ARG(format != nullptr, "NULL pointer");
-  unsigned int ctl[8];
+  unsigned int ctl[12];
   int rc = oi_render_backward_control_words(d, ctl, stream);
   if (rc) return rc;
-  *format = (d->impl != OI_IMPL_FFMA && bwd_mode(ctl, d->flags).f16) ? 1 : 0;
+  // NOTE: the guard word read here is the one the NEXT call will see (a probing call has just marked the workspace
+  // safe and answers 1 although it ran on TF32 itself; a call that has just tripped the guard answers 0)
+  *format = (d->impl != OI_IMPL_FFMA &&
+             bwd_mode(ctl, d->flags, ctl[8] == 1u ? kF16Safe : (ctl[8] == 2u ? kF16Unsafe : 0u)).f16) ? 1 : 0;
   return OI_OK;
 }
 

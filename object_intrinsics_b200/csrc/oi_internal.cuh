@@ -170,7 +170,7 @@ int launch_render_bwd_ffma(const OiRenderBwdDesc& d, const RenderKArgs& geo, con
                            const float* invs_partial, float* d_film, float* scratch, int n_ctas, cudaStream_t st);
 int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
                          float* d_film, float* scratch, float* slabs, float* aux, float* dw_inst,
-                         const unsigned int* ctl, int chunk_tiles, int n_ctas, cudaStream_t st);
+                         const unsigned int* ctl, unsigned int* sticky, int chunk_tiles, int n_ctas, cudaStream_t st);
 size_t render_bwd_tc_dw_floats(int n_inst, int depth);
 int render_bwd_ctas(int n_tiles);
 size_t render_bwd_scratch_floats();

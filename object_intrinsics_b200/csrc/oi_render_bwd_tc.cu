@@ -103,6 +103,7 @@ struct BwdTcArgs {
   float* d_film;           // [n_inst][9][2][128] (unused | db)
   float* dw0;              // [n_inst][128][3] per-instance dW_0 (both parts)
   const unsigned int* ctl; // control block of the call (oi_wgrad.cuh: bwd_mode)
+  unsigned int* sticky;    // fp16 overflow guard word of the workspace (oi_wgrad.cuh)
 };
 
 struct __align__(1024) BwdTcSmem {
@@ -289,8 +290,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   BwdTcSmem& sm = *reinterpret_cast<BwdTcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const BwdMode mode = bwd_mode(a.ctl, a.r.flags);
+  // (the guard word is read before any CTA of this launch can change it: every CTA reads it first thing, a CTA that
+  //  trips it does so at the end of a tile, microseconds later)
+  const unsigned int guard_state = *a.sticky;
+  const BwdMode mode = bwd_mode(a.ctl, a.r.flags, guard_state);
   if (mode.f16 != F16) return;
+  const bool probing = !F16 && guard_state != kF16Unsafe && !(a.r.flags & OI_BWD_FLAG_FORCE_TF32);
   const int D = a.r.D;
   const BlobLayout L = blob_layout(D);
   const float* cst = a.r.blob + L.const_off;
@@ -462,6 +467,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       float sc_fwd = 1.f, sc_adj_inv = 1.f;
       float zu0, zu1, zu2;   // un-scaled z_bar
       float rs_fwd = 0.f, rs_adj = 0.f;
+      uint32_t guard = 0u;
+      const int guard_i = tile & 3;   // the channel pair of each oct that is sampled in this tile
+      float probe_adj = 0.f, probe_fwd = 0.f, probe_max = 0.f;
       {
         const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
         px = pc.px;
@@ -475,16 +483,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         }
         sdf_bar = q0.x; nb0 = q0.y; nb1 = q0.z; nb2 = q0.w;
         zb0 = q1.x; zb1 = q1.y; zb2 = q1.z;
+        zu0 = zb0; zu1 = zb1; zu2 = zb2;
         if (F16) {
           const int e_m = adj_exponent(q0, q1);
           const float sc_adj = pow2i(-e_m - kF16AdjShift);
           sc_adj_inv = pow2i(e_m + kF16AdjShift);
           sc_fwd = pow2i(e_m - mode.e_ref);
-          zu0 = zb0; zu1 = zb1; zu2 = zb2;
           sdf_bar *= sc_adj; nb0 *= sc_adj; nb1 *= sc_adj; nb2 *= sc_adj;
           zb0 *= sc_adj; zb1 *= sc_adj; zb2 *= sc_adj;
-        } else {
-          zu0 = zb0; zu1 = zb1; zu2 = zb2;
+        } else if (probing) {   // what the fp16 path would multiply the two operand types by
+          const int e_m = adj_exponent(q0, q1);
+          probe_adj = pow2i(-e_m - kF16AdjShift);
+          probe_fwd = pow2i(e_m - mode.e_ref);
         }
       }
       named_bar_sync(1 + t, kEpiThreadsPerSlot);
@@ -514,6 +524,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             // even lane: channel 2i of points (m, m+1) = (own.lo, nbr.lo); odd lane: channel 2i+1 of (m-1, m) = (nbr.hi, own.hi)
             const uint32_t pk = __byte_perm(own, nbr, pair_sel);
             *reinterpret_cast<uint32_t*>(pair_ptr[i] + uoff) = pk;
+            // overflow guard, sampled: a half with exponent field >= 30 (|x| >= 32768) carries into bit 15 / 31
+            if (i == guard_i) guard |= (pk & 0x7FFF7FFFu) + 0x08000800u;
           }
           return;
         }
@@ -522,6 +534,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         for (int e = 0; e < 8; ++e) {
           if (OI_BWD_STHINT >= 1) st_hint(p + e * 32 + (mc4 ^ (e << 2)), tf32_bias(v[e]), pol_first);
           else p[e * 32 + (mc4 ^ (e << 2))] = tf32_bias(v[e]);
+        }
+        if (probing) {   // sampled magnitude of the fp16 operand this value would be
+          const float sc = adjoint ? probe_adj : probe_fwd;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i == guard_i) probe_max = fmaxf(probe_max, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])) * sc);
         }
       };
       auto st_arg = [&](float4* p, float4 v) {
@@ -997,6 +1015,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         }, wait_acc, [&]() { if (l >= 2) { arg_pf(l - 2, true); g_pf(kCtaG + l - 2, true); } });
         if (k >= 1) a_ready();
       }
+      if ((F16 && (guard & 0x80008000u)) || (!F16 && probe_max >= 32768.0f)) *a.sticky = kF16Unsafe;
       if (OI_BWD_RANGE_STATS) {
         atomicMax(const_cast<unsigned int*>(a.ctl) + 6, __float_as_uint(rs_fwd));
         atomicMax(const_cast<unsigned int*>(a.ctl) + 7, __float_as_uint(rs_adj));
@@ -1022,7 +1041,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
 __global__ void finalize_bwd_tc_kernel(int D, int n_inst, int R, const float* __restrict__ film,
                                        const float* __restrict__ d_film, const float* __restrict__ invs_partial,
                                        const float* __restrict__ blob, const float* __restrict__ dwi,
-                                       const float* __restrict__ dwc, const float* __restrict__ dw0, OiNetGrads g) {
+                                       const float* __restrict__ dwc, const float* __restrict__ dw0, OiNetGrads g,
+                                       unsigned int* guard) {
   const int n = threadIdx.x;
   const int l = blockIdx.x;
   const BlobLayout L = blob_layout(D);
@@ -1091,6 +1111,8 @@ __global__ void finalize_bwd_tc_kernel(int D, int n_inst, int R, const float* __
       const double tot = red[0] + red[1] + red[2] + red[3];
       const bool inside = inv_s > 1e-6f && inv_s < 1e6f;
       if (inside) g.variance[0] += (float)(tot * 10.0 * (double)inv_s);
+      // fp16 overflow guard (oi_wgrad.cuh): a call that ran (probed) without tripping it marks the workspace safe
+      if (guard != nullptr && *guard != kF16Unsafe) *guard = kF16Safe;
     }
   }
 }
@@ -1115,7 +1137,7 @@ size_t render_bwd_tc_dw_floats(int n_inst, int depth) {
 // Runs the two tensor-core kernels over tiles [0, n_tiles) in chunks of at most `chunk_tiles`.
 int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,
                          float* d_film, float* scratch, float* slabs, float* aux, float* dw_inst,
-                         const unsigned int* ctl, int chunk_tiles, int n_ctas, cudaStream_t st) {
+                         const unsigned int* ctl, unsigned int* sticky, int chunk_tiles, int n_ctas, cudaStream_t st) {
   const int n_inst = geo.n_inst, D = geo.D;
   OI_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(BwdTcSmem)));
@@ -1146,6 +1168,7 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     a.dw0 = dw0;
     const int ctas = render_bwd_tc_ctas(t1 - t0) < n_ctas ? render_bwd_tc_ctas(t1 - t0) : n_ctas;
     a.ctl = ctl;
+    a.sticky = sticky;
     // both operand formats are launched; bwd_mode() (adjoint statistics, on the device) lets one of them exit at once
     // (also with a forced format: bwd_mode() overrides a forced fp16 when the adjoints are not finite)
     bwd_tc_kernel<false><<<ctas, kTcThreads, sizeof(BwdTcSmem), st>>>(a);
@@ -1162,6 +1185,7 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     w.slabs = slabs;
     w.aux = aux;
     w.ctl = ctl;
+    w.sticky = sticky;
     w.flags = geo.flags;
     w.tile0 = t0;
     float* dfilm0 = d_film;
@@ -1208,7 +1232,8 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
   if (d.evt_core_stop) OI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(d.evt_core_stop), st));
 
   finalize_bwd_tc_kernel<<<D + 2, kW, 0, st>>>(D, n_inst, d.n_rays, geo.film, d_film, invs_partial, geo.blob, dwi, dwc,
-                                               dw0, d.grads);
+                                               dw0, d.grads,
+                                               (geo.flags & OI_BWD_FLAG_FORCE_TF32) ? nullptr : sticky);   // no probe ran
   OI_CHECK_CUDA(cudaGetLastError());
   return OI_OK;
 }

@@ -52,13 +52,21 @@ struct BwdMode {
   bool f16;
   int e_ref;
 };
-__host__ __device__ __forceinline__ BwdMode bwd_mode(const unsigned int* ctl, int flags) {
+// Guard against fp16 overflow, one word of the workspace that no call resets (the owner zeroes the workspace once):
+//   0 (unknown)   the call keeps the TF32 operands and PROBES: the sweep samples what the fp16 operands would be (one
+//                 channel pair per oct, rotating with the tile index); if none reaches half of fp16's largest number
+//                 (|x| >= 32768) the finalize kernel marks the workspace kF16Safe
+//   kF16Safe      bwd_mode() may choose fp16; the fp16 sweep keeps sampling
+//   kF16Unsafe    set by any sweep that samples |x| >= 32768 (nothing has saturated at that point): TF32 from the next
+//                 call on, for the life of the workspace
+constexpr unsigned int kF16Safe = 0xF16C0DE5u, kF16Unsafe = 0xF16D15ABu;
+__host__ __device__ __forceinline__ BwdMode bwd_mode(const unsigned int* ctl, int flags, unsigned int guard = kF16Safe) {
   const unsigned int mb = ctl[1];
   const int ex = (int)((mb >> 23) & 0xFFu);
   const unsigned long long tot = (unsigned long long)ctl[2] | ((unsigned long long)ctl[3] << 32);
   const unsigned long long low = (unsigned long long)ctl[4] | ((unsigned long long)ctl[5] << 32);
   BwdMode m;
-  m.f16 = ex > 0 && ex < 255 && low <= (tot >> kF16MassShift);
+  m.f16 = ex > 0 && ex < 255 && low <= (tot >> kF16MassShift) && guard == kF16Safe;
   if (flags & OI_BWD_FLAG_FORCE_TF32) m.f16 = false;
   if ((flags & OI_BWD_FLAG_FORCE_F16) && ex > 0 && ex < 255) m.f16 = true;
   m.e_ref = ex - 127 - kF16RefShift;
@@ -101,6 +109,7 @@ struct WgArgs {
   const float* slabs;  // [n_tiles][slabs_per_tile][4 blocks][128 channels][32 points]
   const float* aux;    // [n_tiles][4 blocks][4 rows][32 points]
   const unsigned int* ctl;   // control block of the backward call (bwd_mode); NULL = TF32 slabs unconditionally
+  const unsigned int* sticky;   // fp16 overflow guard word of the workspace (bwd_mode), or NULL
   int flags;
   WgGroup groups[WG_MAX_GROUPS];
 };

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float out_scale = 1.0f;
   if (a.ctl != nullptr) {
-    const BwdMode mode = bwd_mode(a.ctl, a.flags);
+    const BwdMode mode = bwd_mode(a.ctl, a.flags, a.sticky ? *a.sticky : kF16Safe);
     if (mode.f16 != F16) return;   // the other variant of this launch pair does the work
     if (F16) out_scale = pow2i(mode.e_ref + kF16AdjShift);
   } else if (F16) {

@@ -284,7 +284,8 @@ class _RenderFunction(torch.autograd.Function):
             _lib.check(L.oi_render_backward_workspace_bytes(C.byref(d), C.byref(nbytes)),
                        "oi_render_backward_workspace_bytes")
             if r._bwd_workspace is None or r._bwd_workspace.numel() < nbytes.value or r._bwd_workspace.device != dev:
-                r._bwd_workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+                # zeroed once: the workspace holds the state of the fp16 overflow guard (OiRenderBwdDesc.flags)
+                r._bwd_workspace = torch.zeros(nbytes.value, dtype=torch.uint8, device=dev)
             d.workspace, d.workspace_bytes = r._bwd_workspace.data_ptr(), r._bwd_workspace.numel()
             _lib.check(L.oi_render_backward(C.byref(d), _lib.current_stream_ptr(dev)), "oi_render_backward")
         r._last_bwd_desc = d
@@ -385,11 +386,11 @@ class NeuSRenderer:
         return "fp16" if fmt.value == 1 else "tf32"
 
     def last_backward_control_words(self):
-        """The 8 control words of the last backward (oi_render_backward_control_words): diagnostic, synchronises."""
+        """The 12 control words of the last backward (oi_render_backward_control_words): diagnostic, synchronises."""
         d = getattr(self, "_last_bwd_desc", None)
         if d is None:
             raise RuntimeError("no backward has run on this renderer yet")
-        words = (C.c_uint32 * 8)()
+        words = (C.c_uint32 * 12)()
         dev = self._bwd_workspace.device
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().oi_render_backward_control_words(C.byref(d), words, _lib.current_stream_ptr(dev)),

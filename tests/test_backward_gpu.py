@@ -60,6 +60,11 @@ def _check(meta, c, w, adj_keys, cos_anneal, n_importance=0, t_rand=None, impl="
     torch.manual_seed(seed)
     r = _build(meta, n_importance=n_importance, impl=impl)
     r.flags |= flags
+    if expect is not None:
+        # the first backward on a workspace keeps TF32 and probes the range of the fp16 operands (overflow guard)
+        o = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=cos_anneal, perturb_overwrite=0,
+                     w=w, t_rand=t_rand)
+        torch.autograd.grad(o["color_fine"].sum(), [t for _, t in _params(r)][:1])
     wk = w.detach().clone().requires_grad_(True)
     out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=cos_anneal, perturb_overwrite=0,
                    w=wk, t_rand=t_rand, return_z_vals=True)
@@ -164,6 +169,36 @@ def test_operand_format_follows_the_adjoint_statistics():
         s = float(b.abs().max()) + 1e-30
         assert float((a - b).abs().max()) / s < 1e-5, k      # same kernels (atomics reorder the sums)
         assert float((h - b).abs().max()) / s < 2e-3, k      # the forced fp16 path degrades gracefully here
+
+
+def test_fp16_overflow_guard_of_the_workspace():
+    """First backward on a workspace: TF32 + sampled range probe -> marked safe, fp16 from then on.  An SDF head blown
+    up 3000x pushes the forward-type operands past half of fp16's range: the fp16 sweep trips the guard and every
+    later call on the workspace keeps TF32 (and matches the forced-TF32 gradients)."""
+    meta, c, w = _inputs("cfgd_n16_m4_D8", 64)
+    r = _build(meta, n_importance=0, impl="tcgen05")
+    named = _params(r)
+
+    def grads():
+        out = r.render(c["rays_o"], c["rays_d"], c["near"], c["far"], cos_anneal_ratio=1.0, perturb_overwrite=0, w=w)
+        return torch.autograd.grad(out["color_fine"].sum() + out["weight_sum"].sum(), [t for _, t in named],
+                                   allow_unused=True)
+
+    grads()
+    assert r.last_backward_control_words()[8] == 1 and r.last_backward_operand_format() == "fp16"
+    grads()
+    assert r.last_backward_control_words()[8] == 1
+    with torch.no_grad():
+        r.sdf_network.sigma_linear.weight.mul_(3e3)
+    grads()                                                  # fp16 sweep, trips the guard
+    assert r.last_backward_control_words()[8] == 2 and r.last_backward_operand_format() == "tf32"
+    g_auto = grads()                                         # TF32 from now on
+    r.flags |= 32
+    g_tf32 = grads()
+    for (k, _), a, b in zip(named, g_auto, g_tf32):
+        if a is not None:
+            assert torch.isfinite(a).all(), k
+            assert float((a - b).abs().max()) <= 1e-5 * (float(b.abs().max()) + 1e-30), k
 
 
 @pytest.mark.parametrize("flags", [0, 64])
@@ -313,6 +348,8 @@ def test_backward_under_ddp_single_rank_nccl():
             return out["color_fine"].sum() + out["weight_sum"].sum() + 10.0 * out["gradient_error"]
 
     gen = Gen(r0).cuda()
+    gen(c, w).backward()          # first backward on the workspace: TF32 + range probe (overflow guard); not compared
+    gen.zero_grad(set_to_none=True)
     gen(c, w).backward()
     ref = {k: p.grad.clone() for k, p in gen.named_parameters() if p.grad is not None}
     gen.zero_grad(set_to_none=True)
