@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       float rs_fwd = 0.f, rs_adj = 0.f;
       uint32_t guard = 0u;
       const int guard_i = tile & 3;   // the channel pair of each oct that is sampled in this tile
+      const bool guard_1 = guard_i == 1, guard_2 = guard_i == 2, guard_3 = guard_i == 3;
       float probe_adj = 0.f, probe_fwd = 0.f, probe_max = 0.f;
       {
         const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
@@ -516,6 +517,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             }
           }
           const uint32_t uoff = (uint32_t)slab16_offset(slab) + (uint32_t)o * 1024u;   // warp-uniform part of the address
+          uint32_t pks[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t own;   // (channel 2i+1, channel 2i) of this lane's point
@@ -524,9 +526,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             // even lane: channel 2i of points (m, m+1) = (own.lo, nbr.lo); odd lane: channel 2i+1 of (m-1, m) = (nbr.hi, own.hi)
             const uint32_t pk = __byte_perm(own, nbr, pair_sel);
             *reinterpret_cast<uint32_t*>(pair_ptr[i] + uoff) = pk;
-            // overflow guard, sampled: a half with exponent field >= 30 (|x| >= 32768) carries into bit 15 / 31
-            if (i == guard_i) guard |= (pk & 0x7FFF7FFFu) + 0x08000800u;
+            pks[i] = pk;
           }
+          // overflow guard, sampled (pair guard_i of every oct): a half with exponent field >= 30 (|x| >= 32768)
+          // carries into bit 15 / 31
+          const uint32_t smp = guard_3 ? pks[3] : (guard_2 ? pks[2] : (guard_1 ? pks[1] : pks[0]));
+          guard |= (smp & 0x7FFF7FFFu) + 0x08000800u;
           return;
         }
         float* p = gso + (size_t)slab * kSlabFloats + o * 256;
