@@ -68,9 +68,12 @@ def test_backward_oracle_matches_reference_gradients_fp64(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("impl", ["ffma", "tcgen05"])
+@pytest.mark.parametrize("impl,flags", [("ffma", 0), ("tcgen05", 32), ("tcgen05", 64)],
+                         ids=["ffma", "tcgen05-tf32-operands", "tcgen05-fp16-operands"])
 @pytest.mark.parametrize("name", CASES)
-def test_cuda_backward_matches_reference_gradients(name, impl):
+def test_cuda_backward_matches_reference_gradients(name, impl, flags):
+    """flags: the operand format of the tensor-core backward's weight-gradient contraction, forced (bit 5 TF32, bit 6
+    scaled fp16 -- what the device-side rule picks after the first, probing call on a workspace)."""
     from object_intrinsics_b200 import fields
     from object_intrinsics_b200.renderer import NeuSRenderer
     meta, inp, _, _ = load_case(name)
@@ -81,6 +84,7 @@ def test_cuda_backward_matches_reference_gradients(name, impl):
     r = NeuSRenderer(nerf=None, sdf_network=sdf, deviation_network=dev, color_network=col,
                      n_samples=meta["n_samples"], n_importance=meta["n_importance"], n_outside=0, up_sample_steps=1,
                      perturb=0, impl=impl)
+    r.flags |= flags
     c = {k: inp[k].cuda() for k in ("rays_o", "rays_d", "near", "far", "z")}
     w = sdf.style(c["z"])                     # grad mode: the style layers are reached through w, as in the reference
     w.retain_grad()
@@ -105,4 +109,4 @@ def test_cuda_backward_matches_reference_gradients(name, impl):
         assert err <= tol, f"{k}: rel Linf {err:.3e} > tol {tol:.3e} (reference fp32 floor {floor:.3e}, scale {scale:.3e})"
         if err / tol > worst[0]:
             worst = (err / tol, k)
-    print(f"{name}/{impl}: worst err/tol {worst[0]:.2f} ({worst[1]})")
+    print(f"{name}/{impl}/{flags}: worst err/tol {worst[0]:.2f} ({worst[1]})")
