@@ -216,9 +216,9 @@ typedef struct OiRenderBwdDesc {
                               * TF32); bit 5 (value 32): always TF32; bit 6 (value 64): always scaled fp16.
                               * Overflow guard (one word of the workspace, which the caller zeroes ONCE after
                               * allocating it): the first call on a workspace keeps TF32 and samples what the fp16
-                              * operands would be; fp16 is used from the next call on if none reached half of fp16's
-                              * largest number, and is switched off for the life of the workspace as soon as a sampled
-                              * operand does (nothing has saturated at that point) */
+                              * operands would be; fp16 is used from the next call on if none reached an eighth of fp16's
+                              * largest number, and is switched off for the life of the workspace as soon as an operand
+                              * does -- 8x below saturation */
   int32_t reserved;
   float cos_anneal_ratio;
   float reserved_f;

@@ -491,7 +491,8 @@ int oi_render_backward(const OiRenderBwdDesc* d, void* stream) {
   float* adj = reinterpret_cast<float*>(ws + w.adj);
   float* invs_partial = reinterpret_cast<float*>(ws + w.invs_partial);
   float* d_film = reinterpret_cast<float*>(ws + w.d_film);
-  rc = launch_bwd_tail(*d, a, adj, invs_partial, reinterpret_cast<unsigned int*>(ws + w.relax_count), d_film, w.tc, st);
+  rc = launch_bwd_tail(*d, a, adj, invs_partial, reinterpret_cast<unsigned int*>(ws + w.relax_count),
+                       reinterpret_cast<const unsigned int*>(ws + w.ticket) + kBwdStickyWord, d_film, w.tc, st);
   if (rc) return rc;
   if (!w.tc)
     return launch_render_bwd_ffma(*d, a, adj, invs_partial, d_film, reinterpret_cast<float*>(ws + w.scratch), w.n_ctas,

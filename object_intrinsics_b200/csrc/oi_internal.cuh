@@ -165,7 +165,8 @@ int launch_render_ffma(const RenderKArgs& a, cudaStream_t st);
 int launch_render_tc(const RenderKArgs& a, cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* B, const void* panel, float* D, cudaStream_t st);
 int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
-                    unsigned int* relax_count, float* d_film, bool head_biases, cudaStream_t st);
+                    unsigned int* relax_count, const unsigned int* guard, float* d_film, bool head_biases,
+                    cudaStream_t st);
 int launch_render_bwd_ffma(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj,
                            const float* invs_partial, float* d_film, float* scratch, int n_ctas, cudaStream_t st);
 int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const float* adj, const float* invs_partial,

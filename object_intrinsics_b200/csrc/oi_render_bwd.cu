@@ -1020,7 +1020,11 @@ size_t render_bwd_scratch_floats() { return (size_t)kNumSlots * kSlot; }
 // Adjoint statistics for bwd_mode() (oi_wgrad.cuh): total "mass" sum_m A_m / 2^e_max in 2^-20 fixed point (A_m = max
 // |adjoint component| of point m) and the mass of the points more than 2^kF16LowShift below the global maximum --
 // integer sums, so the decision is the same in every run.
-__global__ void adj_stats_kernel(const float* __restrict__ adj, size_t n_points, unsigned int* ctl) {
+__global__ void adj_stats_kernel(const float* __restrict__ adj, size_t n_points, unsigned int* ctl,
+                                 const unsigned int* __restrict__ guard) {
+  // snapshot of the workspace's fp16 overflow guard: every kernel of this call decides on the SAME state, also when
+  // the sweep trips the guard half-way through the call (the trip then takes effect from the next call on)
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl[kCtlGuardSnapshot] = *guard;
   const unsigned int mb = ctl[1];
   const int ex = (int)((mb >> 23) & 0xFFu);
   if (ex == 0 || ex == 255) return;
@@ -1047,7 +1051,8 @@ __global__ void adj_stats_kernel(const float* __restrict__ adj, size_t n_points,
 }
 
 int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj, float* invs_partial,
-                    unsigned int* relax_count, float* d_film, bool head_biases, cudaStream_t st) {
+                    unsigned int* relax_count, const unsigned int* guard, float* d_film, bool head_biases,
+                    cudaStream_t st) {
   TailArgs t;
   t.R = d.n_rays;
   t.S = d.n_samples_total;
@@ -1086,7 +1091,7 @@ int launch_bwd_tail(const OiRenderBwdDesc& d, const RenderKArgs& geo, float* adj
   tail_bwd_kernel<<<(t.R + 7) / 8, 256, 0, st>>>(t);   // 8 warps per block, one ray per warp
   OI_CHECK_CUDA(cudaGetLastError());
   if (head_biases && !(d.flags & (OI_BWD_FLAG_FORCE_TF32 | OI_BWD_FLAG_FORCE_F16))) {   // tensor-core backward, automatic
-    adj_stats_kernel<<<296, 256, 0, st>>>(adj, (size_t)t.R * t.S, relax_count);
+    adj_stats_kernel<<<296, 256, 0, st>>>(adj, (size_t)t.R * t.S, relax_count, guard);
     OI_CHECK_CUDA(cudaGetLastError());
   }
   return OI_OK;

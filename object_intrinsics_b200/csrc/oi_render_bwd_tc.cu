@@ -290,9 +290,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   BwdTcSmem& sm = *reinterpret_cast<BwdTcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // (the guard word is read before any CTA of this launch can change it: every CTA reads it first thing, a CTA that
-  //  trips it does so at the end of a tile, microseconds later)
-  const unsigned int guard_state = *a.sticky;
+  // the call's snapshot of the workspace's overflow guard (adj_stats_kernel): the same for every kernel of the call
+  const unsigned int guard_state = a.ctl[kCtlGuardSnapshot];
   const BwdMode mode = bwd_mode(a.ctl, a.r.flags, guard_state);
   if (mode.f16 != F16) return;
   const bool probing = !F16 && guard_state != kF16Unsafe && !(a.r.flags & OI_BWD_FLAG_FORCE_TF32);
@@ -468,8 +467,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
       float zu0, zu1, zu2;   // un-scaled z_bar
       float rs_fwd = 0.f, rs_adj = 0.f;
       uint32_t guard = 0u;
-      const int guard_i = tile & 3;   // the channel pair of each oct that is sampled in this tile
-      const bool guard_1 = guard_i == 1, guard_2 = guard_i == 2, guard_3 = guard_i == 3;
+      __half2 guard2 = __float2half2_rn(0.f);
       float probe_adj = 0.f, probe_fwd = 0.f, probe_max = 0.f;
       {
         const PointCtx pc = point_prologue(a.r, inst, tin, m, false);
@@ -528,10 +526,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             *reinterpret_cast<uint32_t*>(pair_ptr[i] + uoff) = pk;
             pks[i] = pk;
           }
-          // overflow guard, sampled (pair guard_i of every oct): a half with exponent field >= 30 (|x| >= 32768)
-          // carries into bit 15 / 31
-          const uint32_t smp = guard_3 ? pks[3] : (guard_2 ? pks[2] : (guard_1 ? pks[1] : pks[0]));
-          guard |= (smp & 0x7FFF7FFFu) + 0x08000800u;
+          // overflow guard: running max |x| over every operand this thread writes (one packed-half max per word)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) guard2 = __hmax2(guard2, __habs2(*reinterpret_cast<const __half2*>(&pks[i])));
           return;
         }
         float* p = gso + (size_t)slab * kSlabFloats + o * 256;
@@ -540,11 +537,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
           if (OI_BWD_STHINT >= 1) st_hint(p + e * 32 + (mc4 ^ (e << 2)), tf32_bias(v[e]), pol_first);
           else p[e * 32 + (mc4 ^ (e << 2))] = tf32_bias(v[e]);
         }
-        if (probing) {   // sampled magnitude of the fp16 operand this value would be
+        if (probing) {   // magnitude of the fp16 operands these values would be
           const float sc = adjoint ? probe_adj : probe_fwd;
+          float mx = 0.f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i == guard_i) probe_max = fmaxf(probe_max, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])) * sc);
+          for (int e = 0; e < 8; ++e) mx = fmaxf(mx, fabsf(v[e]));
+          probe_max = fmaxf(probe_max, mx * sc);
         }
       };
       auto st_arg = [&](float4* p, float4 v) {
@@ -829,7 +827,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
                   nu2 = F16 ? nb2 * sc_adj_inv : nb2;   // un-scaled normal_bar
       if (h == 0) {
         if (F16) {   // rows of 128 B = 64 points, chunk XOR row
-          const float av[4] = {gx * sc_fwd, gy * sc_fwd, gz * sc_fwd, sc_fwd};
+          const float sc_n = sc_fwd * (1.0f / (float)(1 << kF16NormalShift));
+          const float av[4] = {gx * sc_n, gy * sc_n, gz * sc_n, sc_fwd};
+          // overflow guard: the normal is the largest forward-type operand when the SDF head grows (every tile: 3 values)
+          if (fmaxf(fmaxf(fabsf(av[0]), fabsf(av[1])), fabsf(av[2])) >= kF16GuardLimit) guard |= 0x80000000u;
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             unsigned short hbits;
@@ -837,6 +838,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
             *reinterpret_cast<unsigned short*>(auxo16 + r * 128 + (mc16 ^ (r << 4))) = hbits;
           }
         } else {
+          if (probing)
+            probe_max = fmaxf(probe_max, fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fabsf(gz)) * probe_fwd *
+                                             (1.0f / (float)(1 << kF16NormalShift)));
           auxo[0 * 32 + ((mc ^ 0) << 2)] = tf32_bias(gx);
           auxo[1 * 32 + ((mc ^ 1) << 2)] = tf32_bias(gy);
           auxo[2 * 32 + ((mc ^ 2) << 2)] = tf32_bias(gz);
@@ -1020,7 +1024,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const BwdTcArgs a
         }, wait_acc, [&]() { if (l >= 2) { arg_pf(l - 2, true); g_pf(kCtaG + l - 2, true); } });
         if (k >= 1) a_ready();
       }
-      if ((F16 && (guard & 0x80008000u)) || (!F16 && probe_max >= 32768.0f)) *a.sticky = kF16Unsafe;
+      if ((F16 && ((guard & 0x80000000u) || fmaxf(__low2float(guard2), __high2float(guard2)) >= kF16GuardLimit)) ||
+          (!F16 && probe_max >= kF16GuardLimit))
+        *a.sticky = kF16Unsafe;
       if (OI_BWD_RANGE_STATS) {
         atomicMax(const_cast<unsigned int*>(a.ctl) + 6, __float_as_uint(rs_fwd));
         atomicMax(const_cast<unsigned int*>(a.ctl) + 7, __float_as_uint(rs_adj));
@@ -1190,7 +1196,6 @@ int launch_render_bwd_tc(const OiRenderBwdDesc& d, const RenderKArgs& geo, const
     w.slabs = slabs;
     w.aux = aux;
     w.ctl = ctl;
-    w.sticky = sticky;
     w.flags = geo.flags;
     w.tile0 = t0;
     float* dfilm0 = d_film;

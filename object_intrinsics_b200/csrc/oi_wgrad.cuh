@@ -53,13 +53,20 @@ struct BwdMode {
   int e_ref;
 };
 // Guard against fp16 overflow, one word of the workspace that no call resets (the owner zeroes the workspace once):
-//   0 (unknown)   the call keeps the TF32 operands and PROBES: the sweep samples what the fp16 operands would be (one
-//                 channel pair per oct, rotating with the tile index); if none reaches half of fp16's largest number
-//                 (|x| >= 32768) the finalize kernel marks the workspace kF16Safe
-//   kF16Safe      bwd_mode() may choose fp16; the fp16 sweep keeps sampling
-//   kF16Unsafe    set by any sweep that samples |x| >= 32768 (nothing has saturated at that point): TF32 from the next
+//   0 (unknown)   the call keeps the TF32 operands and PROBES: the sweep tracks the largest |x| of what the fp16 operands
+//                 would be (every operand of every tile); if
+//                 none reaches half of fp16's largest number (|x| >= 32768) the finalize kernel marks the workspace
+//                 kF16Safe
+//   kF16Safe      bwd_mode() may choose fp16; the fp16 sweep keeps a running max |x| of the operands it writes
+//   kF16Unsafe    set by any sweep that sees |x| >= 8192 (8x below saturation): TF32 from the next
 //                 call on, for the life of the workspace
+// Every kernel of a call decides on the snapshot adj_stats_kernel takes of that word (control word kCtlGuardSnapshot;
+// 0 = unknown when the format is forced and no snapshot is taken -- forced formats ignore the guard).
 constexpr unsigned int kF16Safe = 0xF16C0DE5u, kF16Unsafe = 0xF16D15ABu;
+constexpr int kF16NormalShift = 4;   // the normal columns of the aux operand carry another 2^-4 (|grad sdf| grows with the
+                                     // SDF head: it is the first forward-type operand to reach the guard limit)
+constexpr float kF16GuardLimit = 8192.0f;   // an eighth of fp16's largest number; measured operands stay below 2 100
+constexpr int kCtlGuardSnapshot = 9;
 __host__ __device__ __forceinline__ BwdMode bwd_mode(const unsigned int* ctl, int flags, unsigned int guard = kF16Safe) {
   const unsigned int mb = ctl[1];
   const int ex = (int)((mb >> 23) & 0xFFu);
@@ -109,7 +116,6 @@ struct WgArgs {
   const float* slabs;  // [n_tiles][slabs_per_tile][4 blocks][128 channels][32 points]
   const float* aux;    // [n_tiles][4 blocks][4 rows][32 points]
   const unsigned int* ctl;   // control block of the backward call (bwd_mode); NULL = TF32 slabs unconditionally
-  const unsigned int* sticky;   // fp16 overflow guard word of the workspace (bwd_mode), or NULL
   int flags;
   WgGroup groups[WG_MAX_GROUPS];
 };

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float out_scale = 1.0f;
   if (a.ctl != nullptr) {
-    const BwdMode mode = bwd_mode(a.ctl, a.flags, a.sticky ? *a.sticky : kF16Safe);
+    const BwdMode mode = bwd_mode(a.ctl, a.flags, a.ctl[kCtlGuardSnapshot]);
     if (mode.f16 != F16) return;   // the other variant of this launch pair does the work
     if (F16) out_scale = pow2i(mode.e_ref + kF16AdjShift);
   } else if (F16) {
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
           float* dst = G.aux_out[c];
           if (dst != nullptr)
             atomicAdd(dst + (size_t)cur_inst * G.aux_inst_stride[c] + (size_t)i * G.aux_ch_stride[c],
-                      __uint_as_float(r[c]) * out_scale);
+                      __uint_as_float(r[c]) * ((F16 && c < 3) ? out_scale * (float)(1 << kF16NormalShift) : out_scale));
         }
       }
       tc::fence_before_thread_sync();
