@@ -464,6 +464,13 @@ int oi_render_backward_operand_format(const OiRenderBwdDesc* desc, int32_t* form
  * overflow guard: 0 unknown (next call probes), 1 safe, 2 unsafe (see OiRenderBwdDesc.flags), [9..11] 0. */
 int oi_render_backward_control_words(const OiRenderBwdDesc* desc, uint32_t* words, void* stream);
 
+/* The device-side rule that picks the operand format of a backward call, evaluated on the host (no GPU needed) for the
+ * given control words (layout above; only [1]..[5] are read), desc flags and guard state (0 unknown, 1 safe, 2
+ * unsafe): *fp16 = 1 when the scaled fp16 operands would be used, *e_ref = exponent the forward-type operands are
+ * referred to. */
+int oi_selftest_bwd_mode(const uint32_t* control_words, int32_t flags, int32_t guard_state, int32_t* fp16,
+                         int32_t* e_ref);
+
 /* Self-test of the tcgen05 building blocks: d[128,128] = a[128,128] * B^T through the split-fp16 UMMA path.
  * B = b[128,128] ([n][k] row-major) when packed_weights is NULL, else panel `panel` of the packed blob
  * (order: forward l=1..D-1, colour features, reverse l=D-1..1; each is 2^8 * W in [n][k] orientation). */

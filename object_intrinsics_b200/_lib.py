@@ -171,7 +171,7 @@ EXPORTS = ["oi_packed_weights_bytes", "oi_pack_weights", "oi_style_mlp", "oi_ren
            "oi_augment_geom_workspace_bytes", "oi_augment_geom_forward", "oi_augment_geom_backward",
            "oi_augment_geom_setup", "oi_render_maps_backward", "oi_augment_geom_setup_ops",
            "oi_augment_geom_setup_raw", "oi_render_backward_operand_format",
-           "oi_render_backward_control_words"]
+           "oi_render_backward_control_words", "oi_selftest_bwd_mode"]
 
 _lib = None
 
@@ -199,6 +199,8 @@ def lib():
     L.oi_render_backward.argtypes = [C.POINTER(OiRenderBwdDesc), C.c_void_p]
     L.oi_render_backward_operand_format.argtypes = [C.POINTER(OiRenderBwdDesc), C.POINTER(C.c_int32), C.c_void_p]
     L.oi_render_backward_control_words.argtypes = [C.POINTER(OiRenderBwdDesc), C.POINTER(C.c_uint32), C.c_void_p]
+    L.oi_selftest_bwd_mode.argtypes = [C.POINTER(C.c_uint32), C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32)]
     L.oi_selftest_wgrad.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
     L.oi_augment_geom_workspace_bytes.argtypes = [C.POINTER(OiAugmentGeomDesc), C.POINTER(C.c_size_t)]
     L.oi_augment_geom_setup.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

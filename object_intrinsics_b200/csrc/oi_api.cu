@@ -536,6 +536,16 @@ int oi_render_backward_operand_format(const OiRenderBwdDesc* d, int32_t* format,
   return OI_OK;
 }
 
+int oi_selftest_bwd_mode(const uint32_t* control_words, int32_t flags, int32_t guard_state, int32_t* fp16,
+                         int32_t* e_ref) {
+  OI_CHECK_ARG(control_words && fp16 && e_ref, "NULL pointer");
+  OI_CHECK_ARG(guard_state >= 0 && guard_state <= 2, "guard_state must be 0 (unknown), 1 (safe) or 2 (unsafe)");
+  const BwdMode m = bwd_mode(control_words, flags, guard_state == 1 ? kF16Safe : (guard_state == 2 ? kF16Unsafe : 0u));
+  *fp16 = m.f16 ? 1 : 0;
+  *e_ref = m.e_ref;
+  return OI_OK;
+}
+
 int oi_selftest_tc(const float* a, const float* b, const void* packed_weights, int32_t depth, int32_t panel,
                    float* d, void* stream) {
   OI_CHECK_ARG(a && d, "a and d must be non-NULL");

@@ -243,3 +243,37 @@ def test_film_graph_edge_matches_the_torch_formulation():
     # w without grad: no gradient is formed for it
     g3, _ = film_graph(sdf, col, w.detach())
     assert torch.autograd.grad([g3], params[:1], [gg])[0] is not None
+
+
+def test_backward_operand_format_rule_without_gpu():
+    """bwd_mode (csrc/oi_wgrad.cuh), the rule every kernel of a backward call evaluates on the device, through its host
+    twin: fp16 needs a safe guard, finite adjoints and < 2^-12 of the adjoint mass more than 2^18 below the maximum;
+    flags bit 5 / 6 force TF32 / fp16 (a forced fp16 still yields to non-finite adjoints)."""
+    import ctypes as C
+    import struct
+    from object_intrinsics_b200 import _lib
+    L = _lib.lib()
+
+    def rule(amax, total, low, flags=0, guard=1):
+        w = (C.c_uint32 * 12)()
+        w[1] = struct.unpack("I", struct.pack("f", amax))[0]
+        w[2], w[3] = total & 0xFFFFFFFF, total >> 32
+        w[4], w[5] = low & 0xFFFFFFFF, low >> 32
+        f16, e_ref = C.c_int32(-1), C.c_int32(0)
+        assert L.oi_selftest_bwd_mode(w, flags, guard, C.byref(f16), C.byref(e_ref)) == 0
+        return f16.value, e_ref.value
+
+    assert rule(1.0, 1 << 30, 0) == (1, -8)                      # e_ref = exponent of the maximum - 8
+    assert rule(3.0e-5, 1 << 30, 0)[1] == -16 - 8                # 3e-5 = 1.97 * 2^-16
+    assert rule(1.0, 1 << 30, (1 << 18) - 1)[0] == 1             # low mass just under 2^-12 of the total
+    assert rule(1.0, 1 << 30, (1 << 18) + 1)[0] == 0             # ... just over: TF32
+    assert rule(1.0, 1 << 40, 1 << 27)[0] == 1 and rule(1.0, 1 << 40, 1 << 29)[0] == 0   # 64-bit sums
+    assert rule(1.0, 1 << 30, 0, guard=0)[0] == 0 and rule(1.0, 1 << 30, 0, guard=2)[0] == 0
+    assert rule(0.0, 0, 0)[0] == 0                               # all-zero adjoints: nothing to scale
+    assert rule(float("inf"), 1 << 30, 0)[0] == 0 and rule(float("inf"), 1 << 30, 0, flags=64)[0] == 0
+    assert rule(1.0, 1 << 30, 0, flags=32)[0] == 0
+    assert rule(1.0, 1 << 30, 1 << 29, flags=64, guard=2)[0] == 1  # forced fp16 ignores statistics and guard
+    assert L.oi_selftest_bwd_mode(None, 0, 1, None, None) == -1
+    w = (C.c_uint32 * 12)()
+    f = C.c_int32()
+    assert L.oi_selftest_bwd_mode(w, 0, 3, C.byref(f), C.byref(f)) == -1
