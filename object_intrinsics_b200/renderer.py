@@ -371,8 +371,11 @@ class NeuSRenderer:
 
     # -------------------------------------------------------------------------------------------
     def last_backward_operand_format(self) -> str:
-        """'fp16' or 'tf32': the format the last tensor-core backward of this renderer chose for the per-point operands
-        of the weight-gradient contraction (OiRenderBwdDesc.flags; `self.flags |= 32` forces TF32, `|= 64` fp16).
+        """'fp16' or 'tf32': the format of the per-point operands of the weight-gradient contraction that the rule of
+        the tensor-core backward yields for the adjoint statistics of the LAST call and the CURRENT state of the
+        workspace's overflow guard -- i.e. what that call ran on, except that the first call on a workspace (the TF32
+        range probe) already answers for the calls after it, and a call that tripped the guard answers 'tf32'
+        although it still ran on fp16 (OiRenderBwdDesc.flags; `self.flags |= 32` forces TF32, `|= 64` fp16).
         Diagnostic: synchronises the stream."""
         d = getattr(self, "_last_bwd_desc", None)
         if d is None:
