@@ -33,10 +33,12 @@ def _nvcc():
 def _stamp():
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [os.path.join(ROOT, "include", "oi_b200.h")]
+    # content and repo-relative names only: the same sources give the same stamp wherever the tree is checked out
+    # (profiles/traffic.json refers to it, and the GPU box runs the tree from a scratch path)
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+            h.update(os.path.relpath(f, ROOT).encode() + b"\0" + fh.read())
+    h.update(" ".join(a.replace(ROOT, ".") for a in NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
