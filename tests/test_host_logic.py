@@ -277,3 +277,32 @@ def test_backward_operand_format_rule_without_gpu():
     w = (C.c_uint32 * 12)()
     f = C.c_int32()
     assert L.oi_selftest_bwd_mode(w, 0, 3, C.byref(f), C.byref(f)) == -1
+
+
+def test_augment_setup_entry_points_validate_without_gpu():
+    """oi_augment_geom_setup / _setup_ops / _setup_raw reject NULL pointers, bad sizes, bad factor kinds and forms
+    before any launch (status -1 = OI_ERR_INVALID_ARGUMENT, message available through oi_last_error)."""
+    import ctypes as C
+    from object_intrinsics_b200 import _lib
+    L = _lib.lib()
+    p = C.c_void_p(0x1000)          # never dereferenced: validation fails first
+    assert L.oi_augment_geom_setup(None, 4, 64, 64, 12, p, p, None) == -1
+    assert L.oi_augment_geom_setup(p, 0, 64, 64, 12, p, p, None) == -1
+    assert L.oi_augment_geom_setup(p, 4, 64, 64, 10, p, p, None) == -1          # taps must be a multiple of 4
+    ops = (_lib.OiAugmentOp * 2)()
+    ops[0].kind, ops[0].p0, ops[0].p1 = 0, C.cast(p, _lib.f32p), C.cast(p, _lib.f32p)
+    ops[1].kind, ops[1].p0 = 5, C.cast(p, _lib.f32p)
+    assert L.oi_augment_geom_setup_ops(ops, 2, 4, 64, 64, 12, p, p, p, None) == -1   # kind 5 does not exist
+    assert b"kind" in L.oi_last_error()
+    assert L.oi_augment_geom_setup_ops(ops, 9, 4, 64, 64, 12, p, p, p, None) == -1   # > OI_AUGMENT_MAX_OPS
+    ops[1].kind = 0                                                                  # scale2d needs p1
+    assert L.oi_augment_geom_setup_ops(ops, 2, 4, 64, 64, 12, p, p, p, None) == -1
+    raw = (_lib.OiAugmentRawOp * 1)()
+    raw[0].form, raw[0].draw, raw[0].gate = 7, C.cast(p, _lib.f32p), C.cast(p, _lib.f32p)
+    assert L.oi_augment_geom_setup_raw(raw, 1, p, 4, 64, 64, 12, p, p, p, None) == -1   # form 7 does not exist
+    assert b"form" in L.oi_last_error()
+    raw[0].form, raw[0].gate = _lib.AUG_SCALE, None
+    assert L.oi_augment_geom_setup_raw(raw, 1, p, 4, 64, 64, 12, p, p, p, None) == -1   # NULL gate draw
+    raw[0].gate = C.cast(p, _lib.f32p)
+    assert L.oi_augment_geom_setup_raw(raw, 1, None, 4, 64, 64, 12, p, p, p, None) == -1  # NULL p
+    assert L.oi_augment_geom_setup_raw(raw, 0, p, 4, 64, 64, 12, p, p, p, None) == -1
