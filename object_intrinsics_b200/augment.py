@@ -329,5 +329,6 @@ class AugmentPipe(torch.nn.Module):
         raw = self.sample_raw(B, images.device)
         if not raw:
             return images
-        theta, margins, _ = geometric_setup_raw_cuda(raw, self.p, B, H, W, len(self._taps), images.device)
+        p = self.p.detach().to(device=images.device, dtype=torch.float32)     # no-op when the module lives with the images
+        theta, margins, _ = geometric_setup_raw_cuda(raw, p, B, H, W, len(self._taps), images.device)
         return _GeomForward.apply(images, theta, margins, self._taps)
